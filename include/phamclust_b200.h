@@ -1,0 +1,195 @@
+/*
+ * phamclust_b200.h -- C ABI of libphamclust_b200.so (sm_100a only).
+ *
+ * The reference (chg60/phamclust, pure Python) has no FFI; its boundary for
+ * this path is one Python call,
+ *
+ *     matrix_de_novo(genomes, func, cpus, as_distance=True)
+ *                                  /root/reference/src/phamclust/matrix.py:432
+ *
+ * with func one of the six metric functions of metrics.py (:26 gcs, :56 jc,
+ * :83 pocp, :118 af, :178 aai, :235 peq).  This header declares exactly what a
+ * ctypes/cffi stub for that call binds: load the packed
+ * genome x pham table and the protein arena once, ask for a metric, get back
+ * the upper triangle in 6-decimal micro-units.
+ *
+ * Conventions
+ *  - every entry point returns 0 on success, a PC_E* code otherwise; the
+ *    message is available from pc_last_error().  No exceptions cross the ABI.
+ *  - plain pointers and sizes only.  "host" pointers are ordinary (pinned or
+ *    pageable) host memory owned by the caller for the duration of the call;
+ *    "dev" pointers are device memory on the ctx's GPU owned by the caller.
+ *    The library owns whatever it allocates inside pc_ctx and never hands
+ *    library-allocated memory out.
+ *  - there is NO CPU fallback: pc_init fails without a usable sm_100 GPU.
+ *  - one pc_ctx per process per GPU; calls on one ctx must be serialised by
+ *    the caller.
+ *
+ * Packed upper triangle: entry (i, j), i <= j, of an N x N symmetric matrix
+ * sits at  idx(i, j) = i*N - i*(i-1)/2 + (j - i)  (row-major, diagonal
+ * included); rows [r0, r1) therefore form one contiguous slice.
+ */
+#ifndef PHAMCLUST_B200_H
+#define PHAMCLUST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pc_ctx pc_ctx;
+
+/* error codes */
+enum {
+    PC_OK = 0,
+    PC_EINVAL = 1,      /* bad argument / malformed table  -> ValueError   */
+    PC_ECUDA = 2,       /* CUDA runtime failure            -> RuntimeError */
+    PC_ENOGPU = 3,      /* no sm_100 device                -> RuntimeError */
+    PC_ESTATE = 4,      /* call order (e.g. aai before pc_load_sequences)  */
+    PC_ENOMEM = 5
+};
+
+/* metric ids, in the order of cli.METRICS (/root/reference/src/phamclust/cli.py:30-35) */
+enum {
+    PC_GCS = 0,         /* gene_content_similarity          metrics.py:26  */
+    PC_JC = 1,          /* jaccard_coefficient              metrics.py:56  */
+    PC_POCP = 2,        /* percentage_of_conserved_proteins metrics.py:83  */
+    PC_AF = 3,          /* alignment_fraction               metrics.py:118 */
+    PC_AAI = 4,         /* average_aminoacid_identity       metrics.py:178 */
+    PC_PEQ = 5          /* proteomic_equivalence_quotient   metrics.py:235 */
+};
+
+/* contraction engines for the shared-pham count products (gcs/jc/pocp/af) */
+enum {
+    PC_ENGINE_AUTO = 0,
+    PC_ENGINE_POPC = 1, /* bit-packed AND + POPC tile kernel                */
+    PC_ENGINE_I8MMA = 2 /* int8 tcgen05.mma (TMA -> smem -> TMEM) GEMM      */
+};
+
+/* -------- lifetime ------------------------------------------------------ */
+/* Replaces: the joblib worker pool set-up of matrix.py:471-472.            */
+int pc_init(int device_id, pc_ctx **out);
+void pc_destroy(pc_ctx *ctx);
+/* ctx may be NULL: returns the last error of a failed pc_init.             */
+const char *pc_last_error(const pc_ctx *ctx);
+int pc_version(void);
+/* external != 0: run all subsequent work of this ctx on the caller's CUDA
+ * stream (e.g. torch.cuda.current_stream().cuda_stream; the handle 0 is the
+ * legacy default stream); external == 0 restores the ctx's own stream.      */
+int pc_set_stream(pc_ctx *ctx, void *cuda_stream, int external);
+int pc_set_engine(pc_ctx *ctx, int engine);
+int pc_sync(pc_ctx *ctx);
+
+/* -------- inputs -------------------------------------------------------- */
+/*
+ * The genome x pham table in CSR form; replaces the list[Genome] argument of
+ * matrix_de_novo (matrix.py:432) / Genome.phams (genome.py:30).  Row g of the
+ * CSR is genome g IN CALLER ORDER (orientation source < target follows that
+ * order, matrix.py:480-486).  Entry e carries: pham_id[e] in [0, n_phams);
+ * copies[e] = len(genome[pham]) >= 1 (genome.py:45-48); len_sum[e] = summed
+ * translation length of those copies (metrics.py:136-147).  pham ids must be
+ * unique within a row; all pointers are host memory.
+ */
+int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
+                  const int64_t *genome_ptr /* n_genomes+1 */,
+                  const int32_t *pham_id /* nnz */,
+                  const uint32_t *copies /* nnz */,
+                  const uint32_t *len_sum /* nnz */);
+
+/*
+ * The translations; replaces the list[str] values of Genome.phams consumed by
+ * metrics.py:203-221.  Genes are laid out in CSR entry order: entry e owns
+ * genes [first(e), first(e)+copies[e]) with first = exclusive cumsum(copies),
+ * paralogs in the order they were added (genome.py:45-48; the order decides
+ * the "last maximum wins" tie of metrics.py:223).  residues are the raw
+ * characters (one byte each, as in the TSV/FASTA); seq_off has n_genes+1
+ * entries.  Needs pc_load_table first.  Host memory.
+ */
+int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
+                      const uint8_t *residues);
+
+/* -------- the path ------------------------------------------------------ */
+/*
+ * matrix_de_novo (matrix.py:432-497) for the whole table: writes
+ * N(N+1)/2 int32 micro-units, value = round(weight, 6) * 1e6 exactly as
+ * metrics.py:50-53 + matrix.py:323 produce it; diagonal = 1 - as_distance
+ * (matrix.py:467-468).  ppos is metrics.py:178's flag (aai only, else 0).
+ * out is host memory unless out_on_device != 0.
+ */
+int pc_matrix(pc_ctx *ctx, int metric, int as_distance, int ppos,
+              int32_t *out_micro_upper, int out_on_device);
+
+/*
+ * The same for genome rows [row_begin, row_end) only (a contiguous slice of
+ * the packed triangle) -- the unit of multi-GPU sharding.  For PC_AAI/PC_PEQ
+ * acc_dev must hold the (all-reduced) accumulators filled by
+ * pc_align_accumulate; it is ignored for the other metrics.
+ */
+int pc_matrix_rows(pc_ctx *ctx, int metric, int as_distance, int ppos,
+                   int64_t row_begin, int64_t row_end,
+                   const uint64_t *acc_dev, int32_t *out, int out_on_device);
+
+/*
+ * Stage 1+2 of aai/peq (metrics.py:203-225): align every within-pham member
+ * pair owned by partition `part` of `n_parts` (phams are dealt round-robin in
+ * descending-cost order) and add each anchor gene's best match into
+ * acc_dev[idx(i,j)] as  (sum matched columns << 32) | sum alignment length.
+ * acc_dev is device memory of N(N+1)/2 uint64, zeroed by the caller; sums of
+ * partitions (ncclAllReduce, integer, order independent) give the full
+ * accumulators.
+ */
+int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
+                        uint64_t *acc_dev);
+
+/* -------- integer test hooks (bit-exact parity) ------------------------- */
+/*
+ * Numerators the reference computes as Python ints, packed triangle, host:
+ *  PC_GCS/PC_JC: len(source & target)            genome.py:124-135
+ *  PC_POCP:      s_conserved + t_conserved       metrics.py:102-104
+ *  PC_AF:        s_conserved + t_conserved (aa)  metrics.py:135-149
+ *  PC_AAI:       out_num = sum matched columns, out_aux = sum aln length
+ * out_aux may be NULL unless metric == PC_AAI.
+ */
+int pc_numerators(pc_ctx *ctx, int metric, int ppos, int32_t *out_num,
+                  int32_t *out_aux);
+
+/*
+ * _align (metrics.py:160-175) + the counts of :216-220 for caller-chosen
+ * ordered gene pairs: out[4*t..] = identical '|' columns, similar '+'
+ * columns, len(traceback.query), alignment score.  Host memory.
+ */
+int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks,
+                            const int32_t *query_gene, const int32_t *ref_gene,
+                            int32_t *out /* n_tasks * 4 */);
+
+/*
+ * The device's round(x, 6) (metrics.py:50-53, matrix.py:323) applied to n
+ * host doubles -> int32 micro-units; lets the tests pin the epilogue's
+ * rounding against CPython's round() on the GPU itself.
+ */
+int pc_debug_round6(pc_ctx *ctx, int64_t n, const double *x, int32_t *out);
+
+/* -------- measurement --------------------------------------------------- */
+enum {
+    PC_T_H2D = 0,       /* host -> device copies                            */
+    PC_T_PACK = 1,      /* operand packing kernels                          */
+    PC_T_CONTRACT = 2,  /* shared-count contraction (+ fused epilogue)      */
+    PC_T_ALIGN = 3,     /* global-alignment DP kernels                      */
+    PC_T_GATHER = 4,    /* best-match gather into pair accumulators         */
+    PC_T_EPILOGUE = 5,  /* standalone normalise/round kernels               */
+    PC_T_D2H = 6,       /* device -> host copy of the result                */
+    PC_T_COUNT = 7
+};
+/* CUDA-event milliseconds per stage accumulated since pc_reset_counters.   */
+int pc_timings(pc_ctx *ctx, double *ms, int n);
+/* kernels launched / DP cells updated / alignments run since the reset.    */
+int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
+                int64_t *alignments, int64_t *contract_launches,
+                int64_t *align_launches);
+int pc_reset_counters(pc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHAMCLUST_B200_H */

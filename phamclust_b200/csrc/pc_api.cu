@@ -1,0 +1,979 @@
+// pc_api.cu -- the C ABI of libphamclust_b200 (include/phamclust_b200.h):
+// context, input loading, host-side planning and the per-metric flows that
+// stand in for matrix_de_novo (/root/reference/src/phamclust/matrix.py:432-497).
+#include <algorithm>
+#include <cctype>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "pc_common.cuh"
+
+int pc_nw_multichunk_warps(pc_ctx *ctx);
+
+static thread_local std::string g_init_error;
+
+int pc_fail(pc_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_init_error = buf;
+    return code;
+}
+
+int devbuf_reserve(pc_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return PC_OK;
+    if (b.p) {
+        // buffers may still be in use by queued work on the ctx stream
+        PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        cudaGetLastError();
+        return pc_fail(ctx, PC_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes,
+                       cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+    return PC_OK;
+}
+
+void devbuf_free(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---------------------------------------------------------------------------
+// stage timers
+// ---------------------------------------------------------------------------
+static int take_event(pc_ctx *ctx, cudaEvent_t *ev)
+{
+    if (!ctx->event_pool.empty()) {
+        *ev = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return PC_OK;
+    }
+    PC_CUDA(ctx, cudaEventCreate(ev));
+    return PC_OK;
+}
+
+int pc_stage_begin(pc_ctx *ctx, int stage)
+{
+    StageTimer t;
+    t.stage = stage;
+    PC_TRY(take_event(ctx, &t.start));
+    PC_TRY(take_event(ctx, &t.stop));
+    PC_CUDA(ctx, cudaEventRecord(t.start, ctx->stream));
+    ctx->timers.push_back(t);
+    return PC_OK;
+}
+
+int pc_stage_end(pc_ctx *ctx)
+{
+    PC_CUDA(ctx, cudaEventRecord(ctx->timers.back().stop, ctx->stream));
+    return PC_OK;
+}
+
+int pc_collect_timers(pc_ctx *ctx)
+{
+    if (ctx->timers.empty()) return PC_OK;
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &t : ctx->timers) {
+        float ms = 0.f;
+        PC_CUDA(ctx, cudaEventElapsedTime(&ms, t.start, t.stop));
+        ctx->stage_ms[t.stage] += ms;
+        ctx->event_pool.push_back(t.start);
+        ctx->event_pool.push_back(t.stop);
+    }
+    ctx->timers.clear();
+    return PC_OK;
+}
+
+// keep the number of pending events bounded on long runs
+static int maybe_collect(pc_ctx *ctx)
+{
+    if (ctx->timers.size() > 512) return pc_collect_timers(ctx);
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------
+extern "C" int pc_version(void) { return 100; }
+
+extern "C" const char *pc_last_error(const pc_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+extern "C" int pc_init(int device_id, pc_ctx **out)
+{
+    if (!out) return pc_fail(nullptr, PC_EINVAL, "pc_init: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return pc_fail(nullptr, PC_ENOGPU,
+                       "no CUDA device (%s); libphamclust_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device_id < 0 || device_id >= n_dev)
+        return pc_fail(nullptr, PC_EINVAL, "device %d out of range [0,%d)", device_id, n_dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess)
+        return pc_fail(nullptr, PC_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return pc_fail(nullptr, PC_ENOGPU,
+                       "device %d (%s) is sm_%d%d; this library is built for sm_100a only",
+                       device_id, prop.name, prop.major, prop.minor);
+    if (cudaSetDevice(device_id) != cudaSuccess)
+        return pc_fail(nullptr, PC_ECUDA, "cudaSetDevice(%d) failed", device_id);
+    pc_ctx *ctx = new pc_ctx();
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return pc_fail(nullptr, PC_ECUDA, "cudaStreamCreate failed");
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return PC_OK;
+}
+
+static void free_plan(AlignPlan &p)
+{
+    devbuf_free(p.ph_mem_off); devbuf_free(p.ph_unit_off); devbuf_free(p.ph_task_off);
+    devbuf_free(p.mem_genome); devbuf_free(p.mem_first_gene); devbuf_free(p.mem_copies);
+    devbuf_free(p.mem_cprefix); devbuf_free(p.mem_rowoff);
+    p.part = p.n_parts = -1;
+}
+
+extern "C" void pc_destroy(pc_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_copies, &ctx->d_len_sum,
+                      &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
+                      &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_codes,
+                      &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_subtab[0],
+                      &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
+                      &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
+                      &ctx->d_acc, &ctx->d_out};
+    for (DevBuf *b : bufs) devbuf_free(*b);
+    free_plan(ctx->plan);
+    for (auto &t : ctx->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+    for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+#define PC_ENTER(ctx)                                                          \
+    do {                                                                       \
+        if (!(ctx)) return PC_EINVAL;                                          \
+        PC_CUDA((ctx), cudaSetDevice((ctx)->device));                          \
+    } while (0)
+
+extern "C" int pc_set_stream(pc_ctx *ctx, void *cuda_stream, int external)
+{
+    PC_ENTER(ctx);
+    PC_TRY(pc_collect_timers(ctx));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = external ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PC_OK;
+}
+
+extern "C" int pc_set_engine(pc_ctx *ctx, int engine)
+{
+    PC_ENTER(ctx);
+    if (engine < PC_ENGINE_AUTO || engine > PC_ENGINE_I8MMA)
+        return pc_fail(ctx, PC_EINVAL, "unknown engine %d", engine);
+    ctx->engine = engine;
+    return PC_OK;
+}
+
+extern "C" int pc_sync(pc_ctx *ctx)
+{
+    PC_ENTER(ctx);
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PC_OK;
+}
+
+template <typename T>
+static int upload(pc_ctx *ctx, DevBuf &b, const T *src, size_t count)
+{
+    PC_TRY(devbuf_reserve(ctx, b, count * sizeof(T)));
+    if (count)
+        PC_CUDA(ctx, cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pc_load_table
+// ---------------------------------------------------------------------------
+extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
+                             const int64_t *genome_ptr, const int32_t *pham_id,
+                             const uint32_t *copies, const uint32_t *len_sum)
+{
+    PC_ENTER(ctx);
+    if (n_genomes <= 0)   // matrix.py:451-452
+        return pc_fail(ctx, PC_EINVAL, "need at least 1 genome to construct matrix de novo");
+    if (n_phams < 0 || !genome_ptr)
+        return pc_fail(ctx, PC_EINVAL, "pc_load_table: bad arguments");
+    if (n_genomes > 2000000)
+        return pc_fail(ctx, PC_EINVAL, "too many genomes (%lld)", (long long)n_genomes);
+    if (genome_ptr[0] != 0) return pc_fail(ctx, PC_EINVAL, "genome_ptr[0] must be 0");
+    const int64_t nnz = genome_ptr[n_genomes];
+    if (nnz < 0 || (nnz > 0 && (!pham_id || !copies || !len_sum)))
+        return pc_fail(ctx, PC_EINVAL, "pc_load_table: missing entry arrays");
+
+    // validate + derive per-genome denominators
+    std::vector<int32_t> den_phams(n_genomes), den_genes(n_genomes), den_len(n_genomes);
+    std::vector<int32_t> entry_genome(nnz);
+    std::vector<int64_t> entry_first_gene(nnz + 1);
+    std::vector<int64_t> seen(n_phams, -1);
+    std::vector<int64_t> pham_count(n_phams + 1, 0);
+    uint32_t max_copies = 0, max_len = 0;
+    int64_t gene_cursor = 0;
+    for (int64_t g = 0; g < n_genomes; ++g) {
+        const int64_t b = genome_ptr[g], e = genome_ptr[g + 1];
+        if (e < b || e > nnz) return pc_fail(ctx, PC_EINVAL, "genome_ptr is not monotone at %lld", (long long)g);
+        int64_t genes = 0, len = 0;
+        for (int64_t k = b; k < e; ++k) {
+            const int32_t p = pham_id[k];
+            if (p < 0 || p >= n_phams)
+                return pc_fail(ctx, PC_EINVAL, "pham id %d out of range at entry %lld", p, (long long)k);
+            if (seen[p] == g)
+                return pc_fail(ctx, PC_EINVAL, "pham %d listed twice for genome %lld", p, (long long)g);
+            seen[p] = g;
+            if (copies[k] == 0)
+                return pc_fail(ctx, PC_EINVAL, "entry %lld has 0 copies", (long long)k);
+            entry_genome[k] = (int32_t)g;
+            entry_first_gene[k] = gene_cursor;
+            gene_cursor += copies[k];
+            genes += copies[k];
+            len += len_sum[k];
+            max_copies = std::max(max_copies, copies[k]);
+            max_len = std::max(max_len, len_sum[k]);
+            pham_count[p + 1]++;
+        }
+        if (genes > (1 << 30) || len > (1 << 30))
+            return pc_fail(ctx, PC_EINVAL, "genome %lld too large for int32 numerators", (long long)g);
+        den_phams[g] = (int32_t)(e - b);
+        den_genes[g] = (int32_t)genes;
+        den_len[g] = (int32_t)len;
+    }
+    entry_first_gene[nnz] = gene_cursor;
+    if (gene_cursor >= (1ll << 31))
+        return pc_fail(ctx, PC_EINVAL, "too many genes (%lld)", (long long)gene_cursor);
+
+    // CSC by stable counting sort: members of a pham in ascending genome order
+    for (int64_t p = 0; p < n_phams; ++p) pham_count[p + 1] += pham_count[p];
+    std::vector<int64_t> members(nnz);
+    {
+        std::vector<int64_t> cursor(pham_count.begin(), pham_count.end() - 1);
+        for (int64_t k = 0; k < nnz; ++k) members[cursor[pham_id[k]]++] = k;
+    }
+
+    ctx->N = n_genomes; ctx->P = n_phams; ctx->nnz = nnz;
+    ctx->h_genome_ptr.assign(genome_ptr, genome_ptr + n_genomes + 1);
+    ctx->h_pham_id.assign(pham_id, pham_id + nnz);
+    ctx->h_copies.assign(copies, copies + nnz);
+    ctx->h_len_sum.assign(len_sum, len_sum + nnz);
+    ctx->h_entry_genome.swap(entry_genome);
+    ctx->h_entry_first_gene.swap(entry_first_gene);
+    ctx->h_pham_ptr.swap(pham_count);
+    ctx->h_pham_members.swap(members);
+    ctx->max_copies = max_copies; ctx->max_len_sum = max_len;
+    ctx->n_genes_total = gene_cursor;
+    ctx->have_seqs = false;
+    ctx->planes_kind = -1; ctx->i8_kind = -1;
+    ctx->plan.part = ctx->plan.n_parts = -1;
+    const int64_t words = (n_phams + 31) / 32;
+    ctx->W = std::max<int64_t>(32, (words + 31) / 32 * 32);
+
+    PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+    PC_TRY(upload(ctx, ctx->d_entry_genome, ctx->h_entry_genome.data(), nnz));
+    PC_TRY(upload(ctx, ctx->d_pham_id, ctx->h_pham_id.data(), nnz));
+    PC_TRY(upload(ctx, ctx->d_copies, ctx->h_copies.data(), nnz));
+    PC_TRY(upload(ctx, ctx->d_len_sum, ctx->h_len_sum.data(), nnz));
+    PC_TRY(upload(ctx, ctx->d_den_phams, den_phams.data(), n_genomes));
+    PC_TRY(upload(ctx, ctx->d_den_genes, den_genes.data(), n_genomes));
+    PC_TRY(upload(ctx, ctx->d_den_len, den_len.data(), n_genomes));
+    PC_TRY(pc_stage_end(ctx));
+    // den_* are stack-owned vectors: the copies above must finish before return
+    PC_TRY(devbuf_reserve(ctx, ctx->d_bits, (size_t)n_genomes * ctx->W * sizeof(uint32_t)));
+    PC_TRY(pc_stage_begin(ctx, PC_T_PACK));
+    PC_TRY(pc_launch_pack_bits(ctx, 0, 0, ctx->d_bits.as<uint32_t>()));
+    PC_TRY(pc_stage_end(ctx));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_table = true;
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pc_load_sequences
+// ---------------------------------------------------------------------------
+static void build_subtab(const pc_ctx *ctx, int ppos, std::vector<int2> &tab)
+{
+    tab.assign(32 * 32, make_int2(-4, 1));
+    for (int a = 0; a < 32; ++a)
+        for (int b = 0; b < 32; ++b) {
+            const int ia = a < ctx->n_codes ? ctx->code_matrix_index[a] : 23;
+            const int ib = b < ctx->n_codes ? ctx->code_matrix_index[b] : 23;
+            const int s = PC_BLOSUM62[ia][ib];
+            // '|' when the characters match, '+' when the score is positive
+            // (Appendix A traceback); codes are per distinct (case-folded) character
+            const bool hit = (a == b) || (ppos && s > 0);
+            tab[a * 32 + b] = make_int2(s, 1 + (hit ? (1 << 16) : 0));
+        }
+}
+
+extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
+                                 const uint8_t *residues)
+{
+    PC_ENTER(ctx);
+    if (!ctx->have_table) return pc_fail(ctx, PC_ESTATE, "pc_load_sequences needs pc_load_table first");
+    if (n_genes != ctx->n_genes_total)
+        return pc_fail(ctx, PC_EINVAL, "got %lld genes but the table's copies sum to %lld",
+                       (long long)n_genes, (long long)ctx->n_genes_total);
+    if (!seq_off || seq_off[0] != 0) return pc_fail(ctx, PC_EINVAL, "seq_off[0] must be 0");
+    const int64_t total = seq_off[n_genes];
+    if (total > 0 && !residues) return pc_fail(ctx, PC_EINVAL, "residues is NULL");
+
+    std::vector<int32_t> gene_len(n_genes);
+    std::vector<int64_t> gene_off(n_genes + 1);
+    int64_t cursor = 0;
+    for (int64_t g = 0; g < n_genes; ++g) {
+        const int64_t len = seq_off[g + 1] - seq_off[g];
+        if (len < 0) return pc_fail(ctx, PC_EINVAL, "seq_off is not monotone at gene %lld", (long long)g);
+        if (len > 32767)
+            return pc_fail(ctx, PC_EINVAL,
+                           "gene %lld has %lld residues; the alignment counters hold at most 32767 "
+                           "(parasail's 16-bit scores are undefined there anyway)",
+                           (long long)g, (long long)len);
+        gene_len[g] = (int32_t)len;
+        gene_off[g] = cursor;
+        cursor += (len + 15) / 16 * 16;
+    }
+    gene_off[n_genes] = cursor;
+    // the table's len_sum must describe these genes (metrics.py:136-147 sums them)
+    for (int64_t e = 0; e < ctx->nnz; ++e) {
+        int64_t s = 0;
+        for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g)
+            s += gene_len[g];
+        if (s != (int64_t)ctx->h_len_sum[e])
+            return pc_fail(ctx, PC_EINVAL, "len_sum[%lld]=%u but its genes sum to %lld",
+                           (long long)e, ctx->h_len_sum[e], (long long)s);
+    }
+
+    // residue codes: one per distinct character after case folding (U5); the
+    // 24 matrix letters keep their matrix index, anything else maps to '*' (U6)
+    bool present[256] = {false};
+    for (int64_t k = 0; k < total; ++k) present[residues[k]] = true;
+    for (int c = 0; c < 256; ++c) ctx->code_of_byte[c] = -1;
+    ctx->n_codes = 24;
+    for (int k = 0; k < 24; ++k) {
+        ctx->code_matrix_index[k] = k;
+        ctx->code_of_byte[(unsigned char)PC_ALPHABET[k]] = k;
+#if !PC_CASE_SENSITIVE
+        ctx->code_of_byte[(unsigned char)tolower((unsigned char)PC_ALPHABET[k])] = k;
+#endif
+    }
+    for (int c = 0; c < 256; ++c) {
+        if (!present[c] || ctx->code_of_byte[c] >= 0) continue;
+#if !PC_CASE_SENSITIVE
+        const int folded = toupper(c);
+        if (folded != c && ctx->code_of_byte[folded] >= 0 && folded < 256) {
+            ctx->code_of_byte[c] = ctx->code_of_byte[folded];
+            continue;
+        }
+#else
+        const int folded = c;
+#endif
+        if (ctx->n_codes >= 32)
+            return pc_fail(ctx, PC_EINVAL,
+                           "more than 32 distinct residue symbols in the input (byte 0x%02x)", c);
+        int midx = 23;
+        const char *pos = strchr(PC_ALPHABET, toupper(c));
+        if (pos && toupper(c) != 0) midx = (int)(pos - PC_ALPHABET);
+        ctx->code_matrix_index[ctx->n_codes] = midx;
+        ctx->code_of_byte[c] = ctx->n_codes;
+        if (folded >= 0 && folded < 256 && ctx->code_of_byte[folded] < 0)
+            ctx->code_of_byte[folded] = ctx->n_codes;
+        ctx->n_codes++;
+    }
+    uint8_t lut[256];
+    for (int c = 0; c < 256; ++c) lut[c] = (uint8_t)(ctx->code_of_byte[c] < 0 ? 23 : ctx->code_of_byte[c]);
+
+    ctx->n_genes = n_genes;
+    ctx->h_gene_len.swap(gene_len);
+
+    DevBuf d_raw_off, d_lut;
+    int rc = PC_OK;
+    do {
+        if ((rc = pc_stage_begin(ctx, PC_T_H2D))) break;
+        if ((rc = upload(ctx, ctx->d_raw, residues, (size_t)total))) break;
+        if ((rc = upload(ctx, d_raw_off, seq_off, (size_t)n_genes + 1))) break;
+        if ((rc = upload(ctx, ctx->d_gene_off, gene_off.data(), (size_t)n_genes + 1))) break;
+        if ((rc = upload(ctx, ctx->d_gene_len, ctx->h_gene_len.data(), (size_t)n_genes))) break;
+        if ((rc = upload(ctx, d_lut, lut, 256))) break;
+        for (int ppos = 0; ppos < 2 && rc == PC_OK; ++ppos) {
+            std::vector<int2> tab;
+            build_subtab(ctx, ppos, tab);
+            rc = upload(ctx, ctx->d_subtab[ppos], tab.data(), tab.size());
+            if (rc == PC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                rc = pc_fail(ctx, PC_ECUDA, "sync failed while uploading the substitution table");
+        }
+        if (rc) break;
+        if ((rc = pc_stage_end(ctx))) break;
+        // + tail padding: lanes read whole K-column words past the last gene
+        if ((rc = devbuf_reserve(ctx, ctx->d_codes, (size_t)cursor + 1024))) break;
+        if (cudaMemsetAsync(ctx->d_codes.p, 0, (size_t)cursor + 1024, ctx->stream) != cudaSuccess) {
+            rc = pc_fail(ctx, PC_ECUDA, "memset of the code arena failed");
+            break;
+        }
+        if ((rc = pc_stage_begin(ctx, PC_T_PACK))) break;
+        if ((rc = pc_launch_encode(ctx, ctx->d_raw.as<uint8_t>(), d_raw_off.as<int64_t>(),
+                                   ctx->d_gene_off.as<int64_t>(), ctx->d_gene_len.as<int32_t>(),
+                                   d_lut.as<uint8_t>(), n_genes, ctx->d_codes.as<uint8_t>()))) break;
+        if ((rc = pc_stage_end(ctx))) break;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = pc_fail(ctx, PC_ECUDA, "encode kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } while (0);
+    devbuf_free(d_raw_off);
+    devbuf_free(d_lut);
+    if (rc) return rc;
+    ctx->plan.part = ctx->plan.n_parts = -1;
+    ctx->have_seqs = true;
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// contraction operands
+// ---------------------------------------------------------------------------
+static int bit_length(uint32_t v)
+{
+    int n = 0;
+    while (v) { ++n; v >>= 1; }
+    return n;
+}
+
+// Build the term list of `metric` on the device (packing weight planes on demand).
+static int prepare_terms(pc_ctx *ctx, int metric, int *n_terms_out)
+{
+    std::vector<PopcTerm> terms;
+    const uint32_t *bits = ctx->d_bits.as<uint32_t>();
+    if (metric == PC_GCS || metric == PC_JC) {
+        terms.push_back({bits, bits, 1});
+    } else {
+        const int kind = metric == PC_POCP ? 1 : 2;
+        const int planes = bit_length(kind == 1 ? ctx->max_copies : ctx->max_len_sum);
+        const size_t plane_words = (size_t)ctx->N * ctx->W;
+        if (ctx->planes_kind != kind) {
+            PC_TRY(devbuf_reserve(ctx, ctx->d_planes, plane_words * sizeof(uint32_t) * std::max(planes, 1)));
+            PC_TRY(pc_stage_begin(ctx, PC_T_PACK));
+            for (int b = 0; b < planes; ++b)
+                PC_TRY(pc_launch_pack_bits(ctx, kind, b, ctx->d_planes.as<uint32_t>() + b * plane_words));
+            PC_TRY(pc_stage_end(ctx));
+            ctx->planes_kind = kind;
+            ctx->planes_count = planes;
+        }
+        for (int b = 0; b < planes; ++b) {
+            const uint32_t *pl = ctx->d_planes.as<uint32_t>() + b * plane_words;
+            terms.push_back({pl, bits, 1 << b});   // source's conserved part
+            terms.push_back({bits, pl, 1 << b});   // target's conserved part
+        }
+    }
+    *n_terms_out = (int)terms.size();
+    PC_TRY(devbuf_reserve(ctx, ctx->d_terms, sizeof(PopcTerm) * std::max<size_t>(terms.size(), 1)));
+    if (!terms.empty()) {
+        PC_CUDA(ctx, cudaMemcpyAsync(ctx->d_terms.p, terms.data(), sizeof(PopcTerm) * terms.size(),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `terms` is a local
+    }
+    return PC_OK;
+}
+
+static const int32_t *den_of(pc_ctx *ctx, int metric)
+{
+    switch (metric) {
+    case PC_GCS: case PC_JC: return ctx->d_den_phams.as<int32_t>();
+    case PC_POCP: return ctx->d_den_genes.as<int32_t>();
+    default: return ctx->d_den_len.as<int32_t>();
+    }
+}
+
+// cheap metric for rows [r0, r1) into out_dev (device)
+static int contract_rows(pc_ctx *ctx, int metric, int as_distance, int raw, int64_t r0,
+                         int64_t r1, int32_t *out_dev)
+{
+    EpilogueArgs ep;
+    ep.den = den_of(ctx, metric);
+    ep.metric = metric;
+    ep.as_distance = as_distance;
+    ep.raw = raw;
+    ep.n = ctx->N;
+    ep.row_begin = r0;
+    ep.row_end = r1;
+    ep.out = out_dev;
+    int engine = ctx->engine == PC_ENGINE_AUTO ? PC_ENGINE_POPC : ctx->engine;
+    if (engine == PC_ENGINE_I8MMA) {
+        PC_TRY(pc_i8_contract(ctx, metric, ep));
+        return PC_OK;
+    }
+    int n_terms = 0;
+    PC_TRY(prepare_terms(ctx, metric, &n_terms));
+    PC_TRY(pc_stage_begin(ctx, PC_T_CONTRACT));
+    PC_TRY(pc_launch_popc_contract(ctx, ctx->d_terms.as<PopcTerm>(), n_terms, ep));
+    PC_TRY(pc_stage_end(ctx));
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// alignment planning (host) -- which member pairs exist, in which order
+// ---------------------------------------------------------------------------
+static int build_plan(pc_ctx *ctx, int part, int n_parts)
+{
+    AlignPlan &pl = ctx->plan;
+    if (pl.part == part && pl.n_parts == n_parts) return PC_OK;
+    struct PhamInfo { int64_t pham; int bucket; double cost; };
+    std::vector<PhamInfo> infos;
+    for (int64_t p = 0; p < ctx->P; ++p) {
+        const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
+        if (e - b < 2) continue;              // cannot be shared by two genomes
+        int max_len = 0;
+        double tot = 0;
+        for (int64_t k = b; k < e; ++k) {
+            const int64_t ent = ctx->h_pham_members[k];
+            for (int64_t g = ctx->h_entry_first_gene[ent]; g < ctx->h_entry_first_gene[ent + 1]; ++g) {
+                max_len = std::max(max_len, ctx->h_gene_len[g]);
+                tot += ctx->h_gene_len[g];
+            }
+        }
+        infos.push_back({p, pc_nw_bucket_of(max_len), tot * tot});
+    }
+    // descending bucket (long first), then descending cost; deal round-robin
+    std::sort(infos.begin(), infos.end(), [](const PhamInfo &x, const PhamInfo &y) {
+        if (x.bucket != y.bucket) return x.bucket > y.bucket;
+        if (x.cost != y.cost) return x.cost > y.cost;
+        return x.pham < y.pham;
+    });
+    std::vector<int64_t> ph_mem_off{0}, ph_unit_off{0}, ph_task_off{0};
+    std::vector<int32_t> mem_genome, mem_first_gene, mem_copies, mem_cprefix;
+    std::vector<int64_t> mem_rowoff;
+    std::vector<int64_t> bucket_tasks(PC_NW_BUCKETS, 0);
+    int32_t max_q_multi = 0;
+    for (size_t pos = 0; pos < infos.size(); ++pos) {
+        if ((int)(pos % (size_t)n_parts) != part) continue;
+        const int64_t p = infos[pos].pham;
+        const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
+        const int64_t m = e - b;
+        int64_t total_copies = 0;
+        for (int64_t k = b; k < e; ++k) total_copies += ctx->h_copies[ctx->h_pham_members[k]];
+        int64_t cprefix = 0, rowoff = 0;
+        for (int64_t k = b; k < e; ++k) {
+            const int64_t ent = ctx->h_pham_members[k];
+            const int64_t c = ctx->h_copies[ent];
+            mem_genome.push_back(ctx->h_entry_genome[ent]);
+            mem_first_gene.push_back((int32_t)ctx->h_entry_first_gene[ent]);
+            mem_copies.push_back((int32_t)c);
+            mem_cprefix.push_back((int32_t)cprefix);
+            mem_rowoff.push_back(rowoff);
+            cprefix += c;
+            rowoff += c * (total_copies - cprefix);   // row a pairs with every later member
+            if (infos[pos].bucket == PC_NW_BUCKETS - 1)
+                for (int64_t g = ctx->h_entry_first_gene[ent]; g < ctx->h_entry_first_gene[ent + 1]; ++g)
+                    max_q_multi = std::max(max_q_multi, ctx->h_gene_len[g]);
+        }
+        ph_mem_off.push_back(ph_mem_off.back() + m);
+        ph_unit_off.push_back(ph_unit_off.back() + m * (m - 1) / 2);
+        ph_task_off.push_back(ph_task_off.back() + rowoff);
+        bucket_tasks[infos[pos].bucket] += rowoff;
+    }
+    pl.n_ph = (int64_t)ph_mem_off.size() - 1;
+    pl.n_units = ph_unit_off.back();
+    pl.n_tasks = ph_task_off.back();
+    pl.n_mem = (int64_t)mem_genome.size();
+    pl.max_qlen_multichunk = max_q_multi;
+    // launch order = storage order: buckets from the largest down
+    pl.bucket_task_off.assign(PC_NW_BUCKETS, 0);
+    pl.bucket_task_count = bucket_tasks;
+    {
+        int64_t off = 0;
+        for (int b = PC_NW_BUCKETS - 1; b >= 0; --b) {
+            pl.bucket_task_off[b] = off;         // start of bucket b
+            off += bucket_tasks[b];
+        }
+    }
+    PC_TRY(upload(ctx, pl.ph_mem_off, ph_mem_off.data(), ph_mem_off.size()));
+    PC_TRY(upload(ctx, pl.ph_unit_off, ph_unit_off.data(), ph_unit_off.size()));
+    PC_TRY(upload(ctx, pl.ph_task_off, ph_task_off.data(), ph_task_off.size()));
+    PC_TRY(upload(ctx, pl.mem_genome, mem_genome.data(), mem_genome.size()));
+    PC_TRY(upload(ctx, pl.mem_first_gene, mem_first_gene.data(), mem_first_gene.size()));
+    PC_TRY(upload(ctx, pl.mem_copies, mem_copies.data(), mem_copies.size()));
+    PC_TRY(upload(ctx, pl.mem_cprefix, mem_cprefix.data(), mem_cprefix.size()));
+    PC_TRY(upload(ctx, pl.mem_rowoff, mem_rowoff.data(), mem_rowoff.size()));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // sources are locals
+    pl.part = part;
+    pl.n_parts = n_parts;
+    return PC_OK;
+}
+
+static void fill_nw_common(pc_ctx *ctx, NwArgs &a, int ppos)
+{
+    a.codes = ctx->d_codes.as<uint8_t>();
+    a.gene_off = ctx->d_gene_off.as<int64_t>();
+    a.gene_len = ctx->d_gene_len.as<int32_t>();
+    a.subtab = ctx->d_subtab[ppos ? 1 : 0].as<int2>();
+    a.gap_open = PC_GAP_OPEN_DEFAULT;
+    a.gap_extend = PC_GAP_EXTEND_DEFAULT;
+    a.cell_counter = ctx->d_counters.as<unsigned long long>() + PC_NW_BUCKETS;
+}
+
+// counters layout: [0..PC_NW_BUCKETS) work counters, [PC_NW_BUCKETS] cumulative cells
+static int ensure_counters(pc_ctx *ctx)
+{
+    if (!ctx->d_counters.p) {
+        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_BUCKETS + 1)));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_BUCKETS + 1), ctx->stream));
+    }
+    return PC_OK;
+}
+
+static int ensure_spill(pc_ctx *ctx, int max_qlen, NwArgs &a)
+{
+    a.spill_stride = (int64_t)max_qlen + 2;
+    const int64_t warps = pc_nw_multichunk_warps(ctx);
+    PC_TRY(devbuf_reserve(ctx, ctx->d_spill, (size_t)warps * a.spill_stride * sizeof(int4)));
+    a.spill = ctx->d_spill.as<int4>();
+    return PC_OK;
+}
+
+extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
+                                   uint64_t *acc_dev)
+{
+    PC_ENTER(ctx);
+    if (!ctx->have_seqs) return pc_fail(ctx, PC_ESTATE, "aai/peq need pc_load_sequences first");
+    if (n_parts < 1 || part < 0 || part >= n_parts || !acc_dev)
+        return pc_fail(ctx, PC_EINVAL, "pc_align_accumulate: bad partition %d/%d", part, n_parts);
+    PC_TRY(build_plan(ctx, part, n_parts));
+    AlignPlan &pl = ctx->plan;
+    if (pl.n_tasks == 0) return PC_OK;
+    if (pl.n_tasks >= (1ll << 40)) return pc_fail(ctx, PC_EINVAL, "too many alignments");
+    PC_TRY(devbuf_reserve(ctx, ctx->d_task_q, (size_t)pl.n_tasks * sizeof(int32_t)));
+    PC_TRY(devbuf_reserve(ctx, ctx->d_task_r, (size_t)pl.n_tasks * sizeof(int32_t)));
+    PC_TRY(devbuf_reserve(ctx, ctx->d_hitlen, (size_t)pl.n_tasks * sizeof(uint32_t)));
+    PC_TRY(ensure_counters(ctx));
+    PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_BUCKETS, ctx->stream));
+
+    UnitArgs u;
+    u.ph_mem_off = pl.ph_mem_off.as<int64_t>();
+    u.ph_unit_off = pl.ph_unit_off.as<int64_t>();
+    u.ph_task_off = pl.ph_task_off.as<int64_t>();
+    u.n_ph = pl.n_ph;
+    u.n_units = pl.n_units;
+    u.mem_genome = pl.mem_genome.as<int32_t>();
+    u.mem_first_gene = pl.mem_first_gene.as<int32_t>();
+    u.mem_copies = pl.mem_copies.as<int32_t>();
+    u.mem_cprefix = pl.mem_cprefix.as<int32_t>();
+    u.mem_rowoff = pl.mem_rowoff.as<int64_t>();
+    u.n_genomes = ctx->N;
+
+    PC_TRY(pc_stage_begin(ctx, PC_T_GATHER));
+    PC_TRY(pc_launch_expand_units(ctx, u, ctx->d_task_q.as<int32_t>(), ctx->d_task_r.as<int32_t>()));
+    PC_TRY(pc_stage_end(ctx));
+
+    NwArgs a;
+    memset(&a, 0, sizeof a);
+    fill_nw_common(ctx, a, ppos);
+    a.task_q = ctx->d_task_q.as<int32_t>();
+    a.task_r = ctx->d_task_r.as<int32_t>();
+    a.perm = nullptr;
+    a.out_hitlen = ctx->d_hitlen.as<uint32_t>();
+    a.out_score = nullptr;
+    PC_TRY(pc_stage_begin(ctx, PC_T_ALIGN));
+    for (int b = PC_NW_BUCKETS - 1; b >= 0; --b) {
+        const int64_t count = pl.bucket_task_count[b];
+        if (count == 0) continue;
+        a.task_base = pl.bucket_task_off[b];
+        a.n_tasks = count;
+        a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
+        if (b == PC_NW_BUCKETS - 1) PC_TRY(ensure_spill(ctx, pl.max_qlen_multichunk, a));
+        PC_TRY(pc_launch_nw(ctx, a, b));
+    }
+    PC_TRY(pc_stage_end(ctx));
+    ctx->alignments += pl.n_tasks;
+
+    PC_TRY(pc_stage_begin(ctx, PC_T_GATHER));
+    PC_TRY(pc_launch_gather_units(ctx, u, ctx->d_hitlen.as<uint32_t>(),
+                                  reinterpret_cast<unsigned long long *>(acc_dev)));
+    PC_TRY(pc_stage_end(ctx));
+    return maybe_collect(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// pc_matrix_rows / pc_matrix / pc_numerators
+// ---------------------------------------------------------------------------
+static int64_t slice_len(const pc_ctx *ctx, int64_t r0, int64_t r1)
+{
+    return pc_tri_index(ctx->N, r1, r1) - pc_tri_index(ctx->N, r0, r0);
+}
+
+static int check_metric(pc_ctx *ctx, int metric)
+{
+    if (!ctx->have_table) return pc_fail(ctx, PC_ESTATE, "no table loaded (pc_load_table)");
+    if (metric < PC_GCS || metric > PC_PEQ) return pc_fail(ctx, PC_EINVAL, "unknown metric %d", metric);
+    if ((metric == PC_AAI || metric == PC_PEQ) && !ctx->have_seqs)
+        return pc_fail(ctx, PC_ESTATE, "aai/peq need pc_load_sequences first");
+    return PC_OK;
+}
+
+static int download(pc_ctx *ctx, void *host, const void *dev, size_t bytes)
+{
+    PC_TRY(pc_stage_begin(ctx, PC_T_D2H));
+    PC_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PC_TRY(pc_stage_end(ctx));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PC_OK;
+}
+
+extern "C" int pc_matrix_rows(pc_ctx *ctx, int metric, int as_distance, int ppos,
+                              int64_t row_begin, int64_t row_end, const uint64_t *acc_dev,
+                              int32_t *out, int out_on_device)
+{
+    PC_ENTER(ctx);
+    PC_TRY(check_metric(ctx, metric));
+    if (row_begin < 0 || row_end > ctx->N || row_begin > row_end || !out)
+        return pc_fail(ctx, PC_EINVAL, "bad row range [%lld,%lld)", (long long)row_begin, (long long)row_end);
+    if (ppos && metric != PC_AAI) return pc_fail(ctx, PC_EINVAL, "ppos only applies to aai");
+    as_distance = as_distance ? 1 : 0;
+    const int64_t count = slice_len(ctx, row_begin, row_end);
+    if (count == 0) return PC_OK;
+    int32_t *out_dev = out;
+    if (!out_on_device) {
+        PC_TRY(devbuf_reserve(ctx, ctx->d_out, (size_t)count * sizeof(int32_t)));
+        out_dev = ctx->d_out.as<int32_t>();
+    }
+    if (metric <= PC_AF) {
+        PC_TRY(contract_rows(ctx, metric, as_distance, 0, row_begin, row_end, out_dev));
+    } else {
+        if (!acc_dev) return pc_fail(ctx, PC_EINVAL, "aai/peq rows need the accumulators");
+        if (metric == PC_PEQ)   // alignment_fraction(source, target) as SIMILARITY, metrics.py:247
+            PC_TRY(contract_rows(ctx, PC_AF, 0, 0, row_begin, row_end, out_dev));
+        PC_TRY(pc_stage_begin(ctx, PC_T_EPILOGUE));
+        PC_TRY(pc_launch_aai_epilogue(ctx, metric, as_distance, 0, row_begin, row_end,
+                                      reinterpret_cast<const unsigned long long *>(acc_dev),
+                                      out_dev, nullptr));
+        PC_TRY(pc_stage_end(ctx));
+    }
+    if (!out_on_device) PC_TRY(download(ctx, out, out_dev, (size_t)count * sizeof(int32_t)));
+    return maybe_collect(ctx);
+}
+
+static int full_accumulate(pc_ctx *ctx, int ppos)
+{
+    const size_t bytes = (size_t)slice_len(ctx, 0, ctx->N) * sizeof(uint64_t);
+    PC_TRY(devbuf_reserve(ctx, ctx->d_acc, bytes));
+    PC_CUDA(ctx, cudaMemsetAsync(ctx->d_acc.p, 0, bytes, ctx->stream));
+    return pc_align_accumulate(ctx, ppos, 0, 1, ctx->d_acc.as<uint64_t>());
+}
+
+extern "C" int pc_matrix(pc_ctx *ctx, int metric, int as_distance, int ppos,
+                         int32_t *out_micro_upper, int out_on_device)
+{
+    PC_ENTER(ctx);
+    PC_TRY(check_metric(ctx, metric));
+    const uint64_t *acc = nullptr;
+    if (metric == PC_AAI || metric == PC_PEQ) {
+        PC_TRY(full_accumulate(ctx, ppos));
+        acc = ctx->d_acc.as<uint64_t>();
+    }
+    return pc_matrix_rows(ctx, metric, as_distance, ppos, 0, ctx->N, acc, out_micro_upper,
+                          out_on_device);
+}
+
+extern "C" int pc_numerators(pc_ctx *ctx, int metric, int ppos, int32_t *out_num,
+                             int32_t *out_aux)
+{
+    PC_ENTER(ctx);
+    PC_TRY(check_metric(ctx, metric));
+    if (!out_num || metric == PC_PEQ || (metric == PC_AAI && !out_aux))
+        return pc_fail(ctx, PC_EINVAL, "pc_numerators: bad arguments");
+    const int64_t count = slice_len(ctx, 0, ctx->N);
+    PC_TRY(devbuf_reserve(ctx, ctx->d_out, (size_t)count * sizeof(int32_t)));
+    if (metric <= PC_AF) {
+        PC_TRY(contract_rows(ctx, metric, 0, 1, 0, ctx->N, ctx->d_out.as<int32_t>()));
+        return download(ctx, out_num, ctx->d_out.p, (size_t)count * sizeof(int32_t));
+    }
+    PC_TRY(full_accumulate(ctx, ppos));
+    PC_TRY(devbuf_reserve(ctx, ctx->d_numer, (size_t)count * sizeof(int32_t)));
+    PC_TRY(pc_stage_begin(ctx, PC_T_EPILOGUE));
+    PC_TRY(pc_launch_aai_epilogue(ctx, PC_AAI, 0, 1, 0, ctx->N,
+                                  ctx->d_acc.as<unsigned long long>(), ctx->d_out.as<int32_t>(),
+                                  ctx->d_numer.as<int32_t>()));
+    PC_TRY(pc_stage_end(ctx));
+    PC_TRY(download(ctx, out_num, ctx->d_out.p, (size_t)count * sizeof(int32_t)));
+    return download(ctx, out_aux, ctx->d_numer.p, (size_t)count * sizeof(int32_t));
+}
+
+// ---------------------------------------------------------------------------
+// pc_alignment_identities -- test hook over caller-chosen gene pairs
+// ---------------------------------------------------------------------------
+extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32_t *query_gene,
+                                       const int32_t *ref_gene, int32_t *out)
+{
+    PC_ENTER(ctx);
+    if (!ctx->have_seqs) return pc_fail(ctx, PC_ESTATE, "pc_alignment_identities needs pc_load_sequences first");
+    if (n_tasks < 0 || (n_tasks > 0 && (!query_gene || !ref_gene || !out)))
+        return pc_fail(ctx, PC_EINVAL, "pc_alignment_identities: bad arguments");
+    if (n_tasks == 0) return PC_OK;
+    // processing order: by kernel config of the ref length, largest first
+    std::vector<int64_t> bucket_count(PC_NW_BUCKETS, 0);
+    std::vector<int> bucket(n_tasks);
+    int32_t max_q_multi = 0;
+    for (int64_t t = 0; t < n_tasks; ++t) {
+        if (query_gene[t] < 0 || query_gene[t] >= ctx->n_genes || ref_gene[t] < 0 || ref_gene[t] >= ctx->n_genes)
+            return pc_fail(ctx, PC_EINVAL, "task %lld names a gene outside [0,%lld)", (long long)t, (long long)ctx->n_genes);
+        bucket[t] = pc_nw_bucket_of(ctx->h_gene_len[ref_gene[t]]);
+        bucket_count[bucket[t]]++;
+        if (bucket[t] == PC_NW_BUCKETS - 1)
+            max_q_multi = std::max(max_q_multi, ctx->h_gene_len[query_gene[t]]);
+    }
+    std::vector<int64_t> bucket_off(PC_NW_BUCKETS + 1, 0);
+    for (int b = 0; b < PC_NW_BUCKETS; ++b) bucket_off[b + 1] = bucket_off[b] + bucket_count[b];
+    std::vector<int64_t> perm(n_tasks);
+    {
+        std::vector<int64_t> cursor(bucket_off.begin(), bucket_off.end() - 1);
+        for (int64_t t = 0; t < n_tasks; ++t) perm[cursor[bucket[t]]++] = t;
+    }
+    PC_TRY(upload(ctx, ctx->d_task_q, query_gene, (size_t)n_tasks));
+    PC_TRY(upload(ctx, ctx->d_task_r, ref_gene, (size_t)n_tasks));
+    PC_TRY(upload(ctx, ctx->d_perm, perm.data(), (size_t)n_tasks));
+    PC_TRY(devbuf_reserve(ctx, ctx->d_hitlen, (size_t)n_tasks * sizeof(uint32_t) * 2));
+    PC_TRY(devbuf_reserve(ctx, ctx->d_score, (size_t)n_tasks * sizeof(int32_t)));
+    PC_TRY(ensure_counters(ctx));
+
+    NwArgs a;
+    memset(&a, 0, sizeof a);
+    a.task_q = ctx->d_task_q.as<int32_t>();
+    a.task_r = ctx->d_task_r.as<int32_t>();
+    a.perm = ctx->d_perm.as<int64_t>();
+    a.out_score = ctx->d_score.as<int32_t>();
+    for (int ppos = 0; ppos < 2; ++ppos) {
+        fill_nw_common(ctx, a, ppos);
+        a.out_hitlen = ctx->d_hitlen.as<uint32_t>() + (size_t)ppos * n_tasks;
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_BUCKETS, ctx->stream));
+        PC_TRY(pc_stage_begin(ctx, PC_T_ALIGN));
+        for (int b = PC_NW_BUCKETS - 1; b >= 0; --b) {
+            if (bucket_count[b] == 0) continue;
+            a.task_base = bucket_off[b];
+            a.n_tasks = bucket_count[b];
+            a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
+            if (b == PC_NW_BUCKETS - 1) PC_TRY(ensure_spill(ctx, max_q_multi, a));
+            PC_TRY(pc_launch_nw(ctx, a, b));
+        }
+        PC_TRY(pc_stage_end(ctx));
+        ctx->alignments += n_tasks;
+    }
+    std::vector<uint32_t> hl((size_t)n_tasks * 2);
+    std::vector<int32_t> score(n_tasks);
+    PC_CUDA(ctx, cudaMemcpyAsync(hl.data(), ctx->d_hitlen.p, hl.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PC_CUDA(ctx, cudaMemcpyAsync(score.data(), ctx->d_score.p, score.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t t = 0; t < n_tasks; ++t) {
+        const uint32_t id = hl[t], pp = hl[(size_t)n_tasks + t];
+        out[4 * t + 0] = (int32_t)(id >> 16);
+        out[4 * t + 1] = (int32_t)(pp >> 16) - (int32_t)(id >> 16);
+        out[4 * t + 2] = (int32_t)(id & 0xffffu);
+        out[4 * t + 3] = score[t];
+    }
+    return maybe_collect(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// pc_debug_round6
+// ---------------------------------------------------------------------------
+__global__ void round6_kernel(const double *__restrict__ x, int64_t n, int32_t *__restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = pc_round6_micro(x[k]);
+}
+
+extern "C" int pc_debug_round6(pc_ctx *ctx, int64_t n, const double *x, int32_t *out)
+{
+    PC_ENTER(ctx);
+    if (n < 0 || (n > 0 && (!x || !out))) return pc_fail(ctx, PC_EINVAL, "pc_debug_round6: bad arguments");
+    if (n == 0) return PC_OK;
+    DevBuf dx, dout;
+    int rc = upload(ctx, dx, x, (size_t)n);
+    if (rc == PC_OK) rc = devbuf_reserve(ctx, dout, (size_t)n * sizeof(int32_t));
+    if (rc == PC_OK) {
+        round6_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dx.as<double>(), n, dout.as<int32_t>());
+        ctx->launches++;
+        if (cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = pc_fail(ctx, PC_ECUDA, "round6 kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    devbuf_free(dx);
+    devbuf_free(dout);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------
+extern "C" int pc_timings(pc_ctx *ctx, double *ms, int n)
+{
+    PC_ENTER(ctx);
+    PC_TRY(pc_collect_timers(ctx));
+    for (int k = 0; k < n && k < PC_T_COUNT; ++k) ms[k] = ctx->stage_ms[k];
+    return PC_OK;
+}
+
+extern "C" int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
+                           int64_t *alignments, int64_t *contract_launches,
+                           int64_t *align_launches)
+{
+    PC_ENTER(ctx);
+    unsigned long long cells = 0;
+    if (ctx->d_counters.p) {
+        PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_BUCKETS,
+                                sizeof cells, cudaMemcpyDeviceToHost));
+    }
+    if (launches) *launches = ctx->launches;
+    if (dp_cells) *dp_cells = (int64_t)cells;
+    if (alignments) *alignments = ctx->alignments;
+    if (contract_launches) *contract_launches = ctx->contract_launches;
+    if (align_launches) *align_launches = ctx->align_launches;
+    return PC_OK;
+}
+
+extern "C" int pc_reset_counters(pc_ctx *ctx)
+{
+    PC_ENTER(ctx);
+    PC_TRY(pc_collect_timers(ctx));
+    for (double &v : ctx->stage_ms) v = 0.0;
+    ctx->launches = ctx->contract_launches = ctx->align_launches = 0;
+    ctx->alignments = 0;
+    if (ctx->d_counters.p) {
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_BUCKETS, 0,
+                                     sizeof(unsigned long long), ctx->stream));
+        PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PC_OK;
+}

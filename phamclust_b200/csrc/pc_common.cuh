@@ -1,0 +1,237 @@
+// pc_common.cuh -- shared declarations of libphamclust_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/phamclust_b200.h"
+#include "nw_rules.h"
+
+#define PC_NEG_INF (-(1 << 28))
+
+// ---------------------------------------------------------------------------
+// error plumbing: no exceptions across the C ABI
+// ---------------------------------------------------------------------------
+struct pc_ctx;
+int pc_fail(pc_ctx *ctx, int code, const char *fmt, ...);
+
+#define PC_CUDA(ctx, expr)                                                     \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess)                                                 \
+            return pc_fail((ctx), PC_ECUDA, "%s failed at %s:%d: %s", #expr,   \
+                           __FILE__, __LINE__, cudaGetErrorString(_e));        \
+    } while (0)
+
+#define PC_TRY(expr)                                                           \
+    do {                                                                       \
+        int _rc = (expr);                                                      \
+        if (_rc != PC_OK) return _rc;                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// a device buffer owned by the ctx (grow-only)
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+int devbuf_reserve(pc_ctx *ctx, DevBuf &b, size_t bytes);
+void devbuf_free(DevBuf &b);
+
+// ---------------------------------------------------------------------------
+// kernel argument blocks
+// ---------------------------------------------------------------------------
+struct PopcTerm {
+    const uint32_t *a;   // bit rows read for the tile's ROW genomes
+    const uint32_t *b;   // bit rows read for the tile's COLUMN genomes
+    int mult;            // weight of this term (2^plane)
+};
+
+struct EpilogueArgs {
+    const int32_t *den;  // per-genome denominator part (n_phams / n_genes / total_len)
+    int metric;          // PC_GCS .. PC_AF
+    int as_distance;
+    int raw;             // 1: write the integer numerator instead of micro-units
+    int64_t n;           // number of genomes
+    int64_t row_begin;   // first genome row covered by `out`
+    int64_t row_end;
+    int32_t *out;        // packed triangle slice starting at idx(row_begin,row_begin)
+};
+
+struct NwArgs {
+    const uint8_t *codes;        // residue codes, genes 16B aligned
+    const int64_t *gene_off;     // byte offset of each gene in codes
+    const int32_t *gene_len;
+    const int32_t *task_q;       // query (s1) gene per task
+    const int32_t *task_r;       // ref   (s2) gene per task
+    const int64_t *perm;         // processing order -> task id (nullable)
+    int64_t n_tasks;             // tasks in this launch
+    int64_t task_base;           // added to the processing index
+    uint32_t *out_hitlen;        // (matched columns << 16) | alignment length
+    int32_t *out_score;          // nullable
+    int4 *spill;                 // multi-chunk boundary column, per warp
+    int64_t spill_stride;        // int4 elements per warp
+    unsigned long long *work_counter;
+    unsigned long long *cell_counter;
+    const int2 *subtab;          // [32*32] {score, 1 + (hit << 16)}
+    int gap_open, gap_extend;
+};
+
+struct UnitArgs {
+    // per pham (processing order of this partition)
+    const int64_t *ph_mem_off;   // [n_ph+1] into the member arrays
+    const int64_t *ph_unit_off;  // [n_ph+1]
+    const int64_t *ph_task_off;  // [n_ph+1]
+    int64_t n_ph;
+    int64_t n_units;
+    // per member, grouped by pham, ascending genome index
+    const int32_t *mem_genome;
+    const int32_t *mem_first_gene;
+    const int32_t *mem_copies;
+    const int32_t *mem_cprefix;  // copies of earlier members of the same pham
+    const int64_t *mem_rowoff;   // tasks of earlier rows of the same pham
+    int64_t n_genomes;
+};
+
+// ---------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------
+struct StageTimer {
+    cudaEvent_t start, stop;
+    int stage;
+};
+
+struct AlignPlan {           // host+device prep for one (part, n_parts)
+    int part = -1, n_parts = -1;
+    int64_t n_ph = 0, n_units = 0, n_tasks = 0, n_mem = 0;
+    std::vector<int64_t> bucket_task_off;   // first task of each NW bucket
+    std::vector<int64_t> bucket_task_count; // tasks in each NW bucket
+    int32_t max_qlen_multichunk = 0;
+    DevBuf ph_mem_off, ph_unit_off, ph_task_off;
+    DevBuf mem_genome, mem_first_gene, mem_copies, mem_cprefix, mem_rowoff;
+};
+
+struct pc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int engine = PC_ENGINE_AUTO;
+
+    // ---- table (host copies kept for the host-side planning) ----
+    bool have_table = false, have_seqs = false;
+    int64_t N = 0, P = 0, nnz = 0;
+    std::vector<int64_t> h_genome_ptr;
+    std::vector<int32_t> h_pham_id;
+    std::vector<uint32_t> h_copies, h_len_sum;
+    std::vector<int32_t> h_entry_genome;
+    std::vector<int64_t> h_entry_first_gene;
+    std::vector<int64_t> h_pham_ptr;      // CSC
+    std::vector<int64_t> h_pham_members;  // entry ids grouped by pham, genome ascending
+    uint32_t max_copies = 0, max_len_sum = 0;
+    int64_t n_genes_total = 0;
+
+    // ---- device: table ----
+    DevBuf d_entry_genome, d_pham_id, d_copies, d_len_sum;
+    DevBuf d_den_phams, d_den_genes, d_den_len;   // int32 [N]
+    int64_t W = 0;                                 // words per bit row (multiple of 32)
+    DevBuf d_bits;                                 // presence bit rows [N][W]
+    DevBuf d_planes;                               // weight bit planes
+    int planes_kind = -1, planes_count = 0;        // what d_planes currently holds
+    DevBuf d_terms;
+    DevBuf d_numer;                                // int32 scratch triangle slice
+    // int8 operand for the tcgen05 engine
+    DevBuf d_i8;                                   // [N_pad][K_pad]
+    int i8_kind = -1; int64_t i8_K = 0, i8_rows = 0;
+
+    // ---- sequences ----
+    int64_t n_genes = 0;
+    std::vector<int32_t> h_gene_len;
+    DevBuf d_codes, d_gene_off, d_gene_len, d_raw;
+    DevBuf d_subtab[2];                            // [0] identity, [1] ppos
+    int code_of_byte[256];
+    int n_codes = 0;
+    int code_matrix_index[32];
+
+    // ---- aai work buffers ----
+    AlignPlan plan;
+    DevBuf d_task_q, d_task_r, d_hitlen, d_score, d_spill, d_counters, d_perm;
+    DevBuf d_acc;                                  // uint64 accumulators (single-GPU path)
+    DevBuf d_out;                                  // int32 result staging
+
+    // ---- measurement ----
+    std::vector<StageTimer> timers;
+    std::vector<cudaEvent_t> event_pool;
+    double stage_ms[PC_T_COUNT] = {0};
+    int64_t launches = 0, contract_launches = 0, align_launches = 0;
+    int64_t dp_cells = 0, alignments = 0;
+};
+
+// stage timing helpers (events on ctx->stream)
+int pc_stage_begin(pc_ctx *ctx, int stage);
+int pc_stage_end(pc_ctx *ctx);
+int pc_collect_timers(pc_ctx *ctx);
+
+// ---------------------------------------------------------------------------
+// launchers implemented in the other translation units
+// ---------------------------------------------------------------------------
+int pc_launch_pack_bits(pc_ctx *ctx, int source /*0 presence,1 copies,2 len*/,
+                        int plane, uint32_t *dst);
+int pc_launch_popc_contract(pc_ctx *ctx, const PopcTerm *d_terms, int n_terms,
+                            const EpilogueArgs &ep);
+int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int bucket);
+int pc_launch_expand_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q,
+                           int32_t *task_r);
+int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen,
+                           unsigned long long *acc);
+int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
+                           int64_t row_begin, int64_t row_end,
+                           const unsigned long long *acc, int32_t *out,
+                           int32_t *out_aux);
+int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
+                     const int64_t *gene_off, const int32_t *gene_len,
+                     const uint8_t *code_lut, int64_t n_genes, uint8_t *codes);
+int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
+
+// NW bucket table: capacity (ref columns per pass) of each kernel config
+#define PC_NW_BUCKETS 9
+extern const int pc_nw_bucket_cap[PC_NW_BUCKETS];
+int pc_nw_bucket_of(int ref_len);
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ int64_t pc_tri_index(int64_t n, int64_t i, int64_t j)
+{
+    // packed upper triangle incl. diagonal, i <= j
+    return i * n - (i * (i - 1)) / 2 + (j - i);
+}
+
+// Python's round(x, 6) as integer micro-units: round-half-even of the EXACT
+// value of the double x times 10^6 (CPython rounds the exact binary value via
+// dtoa mode 3; SURVEY.md 7 hard part 3).  x*1e6 is split exactly into hi+lo.
+__device__ __forceinline__ int pc_round6_micro(double x)
+{
+    const double hi = x * 1e6;
+    const double lo = fma(x, 1e6, -hi);
+    double r = rint(hi);                       // half-even on hi
+    if (fabs(hi - r) == 0.5) {                 // hi is an exact half-integer
+        const double fl = floor(hi);
+        if (lo > 0.0) r = fl + 1.0;
+        else if (lo < 0.0) r = fl;
+    }
+    return (int)r;
+}
+
+// The tail shared by every metric (e.g. metrics.py:50-53): similarity -> the
+// value stored by SymMatrix.set_weight (matrix.py:323), in micro-units.
+__device__ __forceinline__ int pc_finish_micro(double similarity, int as_distance)
+{
+    return pc_round6_micro(as_distance ? 1.0 - similarity : similarity);
+}
+#endif

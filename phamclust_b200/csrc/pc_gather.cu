@@ -1,0 +1,240 @@
+// pc_gather.cu -- the kernels either side of the DP:
+//   * encode:  raw residue bytes -> 5-bit codes in a 16B-aligned arena
+//   * expand:  (pham, member a, member b) units -> ordered gene-pair tasks
+//   * gather:  K5, best match per anchor gene -> per-genome-pair accumulators
+//   * epilogue: K6 for aai / peq
+// Reference semantics: /root/reference/src/phamclust/metrics.py:203-232 (aai),
+// :235-253 (peq), statistics.py:22 (length-weighted mean).
+#include "pc_common.cuh"
+
+// ---------------------------------------------------------------------------
+// encode
+// ---------------------------------------------------------------------------
+__global__ void encode_kernel(const uint8_t *__restrict__ raw,
+                              const int64_t *__restrict__ raw_off,
+                              const int64_t *__restrict__ gene_off,
+                              const int32_t *__restrict__ gene_len,
+                              const uint8_t *__restrict__ lut, int64_t n_genes,
+                              uint8_t *__restrict__ codes)
+{
+    __shared__ uint8_t s_lut[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_lut[x] = lut[x];
+    __syncthreads();
+    // one warp per gene, lanes stride the residues
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t g = warp; g < n_genes; g += n_warps) {
+        const uint8_t *src = raw + raw_off[g];
+        uint8_t *dst = codes + gene_off[g];
+        const int len = gene_len[g];
+        for (int x = lane; x < len; x += 32) dst[x] = s_lut[src[x]];
+    }
+}
+
+int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
+                     const int64_t *gene_off, const int32_t *gene_len,
+                     const uint8_t *code_lut, int64_t n_genes, uint8_t *codes)
+{
+    if (n_genes <= 0) return PC_OK;
+    int64_t blocks = (n_genes * 32 + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    encode_kernel<<<grid, 256, 0, ctx->stream>>>(raw, raw_off, gene_off, gene_len,
+                                                code_lut, n_genes, codes);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// unit decoding shared by expand and gather
+// ---------------------------------------------------------------------------
+struct Unit {
+    int ga, gb;              // genome indices, ga < gb
+    int first_a, first_b;    // first gene of each member
+    int ca, cb;              // copies
+    int64_t task_off;        // first task of this unit
+};
+
+__device__ __forceinline__ Unit decode_unit(const UnitArgs &u, int64_t unit)
+{
+    // pham = last p with ph_unit_off[p] <= unit
+    int64_t lo = 0, hi = u.n_ph;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (u.ph_unit_off[mid] <= unit) lo = mid; else hi = mid;
+    }
+    const int64_t p = lo;
+    const int64_t mem0 = u.ph_mem_off[p];
+    const int64_t m = u.ph_mem_off[p + 1] - mem0;
+    const int64_t lu = unit - u.ph_unit_off[p];
+    // row-major strict upper triangle of an m x m grid: row a holds m-1-a units
+    const double tm = (double)(2 * m - 1);
+    int64_t a = (int64_t)floor((tm - sqrt(tm * tm - 8.0 * (double)lu)) * 0.5);
+    if (a < 0) a = 0;
+    if (a > m - 2) a = m - 2;
+    while (a > 0 && a * (2 * m - a - 1) / 2 > lu) --a;
+    while ((a + 1) * (2 * m - (a + 1) - 1) / 2 <= lu) ++a;
+    const int64_t b = lu - a * (2 * m - a - 1) / 2 + a + 1;
+    Unit r;
+    r.ga = u.mem_genome[mem0 + a];
+    r.gb = u.mem_genome[mem0 + b];
+    r.first_a = u.mem_first_gene[mem0 + a];
+    r.first_b = u.mem_first_gene[mem0 + b];
+    r.ca = u.mem_copies[mem0 + a];
+    r.cb = u.mem_copies[mem0 + b];
+    // tasks before this unit inside the pham: all rows a' < a, then the units
+    // (a, b') with b' < b, each worth ca * c_b'
+    const int64_t c_between = (int64_t)u.mem_cprefix[mem0 + b] -
+                              ((int64_t)u.mem_cprefix[mem0 + a] + r.ca);
+    r.task_off = u.ph_task_off[p] + u.mem_rowoff[mem0 + a] + (int64_t)r.ca * c_between;
+    return r;
+}
+
+// Anchor = the member with FEWER copies, tie -> the lower genome index
+// (metrics.py:208-209; source index < target index by matrix.py:480-486).
+__global__ void expand_units_kernel(const UnitArgs u, int32_t *__restrict__ task_q,
+                                    int32_t *__restrict__ task_r)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+         unit < u.n_units; unit += stride) {
+        const Unit t = decode_unit(u, unit);
+        const bool swap = t.ca > t.cb;
+        const int n_anchor = swap ? t.cb : t.ca, n_other = swap ? t.ca : t.cb;
+        const int anchor0 = swap ? t.first_b : t.first_a;
+        const int other0 = swap ? t.first_a : t.first_b;
+        for (int x = 0; x < n_anchor; ++x)
+            for (int y = 0; y < n_other; ++y) {
+                const int64_t k = t.task_off + (int64_t)x * n_other + y;
+                task_q[k] = anchor0 + x;      // _align(anchor_gene, other_gene)
+                task_r[k] = other0 + y;
+            }
+    }
+}
+
+// For each anchor gene keep the candidate with the best matched/length ratio,
+// ties -> the LAST candidate (sorted(...)[-1] on a stable sort, metrics.py:223);
+// ratios are compared exactly by cross-multiplication.  The unit's sums go to
+// acc[idx(ga, gb)] as (matched << 32) | length with ONE 64-bit integer atomic:
+// exact and order independent.
+__global__ void gather_units_kernel(const UnitArgs u, const uint32_t *__restrict__ hitlen,
+                                    unsigned long long *__restrict__ acc)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+         unit < u.n_units; unit += stride) {
+        const Unit t = decode_unit(u, unit);
+        const bool swap = t.ca > t.cb;
+        const int n_anchor = swap ? t.cb : t.ca, n_other = swap ? t.ca : t.cb;
+        unsigned long long sum_hit = 0, sum_len = 0;
+        for (int x = 0; x < n_anchor; ++x) {
+            unsigned long long best_hit = 0, best_len = 0;
+            bool have = false;
+            for (int y = 0; y < n_other; ++y) {
+                const uint32_t v = hitlen[t.task_off + (int64_t)x * n_other + y];
+                const unsigned long long hit = v >> 16, len = v & 0xffffu;
+                if (len == 0) continue;           // undefined upstream (0-length alignment)
+                if (!have || hit * best_len >= best_hit * len) {
+                    best_hit = hit; best_len = len; have = true;
+                }
+            }
+            sum_hit += best_hit;
+            sum_len += best_len;
+        }
+        if (sum_len)
+            atomicAdd(acc + pc_tri_index(u.n_genomes, t.ga, t.gb), (sum_hit << 32) | sum_len);
+    }
+}
+
+static int unit_grid(pc_ctx *ctx, int64_t n_units)
+{
+    int64_t blocks = (n_units + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    int64_t g = blocks < cap ? blocks : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+int pc_launch_expand_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r)
+{
+    if (u.n_units <= 0) return PC_OK;
+    expand_units_kernel<<<unit_grid(ctx, u.n_units), 256, 0, ctx->stream>>>(u, task_q, task_r);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PC_OK;
+}
+
+int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen,
+                           unsigned long long *acc)
+{
+    if (u.n_units <= 0) return PC_OK;
+    gather_units_kernel<<<unit_grid(ctx, u.n_units), 256, 0, ctx->stream>>>(u, hitlen, acc);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K6 for aai and peq.  For PC_PEQ `out` already holds alignment_fraction in
+// micro-units AS SIMILARITY (metrics.py:247) and is overwritten in place.
+// ---------------------------------------------------------------------------
+__global__ void aai_epilogue_kernel(int metric, int as_distance, int raw, int64_t n,
+                                    int64_t row_begin, int64_t row_end,
+                                    const unsigned long long *__restrict__ acc,
+                                    int32_t *__restrict__ out, int32_t *__restrict__ out_aux)
+{
+    const int64_t base = pc_tri_index(n, row_begin, row_begin);
+    const int64_t total = pc_tri_index(n, row_end, row_end) - base;   // row_end may equal n
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+        // recover (i, j) from the packed index: row i starts at pc_tri_index(n, i, i)
+        const int64_t g = base + k;
+        const double tn = (double)(2 * n + 1);
+        int64_t i = (int64_t)floor((tn - sqrt(tn * tn - 8.0 * (double)g)) * 0.5);
+        if (i < 0) i = 0;
+        if (i > n - 1) i = n - 1;
+        while (i > 0 && pc_tri_index(n, i, i) > g) --i;
+        while (i + 1 < n && pc_tri_index(n, i + 1, i + 1) <= g) ++i;
+        const int64_t j = i + (g - pc_tri_index(n, i, i));
+        const unsigned long long v = acc[g];
+        const unsigned long long hit = v >> 32, len = v & 0xffffffffull;
+        if (raw) {
+            out[k] = (i == j) ? 0 : (int32_t)hit;
+            if (out_aux) out_aux[k] = (i == j) ? 0 : (int32_t)len;
+            continue;
+        }
+        if (i == j) {                               // matrix.py:467-468
+            out[k] = as_distance ? 0 : 1000000;
+            continue;
+        }
+        // aai similarity: length-weighted mean identity = sum(hit) / sum(len)
+        // (statistics.py:22); no shared pham -> 0.0 (metrics.py:198-199)
+        const double aai = len ? (double)hit / (double)len : 0.0;
+        if (metric == PC_AAI) {
+            out[k] = pc_finish_micro(aai, as_distance);
+        } else {
+            // peq multiplies the two ROUNDED factors (metrics.py:247-248)
+            const double af_r = (double)out[k] / 1e6;
+            const double aai_r = (double)pc_round6_micro(aai) / 1e6;
+            out[k] = pc_finish_micro(af_r * aai_r, as_distance);
+        }
+    }
+}
+
+int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
+                           int64_t row_begin, int64_t row_end,
+                           const unsigned long long *acc, int32_t *out, int32_t *out_aux)
+{
+    const int64_t total = pc_tri_index(ctx->N, row_end, row_end) -
+                          pc_tri_index(ctx->N, row_begin, row_begin);
+    if (total <= 0) return PC_OK;
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    aai_epilogue_kernel<<<grid, 256, 0, ctx->stream>>>(metric, as_distance, raw, ctx->N,
+                                                      row_begin, row_end, acc, out, out_aux);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PC_OK;
+}

@@ -1,0 +1,486 @@
+"""Array-backed symmetric matrix + the ``matrix_de_novo`` drop-in.
+
+``SymMatrix`` keeps the API of /root/reference/src/phamclust/matrix.py:33-405
+(the object handed to the unchanged host clustering / heatmap code, SURVEY.md
+3.5) but stores the packed upper triangle the device produces: int32
+micro-units (``round(w, 6) * 1e6`` exactly, matrix.py:323), so a 50k-genome
+matrix is 5 GB of int32 instead of 1.25e9 Python dict entries.
+
+``matrix_de_novo(genomes, func, cpus, as_distance=True)`` has the reference's
+signature (matrix.py:432); ``func`` must be one of the six metric functions of
+``phamclust_b200.metrics`` -- the whole upper triangle is computed by
+libphamclust_b200 in one call instead of one joblib task per pair.
+"""
+import logging
+
+import numpy as np
+
+from phamclust_b200 import _native
+from phamclust_b200.packing import PackedTable, pack_genomes
+from phamclust_b200.statistics import average
+
+_UNSET = -1
+
+
+def _tri_offsets(n):
+    """Start of every row in the packed upper triangle (length n+1)."""
+    i = np.arange(n + 1, dtype=np.int64)
+    return i * n - (i * (i - 1)) // 2
+
+
+class SymMatrix:
+    """Undirected weighted graph over named nodes; drop-in for the reference's
+    dict-of-dicts class.  Weights are exact 6-decimal values."""
+
+    def __init__(self, nodes, is_distance=False, _micro=None):
+        self._nodes = nodes                       # traversal order (mutable, like upstream)
+        self._store = list(nodes)                 # storage order (fixed)
+        self._index = {name: k for k, name in enumerate(self._store)}
+        n = len(self._store)
+        self._offsets = _tri_offsets(n)
+        if _micro is None:
+            _micro = np.full(n * (n + 1) // 2, _UNSET, dtype=np.int32)
+        self._micro = _micro
+        self._is_distance = is_distance
+        self._locked = False
+
+    # -- construction from device output ---------------------------------------
+    @classmethod
+    def from_micro(cls, nodes, micro, is_distance):
+        n = len(nodes)
+        micro = np.ascontiguousarray(micro, dtype=np.int32)
+        if micro.size != n * (n + 1) // 2:
+            raise ValueError(f"need {n * (n + 1) // 2} packed weights but got {micro.size}")
+        return cls(list(nodes), is_distance=is_distance, _micro=micro)
+
+    @property
+    def micro(self):
+        """The packed int32 micro-unit triangle in STORAGE order (read-only view)."""
+        view = self._micro.view()
+        view.flags.writeable = False
+        return view
+
+    # -- properties (matrix.py:51-149) -------------------------------------------
+    @property
+    def is_distance(self):
+        return self._is_distance
+
+    @property
+    def nodes(self):
+        return self._nodes[:]
+
+    @property
+    def diameter(self):
+        if not self.is_distance:
+            raise ValueError("cannot compute diameter for similarity matrix")
+        n = len(self._store)
+        if n < 2:
+            return 0.0
+        mask = np.ones(self._micro.size, dtype=bool)
+        mask[self._offsets[:-1]] = False          # drop the diagonal
+        vals = self._micro[mask]
+        vals = vals[vals != _UNSET]
+        return round(float(vals.max()) / 1e6, 6) if vals.size else 0.0
+
+    def _node_averages(self):
+        """Per node, ``average`` of every weight it appears in while iterating the
+        upper half -- the diagonal is seen as source AND target, so it counts twice
+        (matrix.py:81-96); summed in the reference's order so ties break alike."""
+        full = self.to_ndarray()
+        out = {}
+        for k, name in enumerate(self._nodes):
+            row = full[k]
+            weights = list(row[:k]) + [row[k], row[k]] + list(row[k + 1:])
+            out[name] = average([float(w) for w in weights])
+        return out
+
+    @property
+    def medoid(self):
+        ranked = sorted(self._node_averages().items(), key=lambda x: x[1])
+        return ranked[0] if self.is_distance else ranked[-1]
+
+    @property
+    def anti_medoid(self):
+        ranked = sorted(self._node_averages().items(), key=lambda x: x[1])
+        return ranked[-1] if self.is_distance else ranked[0]
+
+    @property
+    def statistics(self):
+        """(mean, sample std-dev, sample skewness) of the off-diagonal edges
+        (matrix.py:129-149)."""
+        n = len(self)
+        if n == 1:
+            node = self._nodes[0]
+            return self.get_weight(node, node), 0.0, 0.0
+        edges = [w for s, t, w in self if s != t]
+        mean = average(edges)
+        var = sum([(x - mean) ** 2 for x in edges]) / (len(edges) - 1) if len(edges) > 1 else 0.0
+        std = var ** 0.5
+        if std == 0.0:
+            return mean, std, 0.0
+        skew = sum([(x - mean) ** 3 for x in edges]) / ((std ** 3) * (len(edges) - 1))
+        return mean, std, skew
+
+    # -- element access -------------------------------------------------------------
+    def _slot(self, source, target):
+        if source not in self:
+            raise KeyError(f"node '{source}' not in matrix")
+        if target not in self:
+            raise KeyError(f"node '{target}' not in matrix")
+        i, j = self._index[source], self._index[target]
+        if i > j:
+            i, j = j, i
+        return int(self._offsets[i]) + (j - i)
+
+    def get_weight(self, source, target):
+        v = int(self._micro[self._slot(source, target)])
+        return None if v == _UNSET else v / 1e6
+
+    def set_weight(self, source, target, weight):
+        if self._locked:
+            raise AttributeError("matrix is marked as read-only")
+        slot = self._slot(source, target)
+        if not 0 <= weight <= 1:
+            raise ValueError(f"weight {weight} not in [0.0, 1.0]")
+        self._micro[slot] = int(round(round(weight, 6) * 1e6))
+
+    def append_node(self, source, data):
+        """matrix.py:169-216 -- grows the packed triangle by one node."""
+        if source in self:
+            raise KeyError(f"node '{source}' is already in this matrix")
+        if source not in data:
+            raise KeyError(f"incoming data lacks an self-edge for '{source}'")
+        if self.is_distance and data[source] != 0.0:
+            raise ValueError(f"nonsense value {data[source]} for self-edge on distance matrix")
+        if not self.is_distance and data[source] != 1.0:
+            raise ValueError(f"nonsense value {data[source]} for self-edge on similarity matrix")
+        missed = set(self._store) - data.keys()
+        if missed:
+            raise KeyError(f"missing edge(s) for {source} vs: {missed}")
+        extra = set(data.keys()) - {source} - set(self._store)
+        if extra:
+            raise KeyError(f"specified edges for nodes not found in matrix: {extra}")
+        old_n = len(self._store)
+        old = self._dense_micro()
+        self._store.append(source)
+        self._index[source] = old_n
+        self._nodes.append(source)
+        n = old_n + 1
+        dense = np.full((n, n), _UNSET, dtype=np.int32)
+        dense[:old_n, :old_n] = old
+        self._offsets = _tri_offsets(n)
+        self._micro = dense[np.triu_indices(n)].astype(np.int32)
+        for target in self._nodes:
+            self.set_weight(source, target, data[target])
+
+    def extract_submatrix(self, nodes):
+        for node in nodes:
+            if node not in self:
+                raise KeyError(f"node '{node}' not in matrix")
+        idx = np.fromiter((self._index[x] for x in nodes), dtype=np.int64, count=len(nodes))
+        k = len(nodes)
+        iu, ju = np.triu_indices(k)
+        a, b = idx[iu], idx[ju]
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        micro = self._micro[self._offsets[lo] + (hi - lo)]
+        return SymMatrix(nodes, self.is_distance, _micro=np.ascontiguousarray(micro))
+
+    def invert(self):
+        """distance <-> similarity in place: round(1 - w, 6) == (1e6 - n)/1e6."""
+        if self._locked:
+            raise AttributeError("matrix is marked as read-only")
+        unset = self._micro == _UNSET
+        if unset.any():
+            raise TypeError("unsupported operand type(s) for -: 'float' and 'NoneType'")
+        self._micro = (1000000 - self._micro).astype(np.int32)
+        self._is_distance = not self.is_distance
+        return self
+
+    def reorder(self, nodes=None):
+        if not nodes:
+            nodes = [self._nodes[x] for x in _get_tree_order(self)]
+        if len(nodes) != len(self):
+            raise ValueError(f"need {len(self)} nodes but got {len(nodes)}")
+        for node in nodes:
+            if node not in self:
+                raise KeyError(f"node '{node}' not in matrix")
+        self._nodes = nodes
+
+    def nearest_neighbors(self, source, threshold):
+        is_distance = self.is_distance
+        neighbors = []
+        for target in self._nodes:
+            if source == target:
+                continue
+            weight = self.get_weight(source, target)
+            if (is_distance and weight <= threshold) or (not is_distance and weight >= threshold):
+                neighbors.append(target)
+        return sorted(neighbors, reverse=not is_distance,
+                      key=lambda x: self.get_weight(source, x))
+
+    def lock(self):
+        self._locked = True
+
+    def unlock(self):
+        self._locked = False
+
+    def is_locked(self):
+        return self._locked
+
+    # -- bulk views ---------------------------------------------------------------------
+    def _dense_micro(self):
+        """Square int32 matrix in STORAGE order."""
+        n = len(self._store)
+        dense = np.empty((n, n), dtype=np.int32)
+        iu = np.triu_indices(n)
+        dense[iu] = self._micro
+        dense.T[iu] = self._micro
+        return dense
+
+    def to_ndarray(self, condensed=False):
+        """Square float64 matrix in TRAVERSAL order (or scipy's condensed form);
+        what clustering.py:27 and _get_tree_order consume."""
+        dense = self._dense_micro()
+        if self._nodes != self._store:
+            perm = np.fromiter((self._index[x] for x in self._nodes), dtype=np.int64,
+                               count=len(self._nodes))
+            dense = dense[np.ix_(perm, perm)]
+        if (dense == _UNSET).any():
+            full = dense.astype(object) / 1e6
+            full[dense == _UNSET] = None
+            return full
+        full = dense / 1e6
+        if condensed:
+            from scipy.spatial.distance import squareform
+            return squareform(full, force="tovector")
+        return full
+
+    def iterrows(self):
+        full = self.to_ndarray()
+        for k, source in enumerate(self._nodes):
+            yield source, [x if x is None else float(x) for x in full[k]]
+
+    def __iter__(self):
+        """(source, target, weight) over the upper half in traversal order."""
+        for idx, source in enumerate(self._nodes):
+            for target in self._nodes[idx:]:
+                yield source, target, self.get_weight(source, target)
+
+    def __contains__(self, item):
+        if not isinstance(item, str):
+            raise TypeError(f"type(item) should be 'str', not '{type(item)}'")
+        return item in self._index
+
+    def __getitem__(self, item):
+        """Row as the reference stores it: only targets that sort AFTER (or equal
+        to) ``item`` lexicographically (matrix.py:230-234, 319-323)."""
+        if item not in self:
+            raise KeyError(f"node '{item}' not in matrix")
+        row = {}
+        for target in self._store:
+            if target >= item:
+                w = self.get_weight(item, target)
+                if w is not None:
+                    row[target] = w
+        return row
+
+    def __len__(self):
+        return len(self._nodes)
+
+    def __lt__(self, other):
+        if not isinstance(other, SymMatrix):
+            raise TypeError(f"cannot compare SymMatrix to {type(other)}")
+        return len(self) < len(other)
+
+    def __str__(self):
+        s = f"{len(self)}\n"
+        for source, row in self.iterrows():
+            s += f"{source:<24}\t" + "\t".join([f"{x:.6f}" for x in row]) + "\n"
+        return s
+
+
+# ---------------------------------------------------------------------------------------
+# matrix_de_novo and friends (matrix.py:409-497)
+# ---------------------------------------------------------------------------------------
+def _outside_in_index_iterator(num_indices):
+    """[0, n-1, 1, n-2, ...] (matrix.py:409-423).  The reference uses it to
+    balance joblib batches; on the GPU the result is order independent, it is
+    kept for API parity.
+
+    >>> list(_outside_in_index_iterator(5))
+    [0, 4, 1, 3, 2]
+    """
+    lo, hi = 0, num_indices - 1
+    while lo < hi:
+        yield lo
+        yield hi
+        lo, hi = lo + 1, hi - 1
+    if lo == hi:
+        yield lo
+
+
+def calculate_adjacency(source, target, func, distance=True):
+    """matrix.py:426-429."""
+    return source.name, target.name, func(source, target, as_distance=distance)
+
+
+_contexts = {}
+
+
+def get_context(device=0):
+    """The process-wide pc_ctx of a device (created on first use)."""
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = _native.Context(device)
+    return ctx
+
+
+def _metric_key(func):
+    from phamclust_b200 import metrics
+    key = metrics.metric_key(func)
+    if key is None:
+        raise TypeError(
+            "matrix_de_novo runs on the GPU and only knows PhamClust's six metrics "
+            "(gcs, jc, pocp, af, aai, peq from phamclust_b200.metrics); there is no CPU "
+            f"fallback for arbitrary callables such as {func!r}")
+    return key
+
+
+def packed_matrix(table, metric, as_distance=True, ppos=False, device=0, engine=None):
+    """Packed int32 micro-unit triangle for a PackedTable (single GPU)."""
+    ctx = get_context(device)
+    if engine is not None:
+        ctx.set_engine(engine)
+    ctx.load_table(table)
+    if metric in ("aai", "peq"):
+        if table.seq_off is None:
+            raise ValueError(f"metric {metric} needs translations")
+        ctx.load_sequences(table)
+    return ctx.matrix(metric, as_distance=as_distance, ppos=ppos)
+
+
+def matrix_de_novo(genomes, func, cpus=1, as_distance=True):
+    """Drop-in for matrix.py:432-497.
+
+    ``genomes``: list[Genome]; their order fixes the source<target orientation
+    (matrix.py:480-486).  ``func``: one of the six metric functions.  ``cpus`` is
+    accepted for signature parity and ignored (one GPU does the whole triangle;
+    see phamclust_b200.distributed for several).  Returns a ``SymMatrix`` with
+    ``is_distance == as_distance`` whose diagonal is ``1.0 - as_distance``.
+    """
+    if len(genomes) == 0:
+        raise ValueError("need at least 1 genome to construct matrix de novo")
+    key = _metric_key(func)
+    n = len(genomes)
+    logging.debug(f"{n} genomes -> {n * (n - 1) // 2 + n} edges including diagonal")
+    table = genomes if isinstance(genomes, PackedTable) else \
+        pack_genomes(genomes, with_sequences=key in ("aai", "peq"))
+    from phamclust_b200 import distributed
+    if distributed.is_active():
+        micro = distributed.sharded_matrix(table, key, as_distance=as_distance)
+    else:
+        micro = packed_matrix(table, key, as_distance=as_distance)
+    return SymMatrix.from_micro(table.names, micro, is_distance=bool(as_distance))
+
+
+# ---------------------------------------------------------------------------------------
+# file formats (matrix.py:500-670): adjacency, squareform, lower triangle; "%.6f"
+# ---------------------------------------------------------------------------------------
+def read_adjacency(filepath):
+    with open(filepath, "r") as handle:
+        for edge in handle:
+            edge = edge.rstrip().split("\t")
+            yield edge[0], edge[1], float(edge[2])
+
+
+def matrix_from_adjacency(filepath):
+    names, diagonal = dict(), set()
+    for source, target, weight in read_adjacency(filepath):
+        if source == target:
+            diagonal.add(weight)
+        if target in names:
+            break
+        names[target] = None
+    names = list(names.keys())
+    if len(diagonal) > 1:
+        raise ValueError("values on matrix diagonal should be identical")
+    if sum(diagonal) == 0.0:
+        is_distance = True
+    elif sum(diagonal) == 1.0:
+        is_distance = False
+    else:
+        raise ValueError("values on matrix diagonal can only be 0.0 or 1.0")
+    matrix = SymMatrix(names, is_distance=is_distance)
+    for source, target, weight in read_adjacency(filepath):
+        matrix.set_weight(source, target, weight)
+    return matrix
+
+
+def _fmt6(micro):
+    """'%.6f' of micro-units without going through floats."""
+    micro = int(micro)
+    return f"{micro // 1000000}.{micro % 1000000:06d}"
+
+
+def matrix_to_adjacency(matrix, filepath, skip_zero=False):
+    with open(filepath, "w") as handle:
+        for source, target, weight in matrix:
+            if skip_zero and not weight:
+                continue
+            handle.write(f"{source}\t{target}\t{weight:.6f}\n")
+    return filepath
+
+
+def read_squareform(filepath):
+    with open(filepath, "r") as handle:
+        next(handle)                               # first line only has the size
+        for row in handle:
+            row = row.rstrip().split("\t")
+            yield row[0], [float(x) for x in row[1:]]
+
+
+def matrix_from_squareform(filepath):
+    names, diagonal = [], set()
+    for i, (target, row) in enumerate(read_squareform(filepath)):
+        names.append(target)
+        diagonal.add(row[i])
+    if len(diagonal) > 1:
+        raise ValueError("values on matrix diagonal should be identical")
+    if sum(diagonal) == 0.0:
+        is_distance = True
+    elif sum(diagonal) == len(diagonal):
+        is_distance = False
+    else:
+        raise ValueError("values on matrix diagonal can only be 0.0 or 1.0")
+    matrix = SymMatrix(names, is_distance=is_distance)
+    for i, (target, row) in enumerate(read_squareform(filepath)):
+        for source, weight in zip(names[:i + 1], row[:i + 1]):
+            matrix.set_weight(source, target, weight)
+    return matrix
+
+
+def matrix_to_squareform(matrix, filepath, lower_triangle=False):
+    """Squareform / lower-triangle writer; the lower-triangle form is the
+    pipeline's on-disk cache (scripts/phamclust.py:254-262) and must stay
+    byte-identical: '%.6f', tab separated."""
+    with open(filepath, "w") as handle:
+        header = f"{len(matrix)}"
+        if not lower_triangle:
+            header += "\t" + "\t".join(matrix.nodes)
+        handle.write(f"{header}\n")
+        for i, (source, row) in enumerate(matrix.iterrows()):
+            if lower_triangle:
+                row = row[:i + 1]
+            handle.write(f"{source}\t" + "\t".join([f"{x:.6f}" for x in row]) + "\n")
+    return filepath
+
+
+def _get_tree_order(matrix):
+    """Leaf order of a single-linkage dendrogram (matrix.py:673-686)."""
+    from scipy.cluster.hierarchy import dendrogram, linkage
+    if not matrix.is_distance:
+        matrix = matrix.extract_submatrix(matrix.nodes)
+        matrix.invert()
+    z = linkage(matrix.to_ndarray(condensed=True), method="single")
+    d = dendrogram(z, no_plot=True, get_leaves=True, count_sort="descending")
+    return d["leaves"]
