@@ -1,0 +1,107 @@
+"""world_size-2 gloo run of the multi-GPU host logic (row partition, integer
+all-reduce of the pair accumulators, all-gather assembly) with the CPU oracle
+standing in for the per-rank GPU ops -- the N>1 path without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pham_oracle as po
+from oracle import testdata
+from phamclust_b200 import distributed
+from phamclust_b200.genome import Genome
+from phamclust_b200.packing import pack_genomes
+
+
+class OracleOps:
+    """Per-rank compute restated with the oracle (CPU tensors)."""
+
+    def __init__(self, genomes, metric, as_distance):
+        self.genomes, self.metric, self.as_distance = genomes, metric, as_distance
+        self.n = len(genomes)
+        vocab = sorted({p for g in genomes for p in g.phams})
+        self.pham_rank = {p: k for k, p in enumerate(vocab)}
+
+    def accumulate(self, part, n_parts):
+        acc = torch.zeros(self.n * (self.n + 1) // 2, dtype=torch.int64)
+        for i in range(self.n):
+            for j in range(i + 1, self.n):
+                for pham, hit, length in po.aai_best_matches(self.genomes[i], self.genomes[j]):
+                    if self.pham_rank[pham] % n_parts == part:
+                        acc[distributed.tri_offset(self.n, i) + (j - i)] += (hit << 32) | length
+        return acc
+
+    def rows(self, r0, r1, acc):
+        out = []
+        for i in range(r0, r1):
+            for j in range(i, self.n):
+                if i == j:
+                    out.append(0 if self.as_distance else 1000000)
+                    continue
+                s, t = self.genomes[i], self.genomes[j]
+                if self.metric in ("aai", "peq"):
+                    v = int(acc[distributed.tri_offset(self.n, i) + (j - i)])
+                    hit, length = v >> 32, v & 0xFFFFFFFF
+                    sim = round(hit / length, 6) if length else 0.0
+                    if self.metric == "peq":
+                        sim = po.alignment_fraction(s, t) * sim
+                    w = round(1.0 - sim, 6) if self.as_distance else round(sim, 6)
+                else:
+                    w = po.METRICS[self.metric](s, t, as_distance=self.as_distance)
+                out.append(po.round6_micro(w))
+        return torch.tensor(out, dtype=torch.int32)
+
+
+def _worker(rank, world, port, rows, metric, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        genomes = testdata.rows_to_genomes(rows, cls=Genome)
+        table = pack_genomes(genomes)
+        assert distributed.is_active()
+        got = distributed.sharded_matrix(table, metric, as_distance=True,
+                                         backend_ops=OracleOps(genomes, metric, True))
+        queue.put((rank, got.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("metric", ["gcs", "peq"])
+def test_two_rank_sharding_equals_single_rank(metric):
+    rows = testdata.genome_rows(seed=21, n_genomes=7, n_phams=10, lo=10, hi=40, paralog_p=0.3)
+    genomes = testdata.rows_to_genomes(rows, cls=Genome)
+    ops = OracleOps(genomes, metric, True)
+    acc = ops.accumulate(0, 1) if metric == "peq" else None
+    single = ops.rows(0, len(genomes), acc).tolist()
+    # and the single-rank result is the oracle's matrix
+    w = po.matrix_de_novo(genomes, po.METRICS[metric], 1)
+    assert single == [po.round6_micro(w[(i, j)]) for i in range(len(genomes))
+                      for j in range(i, len(genomes))]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rows, metric, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0] == single and results[1] == single
+
+
+def test_assemble_trims_padding():
+    n, bounds = 5, [0, 2, 5]
+    full = np.arange(15, dtype=np.int32)
+    shards = [np.concatenate((full[:9], [99, 99])), np.concatenate((full[9:], [77] * 5))]
+    assert np.array_equal(distributed.assemble(n, bounds, shards), full)

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference interface: Genome, parsers, packing,
+SymMatrix, file formats, and the C-ABI library's symbol table (no GPU calls)."""
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import testdata
+from phamclust_b200 import (Genome, SymMatrix, load_genomes_from_fasta_dir,
+                            load_genomes_from_tsv, matrix_from_adjacency,
+                            matrix_from_squareform, matrix_to_adjacency, matrix_to_squareform,
+                            pack_genomes)
+from phamclust_b200 import _native, distributed, metrics
+from phamclust_b200.matrix import _outside_in_index_iterator, matrix_de_novo
+from phamclust_b200.packing import unpack_genomes
+
+
+# ----------------------------------------------------------------------------- library
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "phamclust_b200.h").read_text()
+    declared = set(re.findall(r"^\s*(?:int|void|const char \*)\s*\**(pc_\w+)\s*\(", header, re.M))
+    assert declared == set(_native.EXPORTS)
+    lib = ctypes.CDLL(str(_native.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pc_version() >= 100
+
+
+def test_product_path_never_imports_the_oracle():
+    for path in (ROOT / "phamclust_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, path
+
+
+# ----------------------------------------------------------------------------- genome
+def test_genome_api():
+    g, h = Genome("g"), Genome("h")
+    for p, t in (("p1", "MKT"), ("p1", "MKTAA"), ("p2", "MKT")):
+        g.add(p, t)
+    h.add("p2", "MKTW")
+    h.add("p3")
+    assert len(g) == 3 and len(g.phams) == 2 and g["p1"] == ["MKT", "MKTAA"]
+    assert g & h == {"p2"} and g | h == {"p1", "p2", "p3"} and g - h == {"p1"}
+    assert g ^ h == {"p1", "p3"} and g.intersection(h) == {"p2"} and h["p3"] == ["M"]
+    assert "p1" in g and "zz" not in g and h < g
+    assert str(g) == ">name=g|pham=p1|n=1\nMKT\n>name=g|pham=p1|n=2\nMKTAA\n>name=g|pham=p2|n=1\nMKT\n"
+    with pytest.raises(TypeError):
+        g.add(1, "M")
+    with pytest.raises(TypeError):
+        g.add("p", 3)
+    with pytest.raises(KeyError):
+        g["nope"]
+    with pytest.raises(TypeError):
+        g & "h"
+    assert g.pop("nope") is None and g.pop("p2") == ["MKT"]
+
+
+def test_genome_matches_reference_class(reference):
+    rows = testdata.genome_rows(seed=5, n_genomes=4, n_phams=6)
+    mine = testdata.rows_to_genomes(rows, cls=Genome)
+    theirs = testdata.rows_to_genomes(rows, cls=reference.genome.Genome)
+    for a, b in zip(mine, theirs):
+        assert str(a) == str(b) and len(a) == len(b) and a.phams == b.phams
+    assert (mine[0] & mine[1]) == (theirs[0] & theirs[1])
+
+
+def test_parsers(tmp_path):
+    tsv = tmp_path / "in.tsv"
+    tsv.write_text("a\tp1\tMKT\na\tp1\tMKTAA\nb\tp2\nb\tp3\t\na\tp2\tMKT\n")
+    genomes = load_genomes_from_tsv(tsv)
+    assert [g.name for g in genomes] == ["a", "b"]
+    assert genomes[0].phams == {"p1": ["MKT", "MKTAA"], "p2": ["MKT"]}
+    assert genomes[1].phams == {"p2": ["M"], "p3": ["M"]}       # rstrip eats the empty column
+    bad = tmp_path / "bad.tsv"
+    bad.write_text("a\tb\tc\td\n")
+    with pytest.raises(ValueError):
+        load_genomes_from_tsv(bad)
+    d = tmp_path / "fa"
+    d.mkdir()
+    genomes[0].save(d / "a.fasta")
+    (d / "b.faa").write_text(">name=b|pham=p9|n=1\nMK\nTW\n")
+    (d / "notes.txt").write_text("skip me")
+    loaded = {g.name: g for g in load_genomes_from_fasta_dir(d)}
+    assert loaded["a"].phams == genomes[0].phams and loaded["b"].phams == {"p9": ["MKTW"]}
+    (d / "a.fa").write_text(">name=a|pham=p1|n=1\nM\n")
+    with pytest.raises(ValueError):
+        load_genomes_from_fasta_dir(d)
+
+
+def test_parsers_match_reference(reference, tmp_path):
+    import importlib
+    rows = testdata.genome_rows(seed=8, n_genomes=5, n_phams=7)
+    tsv = tmp_path / "in.tsv"
+    tsv.write_text("".join(f"{a}\t{b}\t{c}\n" for a, b, c in rows))
+    mine = load_genomes_from_tsv(tsv)
+    theirs = testdata.rows_to_genomes(rows, cls=reference.genome.Genome)
+    assert [str(g) for g in mine] == [str(g) for g in theirs]
+
+
+# ----------------------------------------------------------------------------- packing
+def test_pack_round_trip():
+    rows = testdata.genome_rows(seed=3, n_genomes=7, n_phams=9, paralog_p=0.5)
+    genomes = testdata.rows_to_genomes(rows, cls=Genome)
+    t = pack_genomes(genomes)
+    assert t.n_genomes == 7 and t.n_genes == sum(len(g) for g in genomes)
+    assert int(t.len_sum.sum()) == sum(len(s) for g in genomes for v in g.phams.values() for s in v)
+    back = unpack_genomes(t)
+    assert [g.phams for g in back] == [g.phams for g in genomes]
+    sub = t.subset(3)
+    assert [g.phams for g in unpack_genomes(sub)] == [g.phams for g in genomes[:3]]
+
+
+def test_synthetic_tables_are_deterministic_and_consistent():
+    from phamclust_b200 import synthetic
+    a = synthetic.phage_table(100, seed=42)
+    b = synthetic.phage_table(100, seed=42)
+    assert np.array_equal(a.residues, b.residues) and np.array_equal(a.pham_id, b.pham_id)
+    lens = np.diff(a.seq_off)
+    entry = np.repeat(np.arange(len(a.pham_id)), a.copies)
+    assert np.array_equal(np.bincount(entry, weights=lens, minlength=len(a.pham_id)).astype(np.uint32),
+                          a.len_sum)
+    assert lens.min() >= 10 and lens.max() <= 1600 and a.copies.max() <= 3
+    s = synthetic.sparse_table(300, 3000, seed=1, clusters=10)
+    for g in range(300):
+        ids = s.pham_id[s.genome_ptr[g]:s.genome_ptr[g + 1]]
+        assert len(set(ids.tolist())) == len(ids) and 20 <= len(ids) <= 300
+
+
+# ----------------------------------------------------------------------------- SymMatrix
+def _filled(cls, names, is_distance, seed=0):
+    rng = np.random.default_rng(seed)
+    m = cls(list(names), is_distance=is_distance)
+    for i, a in enumerate(names):
+        m.set_weight(a, a, 0.0 if is_distance else 1.0)
+        for b in names[i + 1:]:
+            m.set_weight(a, b, float(rng.integers(0, 1000001)) / 1e6 + 4e-7 * (rng.random() < 0.3))
+    return m
+
+
+def test_symmatrix_behaves_like_the_reference(reference):
+    names = ["zeta", "alpha", "mu", "beta", "omega", "chi"]
+    for is_distance in (True, False):
+        mine = _filled(SymMatrix, names, is_distance, seed=4)
+        ref = _filled(reference.matrix.SymMatrix, names, is_distance, seed=4)
+        assert list(mine) == list(ref)
+        assert [r for r in mine.iterrows()] == [r for r in ref.iterrows()]
+        assert np.array_equal(mine.to_ndarray(), ref.to_ndarray())
+        assert mine.medoid == ref.medoid and mine.anti_medoid == ref.anti_medoid
+        assert mine.statistics == pytest.approx(ref.statistics)
+        if is_distance:
+            assert mine.diameter == ref.diameter
+            assert np.array_equal(mine.to_ndarray(condensed=True), ref.to_ndarray(condensed=True))
+        assert mine.nearest_neighbors("mu", 0.5) == ref.nearest_neighbors("mu", 0.5)
+        assert mine["beta"] == ref["beta"] and str(mine) == str(ref)
+        sub_m, sub_r = mine.extract_submatrix(["omega", "alpha", "mu"]), \
+            ref.extract_submatrix(["omega", "alpha", "mu"])
+        assert list(sub_m) == list(sub_r)
+        mine.reorder()
+        ref.reorder()
+        assert mine.nodes == ref.nodes and list(mine) == list(ref)
+        mine.invert()
+        ref.invert()
+        assert list(mine) == list(ref) and mine.is_distance == ref.is_distance
+        mine.reorder(names[::-1])
+        ref.reorder(names[::-1])
+        assert np.array_equal(mine.to_ndarray(), ref.to_ndarray())
+        data = {n: 0.25 for n in names}
+        data["new"] = 0.0 if mine.is_distance else 1.0
+        mine.append_node("new", dict(data))
+        ref.append_node("new", dict(data))
+        assert list(mine) == list(ref)
+
+
+def test_symmatrix_errors_and_rounding():
+    m = SymMatrix(["a", "b"], is_distance=True)
+    assert m.get_weight("a", "b") is None
+    m.set_weight("b", "a", 0.1234565)
+    assert m.get_weight("a", "b") == round(0.1234565, 6)
+    with pytest.raises(ValueError):
+        m.set_weight("a", "b", 1.5)
+    with pytest.raises(KeyError):
+        m.get_weight("a", "zz")
+    with pytest.raises(TypeError):
+        3 in m
+    m.lock()
+    with pytest.raises(AttributeError):
+        m.set_weight("a", "b", 0.5)
+    m.unlock()
+    assert not m.is_locked() and len(m) == 2 and m < SymMatrix(["x", "y", "z"])
+    s = SymMatrix(["a"], is_distance=False)
+    with pytest.raises(ValueError):
+        s.diameter
+
+
+def test_from_micro_and_file_formats(tmp_path):
+    names = ["n3", "n1", "n2"]
+    micro = np.array([0, 250000, 1000000, 0, 428571, 0], dtype=np.int32)
+    m = SymMatrix.from_micro(names, micro, is_distance=True)
+    assert m.get_weight("n2", "n1") == 0.428571 and m.get_weight("n3", "n2") == 1.0
+    lower = matrix_to_squareform(m, tmp_path / "lower.tsv", lower_triangle=True)
+    assert pathlib.Path(lower).read_text() == \
+        "3\nn3\t0.000000\nn1\t0.250000\t0.000000\nn2\t1.000000\t0.428571\t0.000000\n"
+    assert list(matrix_from_squareform(lower)) == list(m)
+    square = matrix_to_squareform(m, tmp_path / "square.tsv")
+    assert list(matrix_from_squareform(square)) == list(m)
+    adj = matrix_to_adjacency(m, tmp_path / "adj.tsv")
+    assert list(matrix_from_adjacency(adj)) == list(m)
+    with pytest.raises(ValueError):
+        SymMatrix.from_micro(names, micro[:-1], True)
+
+
+def test_file_formats_match_reference_bytes(reference, tmp_path):
+    names = ["zeta", "alpha", "mu", "beta"]
+    mine = _filled(SymMatrix, names, True, seed=9)
+    ref = _filled(reference.matrix.SymMatrix, names, True, seed=9)
+    for lower in (True, False):
+        a = matrix_to_squareform(mine, tmp_path / "a.tsv", lower_triangle=lower)
+        b = reference.matrix.matrix_to_squareform(ref, tmp_path / "b.tsv", lower_triangle=lower)
+        assert pathlib.Path(a).read_bytes() == pathlib.Path(b).read_bytes()
+    a = matrix_to_adjacency(mine, tmp_path / "a.adj", skip_zero=True)
+    b = reference.matrix.matrix_to_adjacency(ref, tmp_path / "b.adj", skip_zero=True)
+    assert pathlib.Path(a).read_bytes() == pathlib.Path(b).read_bytes()
+
+
+def test_clustering_on_golden_matrix_gives_golden_partitions():
+    """The unchanged host clustering on a SymMatrix built from the reference's
+    own weights must reproduce the reference's partitions."""
+    from phamclust_b200.clustering import hierarchical_clustering
+    for dataset, golden in load_golden("matrices.json").items():
+        for key in ("gcs", "peq"):
+            m = SymMatrix.from_micro(golden["names"], np.array(golden["distance"][key], np.int32), True)
+            for spec, expect in golden["clusters"][key].items():
+                linkage, eps = spec.split(":")
+                got = hierarchical_clustering(m, linkage, eps=float(eps))
+                assert sorted(sorted(c.nodes) for c in got) == expect
+                sizes = [len(c) for c in got]
+                assert sizes == sorted(sizes, reverse=True)
+
+
+# ----------------------------------------------------------------------------- matrix_de_novo (host logic)
+def test_outside_in_index_iterator():
+    assert list(_outside_in_index_iterator(5)) == [0, 4, 1, 3, 2]
+    assert list(_outside_in_index_iterator(4)) == [0, 3, 1, 2]
+    assert list(_outside_in_index_iterator(0)) == [] and list(_outside_in_index_iterator(1)) == [0]
+
+
+def test_matrix_de_novo_argument_errors():
+    with pytest.raises(ValueError):
+        matrix_de_novo([], metrics.gene_content_similarity, 1)
+    with pytest.raises(TypeError):
+        matrix_de_novo([Genome("a")], lambda s, t, as_distance=False: 0.0, 1)
+    assert metrics.metric_key(metrics.METRICS["peq"]) == "peq"
+    assert metrics.metric_key("jc") == "jc" and metrics.metric_key(print) is None
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    ok = True
+    try:
+        ctx = _native.Context(0)
+        ctx.close()
+    except RuntimeError as exc:
+        ok = False
+        assert "no CPU fallback" in str(exc) or "sm_" in str(exc)
+    if not ok:
+        with pytest.raises(RuntimeError):
+            metrics.gene_content_similarity(Genome("a"), Genome("b"))
+
+
+# ----------------------------------------------------------------------------- sharding arithmetic
+def test_row_partition_balances_pairs():
+    for n in (1, 2, 7, 100, 2001):
+        for world in (1, 2, 3, 8):
+            b = distributed.row_partition(n, world)
+            assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+            sizes = [distributed.tri_offset(n, b[r + 1]) - distributed.tri_offset(n, b[r])
+                     for r in range(world)]
+            assert sum(sizes) == n * (n + 1) // 2
+            if n >= 100:
+                assert max(sizes) - min(sizes) <= 2 * n
