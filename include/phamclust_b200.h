@@ -179,9 +179,14 @@ enum {
     PC_T_GATHER = 4,    /* best-match gather into pair accumulators         */
     PC_T_EPILOGUE = 5,  /* standalone normalise/round kernels               */
     PC_T_D2H = 6,       /* device -> host copy of the result                */
-    PC_T_COUNT = 7
+    PC_T_HOST_TABLE = 7,/* host wall-clock inside pc_load_table             */
+    PC_T_HOST_SEQS = 8, /* host wall-clock inside pc_load_sequences         */
+    PC_T_HOST_PLAN = 9, /* host wall-clock planning the alignment work      */
+    PC_T_COUNT = 10
 };
-/* CUDA-event milliseconds per stage accumulated since pc_reset_counters.   */
+/* Milliseconds per stage accumulated since pc_reset_counters: CUDA events on
+ * the ctx stream for the device stages, wall clock for the PC_T_HOST_* ones
+ * (which CONTAIN the device stages issued from inside them).                */
 int pc_timings(pc_ctx *ctx, double *ms, int n);
 /* kernels launched / DP cells updated / alignments run since the reset.    */
 int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,

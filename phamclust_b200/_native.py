@@ -13,7 +13,8 @@ LIB_PATH = _HERE / "libphamclust_b200.so"
 
 METRIC_IDS = {"gcs": 0, "jc": 1, "pocp": 2, "af": 3, "aai": 4, "peq": 5}
 ENGINE_IDS = {"auto": 0, "popc": 1, "i8mma": 2}
-STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h")
+STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h",
+          "host_table", "host_seqs", "host_plan")
 
 EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_stream",
            "pc_set_engine", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",

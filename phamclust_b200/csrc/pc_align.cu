@@ -5,27 +5,36 @@
 // One SUBGROUP of G lanes per alignment (32/G alignments per warp).  Lane l
 // owns K consecutive columns of the ref sequence (s2) in registers and walks
 // down the query (s1) rows one step behind lane l-1 (systolic anti-diagonal);
-// the right-most column's (H, E, cH, cE) travels to the next lane by
-// __shfl_up.  Per cell the recurrences are exactly SURVEY.md Appendix A:
+// the right-most column's state travels to the next lane by __shfl_up.  Per
+// cell the recurrences are exactly SURVEY.md Appendix A:
 //
 //   F = max(H[i-1][j]-open, F[i-1][j]-ext)   open wins only if strictly greater
 //   E = max(H[i][j-1]-open, E[i][j-1]-ext)   (PC_GAP_TIE_EXTENDS)
 //   H = max(Hd, F, E), source priority diag > F > E (PC_H_PRIORITY_DIAG_DEL_INS)
 //
-// and a packed counter c = (matched << 16) | columns rides with each state,
-// selected by the same predicates that parasail's trace bits record, so
-// cH[m][n] equals what the explicit traceback would count -- O(len) state, no
-// trace table (the oracle checks this formulation against the explicit
-// traceback).  The substitution table lives in shared memory as int2
-// {score, 1 + (hit << 16)} so one LDS.64 yields both addends.
+// and a packed counter (matched << 16) + columns rides with each state,
+// selected by the same predicates that parasail's trace bits record, so the
+// counter of H[m][n] equals what the explicit traceback would count -- O(len)
+// state, no trace table (the oracle checks this formulation against the
+// explicit traceback).
 //
-// Integer-issue bound (~21 ALU instructions per cell); traffic is la+lb bytes
-// in, 4-8 bytes out per alignment.
+// Instruction diet (the kernel is integer-issue bound, ncu r1: 87 % issue
+// active; see DESIGN.md "K4"):
+//   * state is kept as X = H - open and Y = X + ext, so the open branch of both
+//     gap states is a plain register and  F = VIADDMNMX(Fup, -ext, Xup);
+//   * counters are stored RELATIVE to (i + j): gap steps then add nothing and a
+//     diagonal step adds (hit << 16) - 1, which comes out of the table; the
+//     true counter is recovered once at the end as d + (m + n);
+//   * the substitution table is int2 {score + open, (hit << 16) - 1}: one
+//     LDS.64 yields both addends.  In the usual case (<= 24 residue codes) it
+//     is replicated once per lane ([24*24][32] int2 = 144 KB) so lane L only
+//     ever touches bank pair L: no bank conflicts (r1 lost 2/3 of the LSU
+//     wavefronts to conflicts on a shared 8 KB table).
 #include "pc_common.cuh"
 
-#define NW_THREADS 128
-
-const int pc_nw_bucket_cap[PC_NW_BUCKETS] = {32, 64, 96, 128, 192, 256, 384, 512, 1 << 30};
+// v2 bucket table: ref columns handled in one pass by each kernel config
+const int pc_nw_bucket_cap[PC_NW_BUCKETS] = {32, 64, 96, 128, 192, 256, 384, 512,
+                                             640, 768, 1024, 1 << 30};
 
 int pc_nw_bucket_of(int ref_len)
 {
@@ -34,22 +43,39 @@ int pc_nw_bucket_of(int ref_len)
     return PC_NW_BUCKETS - 1;
 }
 
-template <int G, int K, bool MULTI>
-__global__ void __launch_bounds__(NW_THREADS) nw_kernel(const NwArgs a)
+#define NW_TAB_CODES 24       // codes of the replicated fast-path table
+
+template <int G, int K, bool MULTI, bool REPL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 {
-    __shared__ int2 s_tab[32 * 32];
-    for (int x = threadIdx.x; x < 32 * 32; x += NW_THREADS) s_tab[x] = a.subtab[x];
+    extern __shared__ __align__(16) int2 s_tab[];
+    const int lane = threadIdx.x & 31;
+    const int open = a.gap_open, ext = a.gap_extend;
+    if (REPL) {
+        // s_tab[(q*24 + r)*32 + lane] = {score(q,r) + open, (hit << 16) - 1}
+        for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
+            const int e = x >> 5;
+            const int2 v = a.subtab[(e / NW_TAB_CODES) * 32 + (e % NW_TAB_CODES)];
+            s_tab[x] = make_int2(v.x + open, v.y - 2);
+        }
+    } else {
+        for (int x = threadIdx.x; x < 32 * 32; x += THREADS) {
+            const int2 v = a.subtab[x];
+            s_tab[x] = make_int2(v.x + open, v.y - 2);
+        }
+    }
     __syncthreads();
 
     constexpr int SUBS = 32 / G;
     constexpr int CAP = G * K;
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    constexpr int QSTRIDE = REPL ? NW_TAB_CODES * 32 : 32;   // int2 elements per query code
+    constexpr int RSHIFT = REPL ? 5 : 0;                     // ref code -> element offset
     const int sub = lane / G;
     const int sl = lane % G;
-    const int open = a.gap_open, ext = a.gap_extend;
-    const int64_t warp_id = ((int64_t)blockIdx.x * NW_THREADS + threadIdx.x) >> 5;
+    const int64_t warp_id = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
     int4 *spill = MULTI ? a.spill + warp_id * a.spill_stride : nullptr;
+    const int2 *tab_lane = REPL ? s_tab + lane : s_tab;
 
     for (;;) {
         unsigned long long base = 0;
@@ -78,31 +104,37 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(const NwArgs a)
         // warp-uniform trip count (subgroups of one warp run in lock step)
         const int steps = __reduce_max_sync(FULL, m) + G - 1;
 
-        int res_h = 0, res_c = 0;   // valid on the owner lane after the last chunk
+        int res_x = 0, res_c = 0;   // valid on the owner lane after the last chunk
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int col0 = chunk * CAP + sl * K;   // 0-based first column of this lane
-            int Hp[K], Fp[K], cHp[K], cFp[K], rc[K];
+            // per column: X = H - open, Y = X + ext, F, and the relative counters
+            int Xp[K], Yp[K], Fp[K], cHp[K], cFp[K], rc[K];
             // ref residues: K multiple of 4 and genes 16B aligned -> word loads
 #pragma unroll
             for (int w = 0; w < K / 4; ++w) {
                 const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(r + col0) + w);
 #pragma unroll
-                for (int b = 0; b < 4; ++b) rc[4 * w + b] = (int)((word >> (8 * b)) & 31u);
+                for (int b = 0; b < 4; ++b) {
+                    int code = (int)((word >> (8 * b)) & 31u);
+                    if (REPL && code >= NW_TAB_CODES) code = 0;   // padding past the gene only
+                    rc[4 * w + b] = code << RSHIFT;
+                }
             }
 #pragma unroll
             for (int x = 0; x < K; ++x) {
                 const int j = col0 + x + 1;          // 1-based column
-                Hp[x] = -open - (j - 1) * ext;       // H[0][j]
+                Xp[x] = -open - (j - 1) * ext - open;   // H[0][j] - open
+                Yp[x] = Xp[x] + ext;
                 Fp[x] = PC_NEG_INF;                  // F[0][j]
-                cHp[x] = j;                          // cH[0][j] = (0, j)
+                cHp[x] = 0;                          // cH[0][j] = (0, j)  -> relative 0
                 cFp[x] = 0;
             }
-            int diagH = (col0 == 0) ? 0 : -open - (col0 - 1) * ext;   // H[0][col0]
-            int diagC = col0;
-            int outH = 0, outE = PC_NEG_INF, outcH = 0, outcE = 0;
+            int diagX = ((col0 == 0) ? 0 : -open - (col0 - 1) * ext) - open;   // H[0][col0] - open
+            int diagC = 0;
+            int outX = 0, outE = PC_NEG_INF, outcH = 0, outcE = 0;
 
             for (int s = 1; s <= steps; ++s) {
-                int inH = __shfl_up_sync(FULL, outH, 1, G);
+                int inX = __shfl_up_sync(FULL, outX, 1, G);
                 int inE = __shfl_up_sync(FULL, outE, 1, G);
                 int incH = __shfl_up_sync(FULL, outcH, 1, G);
                 int incE = __shfl_up_sync(FULL, outcE, 1, G);
@@ -110,51 +142,56 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(const NwArgs a)
                 const bool active = (i >= 1) && (i <= m);
                 if (sl == 0) {
                     if (!MULTI || chunk == 0) {
-                        inH = -open - (i - 1) * ext; // H[i][0]
+                        inX = -open - (i - 1) * ext - open;   // H[i][0] - open
                         inE = PC_NEG_INF;
-                        incH = i;                    // cH[i][0] = (0, i)
+                        incH = 0;                    // cH[i][0] = (0, i) -> relative 0
                         incE = 0;
                     } else if (active) {
                         const int4 v = __ldcg(spill + i);
-                        inH = v.x; inE = v.y; incH = v.z; incE = v.w;
+                        inX = v.x; inE = v.y; incH = v.z; incE = v.w;
                     }
                 }
                 if (active) {
-                    const int qc = (int)(__ldg(q + (i - 1)) & 31u);
-                    const int2 *trow = s_tab + qc * 32;
-                    int hl = inH, el = inE, cl = incH, ce = incE;
-                    int hd = diagH, cd = diagC;
-                    diagH = inH;
+                    int qc = (int)(__ldg(q + (i - 1)) & 31u);
+                    if (REPL && qc >= NW_TAB_CODES) qc = 0;
+                    const int2 *trow = tab_lane + qc * QSTRIDE;
+                    int xl = inX, yl = inX + ext, el = inE, cl = incH, ce = incE;
+                    int xd = diagX, cd = diagC;
+                    diagX = inX;
                     diagC = incH;
 #pragma unroll
                     for (int x = 0; x < K; ++x) {
-                        const int2 sc = trow[rc[x]];
-                        const int fo = Hp[x] - open, fe = Fp[x] - ext;
-                        const int eo = hl - open, ee = el - ext;
+                        const int2 sc = trow[rc[x]];         // {score + open, (hit<<16) - 1}
+                        // F: from above.  open branch = X[i-1][j]; strict > means ties extend
 #if PC_GAP_TIE_EXTENDS
-                        const bool pf = fo > fe, pe = eo > ee;
+                        const bool pf = Yp[x] > Fp[x];       // H-open > F-ext
+                        const bool pe = yl > el;
 #else
-                        const bool pf = fo >= fe, pe = eo >= ee;
+                        const bool pf = Yp[x] >= Fp[x];
+                        const bool pe = yl >= el;
 #endif
-                        const int f = max(fo, fe);
-                        const int e = max(eo, ee);
-                        const int cf = (pf ? cHp[x] : cFp[x]) + 1;
-                        const int cee = (pe ? cl : ce) + 1;
-                        const int hdg = hd + sc.x;
-                        const int h = max(hdg, max(f, e));
+                        const int f = __viaddmax_s32(Fp[x], -ext, Xp[x]);
+                        const int e = __viaddmax_s32(el, -ext, xl);
+                        const int cf = pf ? cHp[x] : cFp[x];
+                        const int cee = pe ? cl : ce;
+                        const int hdg = xd + sc.x;           // H[i-1][j-1] + score
+                        const int cdg = cd + sc.y;
+                        const int h = __vimax3_s32(hdg, f, e);
 #if PC_H_PRIORITY_DIAG_DEL_INS
-                        const int ch = (h == hdg) ? cd + sc.y : (h == f) ? cf : cee;
+                        const int ch = (h == hdg) ? cdg : (h == f) ? cf : cee;
 #else
-                        const int ch = (h == hdg) ? cd + sc.y : (h == e) ? cee : cf;
+                        const int ch = (h == hdg) ? cdg : (h == e) ? cee : cf;
 #endif
-                        hd = Hp[x];
+                        xd = Xp[x];
                         cd = cHp[x];
-                        Hp[x] = h; Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
-                        hl = h; el = e; cl = ch; ce = cee;
+                        xl = h - open;
+                        yl = h - (open - ext);
+                        Xp[x] = xl; Yp[x] = yl; Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
+                        el = e; cl = ch; ce = cee;
                     }
-                    outH = hl; outE = el; outcH = cl; outcE = ce;
+                    outX = xl; outE = el; outcH = cl; outcE = ce;
                     if (MULTI && sl == G - 1 && chunk + 1 < nchunks)
-                        __stcg(spill + i, make_int4(outH, outE, outcH, outcE));
+                        __stcg(spill + i, make_int4(outX, outE, outcH, outcE));
                 }
             }
             if (MULTI) __syncwarp();
@@ -164,70 +201,82 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(const NwArgs a)
                     const int xs = last % K;
 #pragma unroll
                     for (int x = 0; x < K; ++x)
-                        if (x == xs) { res_h = Hp[x]; res_c = cHp[x]; }
+                        if (x == xs) { res_x = Xp[x]; res_c = cHp[x]; }
                 }
             }
         }
         if (valid) {
             bool owner;
+            int score, counter;
             if (n == 0) {            // no DP columns: the answer is a boundary cell
                 owner = (sl == 0);
-                res_h = (m == 0) ? 0 : -open - (m - 1) * ext;
-                res_c = m;
+                score = (m == 0) ? 0 : -open - (m - 1) * ext;
+                counter = m;
             } else {
                 owner = (sl == ((n - 1) % CAP) / K);
+                score = res_x + open;
+                counter = res_c + (m + n);          // undo the (i + j) normalisation
             }
             if (owner) {
-                a.out_hitlen[slot] = (uint32_t)res_c;
-                if (a.out_score) a.out_score[slot] = res_h;
+                a.out_hitlen[slot] = (uint32_t)counter;
+                if (a.out_score) a.out_score[slot] = score;
             }
         }
     }
 }
 
-template <int G, int K, bool MULTI>
-static int launch_one(pc_ctx *ctx, const NwArgs &args)
+template <int G, int K, bool MULTI, bool REPL, int THREADS>
+static int launch_cfg(pc_ctx *ctx, const NwArgs &args)
 {
+    const size_t smem = REPL ? (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int2)
+                             : (size_t)32 * 32 * sizeof(int2);
+    auto kern = nw_kernel<G, K, MULTI, REPL, THREADS>;
+    PC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
-    PC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                     &blocks_per_sm, nw_kernel<G, K, MULTI>, NW_THREADS, 0));
+    PC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    int64_t groups = (args.n_tasks + (32 / G) - 1) / (32 / G);
-    int64_t want = (groups + (NW_THREADS / 32) - 1) / (NW_THREADS / 32);
-    int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;   // persistent: one resident wave
+    const int64_t groups = (args.n_tasks + (32 / G) - 1) / (32 / G);
+    const int64_t want = (groups + (THREADS / 32) - 1) / (THREADS / 32);
+    const int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;   // persistent: one resident wave
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    nw_kernel<G, K, MULTI><<<grid, NW_THREADS, 0, ctx->stream>>>(args);
+    kern<<<grid, THREADS, smem, ctx->stream>>>(args);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     ctx->align_launches++;
     return PC_OK;
 }
 
-// number of warps a launch of the multi-chunk config can have resident
+template <int G, int K, bool MULTI, int THREADS>
+static int launch_one(pc_ctx *ctx, const NwArgs &args, bool repl)
+{
+    return repl ? launch_cfg<G, K, MULTI, true, THREADS>(ctx, args)
+                : launch_cfg<G, K, MULTI, false, THREADS>(ctx, args);
+}
+
+// upper bound on the warps a launch of the multi-chunk config keeps resident
 int pc_nw_multichunk_warps(pc_ctx *ctx)
 {
-    int blocks_per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &blocks_per_sm, nw_kernel<32, 16, true>, NW_THREADS, 0) != cudaSuccess)
-        blocks_per_sm = 16;
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    return ctx->sm_count * blocks_per_sm * (NW_THREADS / 32);
+    return ctx->sm_count * 8 * 2;      // 256-thread blocks, at most 2 per SM
 }
 
 int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int bucket)
 {
     if (args.n_tasks <= 0) return PC_OK;
+    const bool repl = ctx->n_codes <= NW_TAB_CODES;
     switch (bucket) {
-    case 0: return launch_one<4, 8, false>(ctx, args);
-    case 1: return launch_one<8, 8, false>(ctx, args);
-    case 2: return launch_one<8, 12, false>(ctx, args);
-    case 3: return launch_one<8, 16, false>(ctx, args);
-    case 4: return launch_one<16, 12, false>(ctx, args);
-    case 5: return launch_one<16, 16, false>(ctx, args);
-    case 6: return launch_one<32, 12, false>(ctx, args);
-    case 7: return launch_one<32, 16, false>(ctx, args);
-    case 8: return launch_one<32, 16, true>(ctx, args);
+    case 0: return launch_one<4, 8, false, 384>(ctx, args, repl);
+    case 1: return launch_one<8, 8, false, 384>(ctx, args, repl);
+    case 2: return launch_one<8, 12, false, 384>(ctx, args, repl);
+    case 3: return launch_one<8, 16, false, 384>(ctx, args, repl);
+    case 4: return launch_one<16, 12, false, 384>(ctx, args, repl);
+    case 5: return launch_one<16, 16, false, 384>(ctx, args, repl);
+    case 6: return launch_one<32, 12, false, 384>(ctx, args, repl);
+    case 7: return launch_one<32, 16, false, 384>(ctx, args, repl);
+    case 8: return launch_one<32, 20, false, 256>(ctx, args, repl);
+    case 9: return launch_one<32, 24, false, 256>(ctx, args, repl);
+    case 10: return launch_one<32, 32, false, 256>(ctx, args, repl);
+    case 11: return launch_one<32, 32, true, 256>(ctx, args, repl);
     }
     return pc_fail(ctx, PC_EINVAL, "bad NW bucket %d", bucket);
 }

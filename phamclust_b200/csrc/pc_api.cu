@@ -7,12 +7,23 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <chrono>
 
 #include "pc_common.cuh"
 
 int pc_nw_multichunk_warps(pc_ctx *ctx);
 
 static thread_local std::string g_init_error;
+
+struct HostTimer {
+    pc_ctx *ctx; int stage;
+    std::chrono::steady_clock::time_point t0;
+    HostTimer(pc_ctx *c, int s) : ctx(c), stage(s), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() {
+        ctx->stage_ms[stage] += std::chrono::duration<double, std::milli>(
+            std::chrono::steady_clock::now() - t0).count();
+    }
+};
 
 int pc_fail(pc_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -229,6 +240,7 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
                              const uint32_t *copies, const uint32_t *len_sum)
 {
     PC_ENTER(ctx);
+    HostTimer host_timer(ctx, PC_T_HOST_TABLE);
     if (n_genomes <= 0)   // matrix.py:451-452
         return pc_fail(ctx, PC_EINVAL, "need at least 1 genome to construct matrix de novo");
     if (n_phams < 0 || !genome_ptr)
@@ -346,6 +358,7 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
                                  const uint8_t *residues)
 {
     PC_ENTER(ctx);
+    HostTimer host_timer(ctx, PC_T_HOST_SEQS);
     if (!ctx->have_table) return pc_fail(ctx, PC_ESTATE, "pc_load_sequences needs pc_load_table first");
     if (n_genes != ctx->n_genes_total)
         return pc_fail(ctx, PC_EINVAL, "got %lld genes but the table's copies sum to %lld",
@@ -550,6 +563,7 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
 {
     AlignPlan &pl = ctx->plan;
     if (pl.part == part && pl.n_parts == n_parts) return PC_OK;
+    HostTimer host_timer(ctx, PC_T_HOST_PLAN);
     struct PhamInfo { int64_t pham; int bucket; double cost; };
     std::vector<PhamInfo> infos;
     for (int64_t p = 0; p < ctx->P; ++p) {

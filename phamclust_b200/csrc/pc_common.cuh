@@ -198,7 +198,7 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
 
 // NW bucket table: capacity (ref columns per pass) of each kernel config
-#define PC_NW_BUCKETS 9
+#define PC_NW_BUCKETS 12
 extern const int pc_nw_bucket_cap[PC_NW_BUCKETS];
 int pc_nw_bucket_of(int ref_len);
 
