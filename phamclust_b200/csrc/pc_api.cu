@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <chrono>
 
@@ -14,6 +15,16 @@
 int pc_nw_multichunk_warps(pc_ctx *ctx);
 
 static thread_local std::string g_init_error;
+
+static void dbg_mark(const char *what)
+{
+    static const bool on = getenv("PC_DEBUG") != nullptr;
+    static auto last = std::chrono::steady_clock::now();
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pc] %-28s +%.2f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
 
 struct HostTimer {
     pc_ctx *ctx; int stage;
@@ -179,7 +190,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_copies, &ctx->d_len_sum,
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
                       &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_codes,
-                      &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_subtab[0],
+                      &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_subtab[0],
                       &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
                       &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
                       &ctx->d_acc, &ctx->d_out};
@@ -367,6 +378,7 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     const int64_t total = seq_off[n_genes];
     if (total > 0 && !residues) return pc_fail(ctx, PC_EINVAL, "residues is NULL");
 
+    dbg_mark("seqs: enter");
     std::vector<int32_t> gene_len(n_genes);
     std::vector<int64_t> gene_off(n_genes + 1);
     int64_t cursor = 0;
@@ -393,6 +405,7 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
                            (long long)e, ctx->h_len_sum[e], (long long)s);
     }
 
+    dbg_mark("seqs: lengths validated");
     // residue codes: one per distinct character after case folding (U5); the
     // 24 matrix letters keep their matrix index, anything else maps to '*' (U6)
     bool present[256] = {false};
@@ -429,13 +442,14 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
             ctx->code_of_byte[folded] = ctx->n_codes;
         ctx->n_codes++;
     }
+    dbg_mark("seqs: alphabet scanned");
     uint8_t lut[256];
     for (int c = 0; c < 256; ++c) lut[c] = (uint8_t)(ctx->code_of_byte[c] < 0 ? 23 : ctx->code_of_byte[c]);
 
     ctx->n_genes = n_genes;
     ctx->h_gene_len.swap(gene_len);
 
-    DevBuf d_raw_off, d_lut;
+    DevBuf &d_raw_off = ctx->d_raw_off, &d_lut = ctx->d_lut;
     int rc = PC_OK;
     do {
         if ((rc = pc_stage_begin(ctx, PC_T_H2D))) break;
@@ -453,6 +467,7 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
         }
         if (rc) break;
         if ((rc = pc_stage_end(ctx))) break;
+        dbg_mark("seqs: uploads queued");
         // + tail padding: lanes read whole K-column words past the last gene
         if ((rc = devbuf_reserve(ctx, ctx->d_codes, (size_t)cursor + 1024))) break;
         if (cudaMemsetAsync(ctx->d_codes.p, 0, (size_t)cursor + 1024, ctx->stream) != cudaSuccess) {
@@ -464,12 +479,12 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
                                    ctx->d_gene_off.as<int64_t>(), ctx->d_gene_len.as<int32_t>(),
                                    d_lut.as<uint8_t>(), n_genes, ctx->d_codes.as<uint8_t>()))) break;
         if ((rc = pc_stage_end(ctx))) break;
+        dbg_mark("seqs: encode queued");
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             rc = pc_fail(ctx, PC_ECUDA, "encode kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     } while (0);
-    devbuf_free(d_raw_off);
-    devbuf_free(d_lut);
     if (rc) return rc;
+    dbg_mark("seqs: synced");
     ctx->plan.part = ctx->plan.n_parts = -1;
     ctx->have_seqs = true;
     return PC_OK;
@@ -543,7 +558,9 @@ static int contract_rows(pc_ctx *ctx, int metric, int as_distance, int raw, int6
     ep.row_begin = r0;
     ep.row_end = r1;
     ep.out = out_dev;
-    int engine = ctx->engine == PC_ENGINE_AUTO ? PC_ENGINE_POPC : ctx->engine;
+    // AUTO: the tensor-core engine whenever the weights fit its limb layout
+    int engine = ctx->engine;
+    if (engine == PC_ENGINE_AUTO) engine = pc_i8_supported(ctx, metric) ? PC_ENGINE_I8MMA : PC_ENGINE_POPC;
     if (engine == PC_ENGINE_I8MMA) {
         PC_TRY(pc_i8_contract(ctx, metric, ep));
         return PC_OK;

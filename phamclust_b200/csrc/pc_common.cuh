@@ -151,7 +151,7 @@ struct pc_ctx {
     // ---- sequences ----
     int64_t n_genes = 0;
     std::vector<int32_t> h_gene_len;
-    DevBuf d_codes, d_gene_off, d_gene_len, d_raw;
+    DevBuf d_codes, d_gene_off, d_gene_len, d_raw, d_raw_off, d_lut;
     DevBuf d_subtab[2];                            // [0] identity, [1] ppos
     int code_of_byte[256];
     int n_codes = 0;
@@ -196,6 +196,7 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
                      const int64_t *gene_off, const int32_t *gene_len,
                      const uint8_t *code_lut, int64_t n_genes, uint8_t *codes);
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
+int pc_i8_supported(const pc_ctx *ctx, int metric);
 
 // NW bucket table: capacity (ref columns per pass) of each kernel config
 #define PC_NW_BUCKETS 12
@@ -234,4 +235,23 @@ __device__ __forceinline__ int pc_finish_micro(double similarity, int as_distanc
 {
     return pc_round6_micro(as_distance ? 1.0 - similarity : similarity);
 }
+
+// fused epilogue for one pair of the cheap metrics (both contraction engines)
+__device__ __forceinline__ int pc_cheap_metric_micro(int metric, int as_distance, int numer,
+                                                     int den_i, int den_j)
+{
+    // numer: shared phams (gcs, jc) or conserved genes / residues (pocp, af)
+    double sim = 0.0;
+    if (numer > 0) {
+        const int64_t den = (int64_t)den_i + (int64_t)den_j;
+        if (metric == PC_GCS)
+            sim = (2.0 * (double)numer) / (double)den;            // metrics.py:45-48
+        else if (metric == PC_JC)
+            sim = (double)numer / (double)(den - numer);          // |S u T| = |S|+|T|-|S n T|
+        else
+            sim = (double)numer / (double)den;                    // metrics.py:110, :152
+    }
+    return pc_finish_micro(sim, as_distance);
+}
+
 #endif

@@ -1,9 +1,416 @@
-// pc_contract_i8.cu -- int8 tcgen05 engine for the shared-count contraction.
-// (placeholder until the TMA/TMEM kernel lands; the popc engine is the default)
+// pc_contract_i8.cu -- K1/K2/K3 as an int8 tcgen05 GEMM: S = M_a . M_b^T over
+// the dense genome x pham operand, s32 accumulators in TMEM, TMA-fed, with the
+// per-metric normalisation + Python-exact rounding (K6) fused into the epilogue
+// so that only the upper-triangle tiles of the result are ever written.
+//
+// Replaces, per genome pair, Genome.__and__ + len()
+// (/root/reference/src/phamclust/genome.py:124-135) and the arithmetic of
+// metrics.py:40-53 (gcs), :70-80 (jc), :102-115 (pocp), :135-157 (af).
+//
+// Operand (row-major uint8, one row per genome, K contiguous = "K-major"):
+//   gcs/jc : [ B ]                    B = 0/1 presence          K = P_pad
+//   pocp   : [ C | B ]                C = copies (1 limb)       K = 2 P_pad
+//   af     : [ L0 | L1 | B ]          L = L0 + 256 L1 (aa)      K = 3 P_pad
+// shared(i,j) = B_i.B_j ; conserved(i,j) = sum_t 256^t (Lt_i.B_j + B_i.Lt_j):
+// the row tile reads segment t while the column tile reads segment B and vice
+// versa, limb t accumulating into its own TMEM accumulator.
+//
+// CTA = one 128 x 256 output tile (UMMA M=128, N=256, K=32 per instruction,
+// cta_group::1), 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected lane each), warps 2-5 = epilogue (tcgen05.ld 32x32b, one TMEM lane
+// quadrant per warp).  4-stage 48 KB smem ring (128B-swizzled 128-byte K
+// slabs), mbarrier full/empty pairs, tcgen05.commit releases the slots.
+// Tensor-pipe bound: 2*K*128*256 int8 ops per tile.
+#include <cuda.h>
+
 #include "pc_common.cuh"
+
+#define I8_BM 128
+#define I8_BN 256
+#define I8_BK 128                 // bytes (= int8 elements) per stage
+#define I8_STAGES 4
+#define I8_THREADS 192
+#define I8_A_BYTES (I8_BM * I8_BK)
+#define I8_B_BYTES (I8_BN * I8_BK)
+#define I8_STAGE_BYTES (I8_A_BYTES + I8_B_BYTES)
+#define I8_SMEM_BYTES (I8_STAGES * I8_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * I8_BN * 4)
+
+struct I8Args {
+    int64_t p_pad;        // bytes per segment (multiple of 128)
+    int n_limbs;          // 0: gcs/jc (single segment); else weight limbs before the B segment
+    int tile_row0;        // first 128-row tile of the launch
+    EpilogueArgs ep;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                            int32_t c0, int32_t c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr)
+{
+    // cute::UMMA::SmemDescriptor, K-major, SWIZZLE_128B: rows are 128 B, groups
+    // of 8 rows are SBO = 1024 B apart, LBO = 1 (unused with swizzle), version 1
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address
+    d |= (uint64_t)1 << 16;                             // leading byte offset (16 B units)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+    d |= (uint64_t)1 << 46;                             // version = 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// instruction descriptor: D = s32, A = B = unsigned 8 bit, K-major, N = 256, M = 128
+__device__ __forceinline__ constexpr uint32_t i8_idesc()
+{
+    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(I8_BN >> 3) << 17) |
+           ((uint32_t)(I8_BM >> 4) << 24);
+}
+
+// step `it` of the K schedule -> (segment read by the row tile, segment read by
+// the column tile, accumulator, k-block)
+__device__ __forceinline__ void i8_schedule(const I8Args &a, int64_t kb_per_seg, int64_t it,
+                                            int64_t &a_col, int64_t &b_col, int &acc, bool &first)
+{
+    if (a.n_limbs == 0) {
+        a_col = b_col = it * I8_BK;
+        acc = 0;
+        first = (it == 0);
+        return;
+    }
+    const int64_t per_limb = 2 * kb_per_seg;
+    const int limb = (int)(it / per_limb);
+    const int64_t r = it % per_limb;
+    const int64_t kb = r % kb_per_seg;
+    const bool swapped = r >= kb_per_seg;
+    const int64_t wcol = (int64_t)limb * a.p_pad + kb * I8_BK;
+    const int64_t bcol = (int64_t)a.n_limbs * a.p_pad + kb * I8_BK;
+    a_col = swapped ? bcol : wcol;
+    b_col = swapped ? wcol : bcol;
+    acc = limb;
+    first = (r == 0);
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const I8Args a)
+{
+    const int bi = blockIdx.y + a.tile_row0;      // 128-row tile
+    const int bj = blockIdx.x;                    // 256-column tile
+    if ((int64_t)bj * I8_BN + (I8_BN - 1) < (int64_t)bi * I8_BM) return;   // strictly lower triangle
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *tiles = smem;                                            // STAGES x (A | B)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + I8_STAGES * I8_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + I8_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + I8_STAGES;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    int32_t *s_den = reinterpret_cast<int32_t *>(smem + I8_STAGES * I8_STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_acc = a.n_limbs == 0 ? 1 : a.n_limbs;
+    const uint32_t tmem_cols = n_acc * I8_BN <= 256 ? 256 : 512;
+    const int64_t kb_per_seg = a.p_pad / I8_BK;
+    const int64_t n_steps = a.n_limbs == 0 ? kb_per_seg : 2 * (int64_t)a.n_limbs * kb_per_seg;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_ptr)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int64_t it = 0; it < n_steps; ++it) {
+                const int s = (int)(it % I8_STAGES);
+                const uint32_t ph = (uint32_t)((it / I8_STAGES) & 1);
+                int64_t a_col, b_col; int acc; bool first;
+                i8_schedule(a, kb_per_seg, it, a_col, b_col, acc, first);
+                mbar_wait(empty_bar + s, ph ^ 1);
+                mbar_expect_tx(full_bar + s, I8_STAGE_BYTES);
+                uint8_t *sa = tiles + (size_t)s * I8_STAGE_BYTES;
+                tma_load_2d(sa, &map_a, full_bar + s, (int32_t)a_col, bi * I8_BM);
+                tma_load_2d(sa + I8_A_BYTES, &map_b, full_bar + s, (int32_t)b_col, bj * I8_BN);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = i8_idesc();
+            for (int64_t it = 0; it < n_steps; ++it) {
+                const int s = (int)(it % I8_STAGES);
+                const uint32_t ph = (uint32_t)((it / I8_STAGES) & 1);
+                int64_t a_col, b_col; int acc; bool first;
+                i8_schedule(a, kb_per_seg, it, a_col, b_col, acc, first);
+                mbar_wait(full_bar + s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(tiles + (size_t)s * I8_STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128_kmajor(sa);
+                const uint64_t bdesc = umma_desc_sw128_kmajor(sa + I8_A_BYTES);
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * I8_BN;
+#pragma unroll
+                for (int k = 0; k < I8_BK / 32; ++k) {
+                    // advance 32 bytes of K inside the 128B swizzle atom: +2 in 16 B units
+                    umma_i8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            (first && k == 0) ? 0u : 1u);
+                }
+                umma_commit(empty_bar + s);          // frees the smem slot when the MMAs retire
+            }
+            umma_commit(tmem_full_bar);              // accumulators complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+        const int quad = warp & 3;
+        const int et = threadIdx.x - 64;              // 0..127
+        const EpilogueArgs &ep = a.ep;
+        const int64_t n = ep.n;
+        const int64_t col0 = (int64_t)bj * I8_BN;
+        if (!ep.raw)
+            for (int x = et; x < I8_BN; x += 128) s_den[x] = (col0 + x < n) ? ep.den[col0 + x] : 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        const int64_t i = (int64_t)bi * I8_BM + quad * 32 + lane;
+        const bool row_ok = i < n && i >= ep.row_begin && i < ep.row_end;
+        const int den_i = (row_ok && !ep.raw) ? ep.den[i] : 0;
+        const int64_t out_base = pc_tri_index(n, ep.row_begin, ep.row_begin);
+        const int64_t row_base = row_ok ? pc_tri_index(n, i, i) - out_base - i : 0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int c = 0; c < I8_BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+            if (n_acc == 2) {
+                uint32_t hi[32];
+                tmem_ld32(lane_addr + (uint32_t)(I8_BN + c * 32), hi);
+#pragma unroll
+                for (int x = 0; x < 32; ++x) v[x] += hi[x] << 8;
+            }
+            if (!row_ok) continue;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+                const int64_t j = col0 + c * 32 + x;
+                if (j >= n || j < i) continue;
+                int val;
+                if (ep.raw)
+                    val = (i == j) ? 0 : (int)v[x];
+                else if (i == j)
+                    val = ep.as_distance ? 0 : 1000000;                  // matrix.py:467-468
+                else
+                    val = pc_cheap_metric_micro(ep.metric, ep.as_distance, (int)v[x], den_i,
+                                                s_den[c * 32 + x]);
+                ep.out[row_base + j] = val;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// operand packing: CSR entries -> dense uint8 rows
+// ---------------------------------------------------------------------------
+__global__ void pack_i8_kernel(const int32_t *__restrict__ entry_genome,
+                               const int32_t *__restrict__ pham_id,
+                               const uint32_t *__restrict__ weight, int n_limbs, int64_t p_pad,
+                               int64_t row_bytes, int64_t nnz, uint8_t *__restrict__ dst)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        uint8_t *row = dst + (int64_t)entry_genome[e] * row_bytes;
+        const int32_t p = pham_id[e];
+        const uint32_t w = weight ? weight[e] : 0;
+        for (int t = 0; t < n_limbs; ++t) row[(int64_t)t * p_pad + p] = (uint8_t)((w >> (8 * t)) & 0xffu);
+        row[(int64_t)n_limbs * p_pad + p] = 1;
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(pc_ctx *ctx, CUtensorMap *map, void *base, int64_t row_bytes, int64_t rows,
+                    int box_rows)
+{
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        PC_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess)
+            return pc_fail(ctx, PC_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        encode = (PFN_encodeTiled)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)I8_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return pc_fail(ctx, PC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PC_OK;
+}
+
+// 0 if the int8 engine can serve `metric` for the loaded table
+int pc_i8_supported(const pc_ctx *ctx, int metric)
+{
+    if (metric == PC_POCP && ctx->max_copies > 255) return 0;
+    if (metric == PC_AF && ctx->max_len_sum > 65535) return 0;
+    return 1;
+}
 
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
 {
-    (void)metric; (void)ep;
-    return pc_fail(ctx, PC_EINVAL, "the int8 tcgen05 engine is not available in this build");
+    if (ep.row_end <= ep.row_begin) return PC_OK;
+    if (!pc_i8_supported(ctx, metric))
+        return pc_fail(ctx, PC_EINVAL, "int8 engine: weights of metric %d do not fit the limb layout", metric);
+    const int kind = (metric == PC_GCS || metric == PC_JC) ? 0 : (metric == PC_POCP ? 1 : 2);
+    int n_limbs = 0;
+    if (kind == 1) n_limbs = 1;
+    if (kind == 2) n_limbs = ctx->max_len_sum > 255 ? 2 : 1;
+    const int64_t p_pad = std::max<int64_t>(I8_BK, (ctx->P + I8_BK - 1) / I8_BK * I8_BK);
+    const int64_t row_bytes = p_pad * (n_limbs + 1);
+    const int64_t rows_pad = (ctx->N + I8_BN - 1) / I8_BN * I8_BN;
+    if (ctx->i8_kind != kind || ctx->i8_K != row_bytes) {
+        const size_t bytes = (size_t)rows_pad * row_bytes;
+        PC_TRY(devbuf_reserve(ctx, ctx->d_i8, bytes));
+        PC_TRY(pc_stage_begin(ctx, PC_T_PACK));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8.p, 0, bytes, ctx->stream));
+        if (ctx->nnz) {
+            const uint32_t *w = kind == 0 ? nullptr
+                              : kind == 1 ? ctx->d_copies.as<uint32_t>() : ctx->d_len_sum.as<uint32_t>();
+            int64_t blocks = (ctx->nnz + 255) / 256;
+            int64_t cap = (int64_t)ctx->sm_count * 16;
+            pack_i8_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
+                ctx->d_entry_genome.as<int32_t>(), ctx->d_pham_id.as<int32_t>(), w, n_limbs, p_pad,
+                row_bytes, ctx->nnz, ctx->d_i8.as<uint8_t>());
+            PC_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+        PC_TRY(pc_stage_end(ctx));
+        ctx->i8_kind = kind;
+        ctx->i8_K = row_bytes;
+    }
+    CUtensorMap map_a, map_b;
+    PC_TRY(make_map(ctx, &map_a, ctx->d_i8.p, row_bytes, rows_pad, I8_BM));
+    PC_TRY(make_map(ctx, &map_b, ctx->d_i8.p, row_bytes, rows_pad, I8_BN));
+    I8Args args;
+    args.p_pad = p_pad;
+    args.n_limbs = n_limbs;
+    args.tile_row0 = (int)(ep.row_begin / I8_BM);
+    args.ep = ep;
+    const int tile_row1 = (int)((ep.row_end + I8_BM - 1) / I8_BM);
+    dim3 grid((unsigned)((ctx->N + I8_BN - 1) / I8_BN), (unsigned)(tile_row1 - args.tile_row0));
+    PC_CUDA(ctx, cudaFuncSetAttribute(i8_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      I8_SMEM_BYTES));
+    PC_TRY(pc_stage_begin(ctx, PC_T_CONTRACT));
+    i8_contract_kernel<<<grid, I8_THREADS, I8_SMEM_BYTES, ctx->stream>>>(map_a, map_b, args);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->contract_launches++;
+    PC_TRY(pc_stage_end(ctx));
+    return PC_OK;
 }

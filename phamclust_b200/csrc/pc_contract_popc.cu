@@ -60,26 +60,6 @@ int pc_launch_pack_bits(pc_ctx *ctx, int source, int plane, uint32_t *dst)
 }
 
 // ---------------------------------------------------------------------------
-// fused epilogue for one pair (also used by the int8 engine)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ int pc_cheap_metric_micro(int metric, int as_distance, int numer,
-                                                     int den_i, int den_j)
-{
-    // numer: shared phams (gcs, jc) or conserved genes / residues (pocp, af)
-    double sim = 0.0;
-    if (numer > 0) {
-        const int64_t den = (int64_t)den_i + (int64_t)den_j;
-        if (metric == PC_GCS)
-            sim = (2.0 * (double)numer) / (double)den;            // metrics.py:45-48
-        else if (metric == PC_JC)
-            sim = (double)numer / (double)(den - numer);          // |S u T| = |S|+|T|-|S n T|
-        else
-            sim = (double)numer / (double)den;                    // metrics.py:110, :152
-    }
-    return pc_finish_micro(sim, as_distance);
-}
-
-// ---------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(PB_THREADS)

@@ -1,0 +1,55 @@
+"""The int8 tcgen05 engine of the shared-count contraction against the popc
+engine and the array oracle: integers bit-exact, every cheap metric."""
+import numpy as np
+import pytest
+
+from oracle import pham_oracle as po
+from phamclust_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+CHEAP = ("gcs", "jc", "pocp", "af")
+
+
+def _with_lengths(table, seed):
+    """Give a sequence-less sparse table varied per-entry lengths (af needs > 1 limb)."""
+    rng = np.random.default_rng(seed)
+    table.len_sum = (table.copies * rng.integers(30, 1500, size=len(table.copies))).astype(np.uint32)
+    return table
+
+
+@pytest.mark.parametrize("n,p,seed", [(130, 1500, 5), (300, 5000, 6), (257, 40000, 7), (1, 10, 8)])
+def test_i8_engine_matches_popc_and_oracle(gpu_ctx, n, p, seed):
+    table = _with_lengths(synthetic.sparse_table(n, max(p, 400), seed=seed, clusters=4, mean_phams=30), seed)
+    gpu_ctx.load_table(table)
+    iu = np.triu_indices(n)
+    try:
+        for key in CHEAP:
+            gpu_ctx.set_engine("popc")
+            want_num = gpu_ctx.numerators(key)
+            want = {d: gpu_ctx.matrix(key, as_distance=d) for d in (True, False)}
+            oracle_num = po.table_numerators(table, key)[iu].copy()
+            oracle_num[iu[0] == iu[1]] = 0
+            assert np.array_equal(want_num, oracle_num), key
+            gpu_ctx.set_engine("i8mma")
+            assert np.array_equal(gpu_ctx.numerators(key), want_num), key
+            for d in (True, False):
+                assert np.array_equal(gpu_ctx.matrix(key, as_distance=d), want[d]), (key, d)
+            # row blocks through the int8 engine recompose as well
+            if n > 128:
+                parts = [gpu_ctx.matrix_rows(key, True, r0, r1) for r0, r1 in ((0, 100), (100, 129), (129, n))]
+                assert np.array_equal(np.concatenate(parts), want[True]), key
+    finally:
+        gpu_ctx.set_engine("auto")
+
+
+def test_i8_engine_at_benchmark_size(gpu_ctx):
+    table = synthetic.sparse_table(4000, 60000, seed=1)
+    gpu_ctx.load_table(table)
+    try:
+        gpu_ctx.set_engine("popc")
+        want = gpu_ctx.matrix("jc")
+        gpu_ctx.set_engine("i8mma")
+        assert np.array_equal(gpu_ctx.matrix("jc"), want)
+    finally:
+        gpu_ctx.set_engine("auto")
