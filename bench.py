@@ -36,9 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALIGN_METRICS = ("aai", "peq")
-# SASS instructions per DP cell in the unrolled inner loop of nw_kernel<.,16,.>
-# (cuobjdump -sass, see DESIGN.md "K4 roofline"); issue-slot roofline below
-DP_INSTR_PER_CELL = 22.0
+# SASS instructions per DP cell: 304 per 16-cell row step of nw_kernel<16,16,...>
+# (cuobjdump -sass); issue-slot roofline below
+DP_INSTR_PER_CELL = 19.0
 SM_COUNT = 148
 
 
@@ -269,7 +269,10 @@ def run_native(args):
     total_ms = float(total_ms.item())
     counters = ctx.counters()
     timings = ctx.timings()
-    checksum = int(out_local[:_native.tri_len(n, r0, r1)].to(torch.int64).sum().item())
+    local_sum = out_local[:_native.tri_len(n, r0, r1)].to(torch.int64).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(local_sum, op=dist.ReduceOp.SUM)
+    checksum = int(local_sum.item())          # sum of every entry of the packed triangle
 
     # ---- e2e: host buffers in, host buffer out, through the C ABI, every step ----
     e2e = None
@@ -315,6 +318,7 @@ def run_native(args):
             t0 = time.perf_counter()
             m = matrix_de_novo(table, METRICS[metric], 1)
             barrier()
+            assert int(m.micro.astype(np.int64).sum()) == checksum, "sharded API result differs"
             if it >= min(args.warmup, 1):
                 secs.append(time.perf_counter() - t0)
         worst = torch.tensor([float(np.mean(secs))], dtype=torch.float64, device=dev)
@@ -353,7 +357,7 @@ def run_native(args):
         limbs = {"gcs": 1, "jc": 1, "pocp": 2, "af": 4}[metric]     # K multiplier of the operand
         if engine in ("i8mma", "auto"):
             # algorithmic int8 ops: 2 * K * N(N+1)/2 with K = P (gcs/jc), 2P (pocp), 4P (af, 2 limbs)
-            ops = 2.0 * table.n_phams * limbs * tri
+            ops = 2.0 * table.n_phams * limbs * _native.tri_len(n, r0, r1)   # this rank's row block
             tops = ops / (per_launch_ms * 1e-3) / 1e12
             peak = 2.0 * peaks["bf16_tflops"]
             roofline = {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05 kind::i8 + fused epilogue)",
