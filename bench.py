@@ -354,9 +354,10 @@ def run_native(args):
         launches = max(counters["contract_launches"], 1)
         per_launch_ms = contract_ms / launches
         engine = args.engine or "auto"
-        limbs = {"gcs": 1, "jc": 1, "pocp": 2, "af": 4}[metric]     # K multiplier of the operand
+        af_limbs = 1 if int(table.len_sum.max(initial=0)) <= 255 else 2
+        limbs = {"gcs": 1, "jc": 1, "pocp": 2, "af": 2 * af_limbs}[metric]     # K multiplier of the operand
         if engine in ("i8mma", "auto"):
-            # algorithmic int8 ops: 2 * K * N(N+1)/2 with K = P (gcs/jc), 2P (pocp), 4P (af, 2 limbs)
+            # algorithmic int8 ops: 2 * K * N(N+1)/2 with K = P (gcs/jc), 2P (pocp), 2P per af limb
             ops = 2.0 * table.n_phams * limbs * _native.tri_len(n, r0, r1)   # this rank's row block
             tops = ops / (per_launch_ms * 1e-3) / 1e12
             peak = 2.0 * peaks["bf16_tflops"]

@@ -15,8 +15,11 @@
 // the row tile reads segment t while the column tile reads segment B and vice
 // versa, limb t accumulating into its own TMEM accumulator.
 //
-// CTA = one 128 x 256 output tile (UMMA M=128, N=256, K=32 per instruction,
-// cta_group::1), 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
+// CTA = one (128*MT) x 256 output tile (UMMA M=128, N=256, K=32 per
+// instruction, cta_group::1; MT = 2 row tiles sharing one column tile whenever a
+// single accumulator per row tile suffices -- r1 ncu showed the 128x256 tile at
+// 55 % tensor / 55 % L2 throughput, i.e. limited by operand traffic from L2, and
+// the taller tile moves 1.5x fewer bytes per MAC), 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
 // elected lane each), warps 2-5 = epilogue (tcgen05.ld 32x32b, one TMEM lane
 // quadrant per warp).  4-stage 48 KB smem ring (128B-swizzled 128-byte K
 // slabs), mbarrier full/empty pairs, tcgen05.commit releases the slots.
@@ -28,12 +31,15 @@
 #define I8_BM 128
 #define I8_BN 256
 #define I8_BK 128                 // bytes (= int8 elements) per stage
-#define I8_STAGES 4
 #define I8_THREADS 192
 #define I8_A_BYTES (I8_BM * I8_BK)
 #define I8_B_BYTES (I8_BN * I8_BK)
-#define I8_STAGE_BYTES (I8_A_BYTES + I8_B_BYTES)
-#define I8_SMEM_BYTES (I8_STAGES * I8_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * I8_BN * 4)
+#define I8_MAX_STAGES 4
+template <int MT> struct I8Cfg {
+    static constexpr int STAGE_BYTES = MT * I8_A_BYTES + I8_B_BYTES;     // 48 KB / 64 KB
+    static constexpr int STAGES = MT == 1 ? 4 : 3;                        // 192 KB ring either way
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * I8_BN * 4;
+};
 
 struct I8Args {
     int64_t p_pad;        // bytes per segment (multiple of 128)
@@ -167,13 +173,16 @@ __device__ __forceinline__ void i8_schedule(const I8Args &a, int64_t kb_per_seg,
     first = (r == 0);
 }
 
+template <int MT>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const I8Args a)
 {
-    const int bi = blockIdx.y + a.tile_row0;      // 128-row tile
+    constexpr int I8_STAGES = I8Cfg<MT>::STAGES;
+    constexpr int I8_STAGE_BYTES = I8Cfg<MT>::STAGE_BYTES;
+    const int bi = blockIdx.y + a.tile_row0;      // (128*MT)-row tile
     const int bj = blockIdx.x;                    // 256-column tile
-    if ((int64_t)bj * I8_BN + (I8_BN - 1) < (int64_t)bi * I8_BM) return;   // strictly lower triangle
+    if ((int64_t)bj * I8_BN + (I8_BN - 1) < (int64_t)bi * I8_BM * MT) return;   // strictly lower triangle
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -186,7 +195,7 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_acc = a.n_limbs == 0 ? 1 : a.n_limbs;
+    const int n_acc = (a.n_limbs == 0 ? 1 : a.n_limbs) * MT;       // host guarantees <= 2
     const uint32_t tmem_cols = n_acc * I8_BN <= 256 ? 256 : 512;
     const int64_t kb_per_seg = a.p_pad / I8_BK;
     const int64_t n_steps = a.n_limbs == 0 ? kb_per_seg : 2 * (int64_t)a.n_limbs * kb_per_seg;
@@ -226,8 +235,11 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 mbar_wait(empty_bar + s, ph ^ 1);
                 mbar_expect_tx(full_bar + s, I8_STAGE_BYTES);
                 uint8_t *sa = tiles + (size_t)s * I8_STAGE_BYTES;
-                tma_load_2d(sa, &map_a, full_bar + s, (int32_t)a_col, bi * I8_BM);
-                tma_load_2d(sa + I8_A_BYTES, &map_b, full_bar + s, (int32_t)b_col, bj * I8_BN);
+#pragma unroll
+                for (int u = 0; u < MT; ++u)
+                    tma_load_2d(sa + u * I8_A_BYTES, &map_a, full_bar + s, (int32_t)a_col,
+                                (bi * MT + u) * I8_BM);
+                tma_load_2d(sa + MT * I8_A_BYTES, &map_b, full_bar + s, (int32_t)b_col, bj * I8_BN);
             }
         }
     } else if (warp == 1) {
@@ -242,14 +254,17 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 mbar_wait(full_bar + s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(tiles + (size_t)s * I8_STAGE_BYTES);
-                const uint64_t adesc = umma_desc_sw128_kmajor(sa);
-                const uint64_t bdesc = umma_desc_sw128_kmajor(sa + I8_A_BYTES);
-                const uint32_t tmem_d = tmem_base + (uint32_t)acc * I8_BN;
+                const uint64_t bdesc = umma_desc_sw128_kmajor(sa + MT * I8_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < I8_BK / 32; ++k) {
-                    // advance 32 bytes of K inside the 128B swizzle atom: +2 in 16 B units
-                    umma_i8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                            (first && k == 0) ? 0u : 1u);
+                for (int u = 0; u < MT; ++u) {
+                    const uint64_t adesc = umma_desc_sw128_kmajor(sa + u * I8_A_BYTES);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(MT == 1 ? acc : u) * I8_BN;
+#pragma unroll
+                    for (int k = 0; k < I8_BK / 32; ++k) {
+                        // advance 32 bytes of K inside the 128B swizzle atom: +2 in 16 B units
+                        umma_i8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                (first && k == 0) ? 0u : 1u);
+                    }
                 }
                 umma_commit(empty_bar + s);          // frees the smem slot when the MMAs retire
             }
@@ -268,35 +283,41 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        const int64_t i = (int64_t)bi * I8_BM + quad * 32 + lane;
-        const bool row_ok = i < n && i >= ep.row_begin && i < ep.row_end;
-        const int den_i = (row_ok && !ep.raw) ? ep.den[i] : 0;
         const int64_t out_base = pc_tri_index(n, ep.row_begin, ep.row_begin);
-        const int64_t row_base = row_ok ? pc_tri_index(n, i, i) - out_base - i : 0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        for (int c = 0; c < I8_BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
-            if (n_acc == 2) {
-                uint32_t hi[32];
-                tmem_ld32(lane_addr + (uint32_t)(I8_BN + c * 32), hi);
+#pragma unroll 1
+        for (int u = 0; u < MT; ++u) {
+            const int64_t i = ((int64_t)bi * MT + u) * I8_BM + quad * 32 + lane;
+            const bool row_ok = i < n && i >= ep.row_begin && i < ep.row_end;
+            const int den_i = (row_ok && !ep.raw) ? ep.den[i] : 0;
+            const int64_t row_base = row_ok ? pc_tri_index(n, i, i) - out_base - i : 0;
+            // column chunks entirely left of this warp's rows hold nothing to write
+            const int64_t warp_row0 = ((int64_t)bi * MT + u) * I8_BM + quad * 32;
+            for (int c = 0; c < I8_BN / 32; ++c) {
+                if (col0 + c * 32 + 31 < warp_row0) continue;          // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(lane_addr + (uint32_t)((MT == 1 ? 0 : u) * I8_BN + c * 32), v);
+                if (MT == 1 && n_acc == 2) {
+                    uint32_t hi[32];
+                    tmem_ld32(lane_addr + (uint32_t)(I8_BN + c * 32), hi);
 #pragma unroll
-                for (int x = 0; x < 32; ++x) v[x] += hi[x] << 8;
-            }
-            if (!row_ok) continue;
+                    for (int x = 0; x < 32; ++x) v[x] += hi[x] << 8;
+                }
+                if (!row_ok) continue;
 #pragma unroll
-            for (int x = 0; x < 32; ++x) {
-                const int64_t j = col0 + c * 32 + x;
-                if (j >= n || j < i) continue;
-                int val;
-                if (ep.raw)
-                    val = (i == j) ? 0 : (int)v[x];
-                else if (i == j)
-                    val = ep.as_distance ? 0 : 1000000;                  // matrix.py:467-468
-                else
-                    val = pc_cheap_metric_micro(ep.metric, ep.as_distance, (int)v[x], den_i,
-                                                s_den[c * 32 + x]);
-                ep.out[row_base + j] = val;
+                for (int x = 0; x < 32; ++x) {
+                    const int64_t j = col0 + c * 32 + x;
+                    if (j >= n || j < i) continue;
+                    int val;
+                    if (ep.raw)
+                        val = (i == j) ? 0 : (int)v[x];
+                    else if (i == j)
+                        val = ep.as_distance ? 0 : 1000000;                  // matrix.py:467-468
+                    else
+                        val = pc_cheap_metric_micro(ep.metric, ep.as_distance, (int)v[x], den_i,
+                                                    s_den[c * 32 + x]);
+                    ep.out[row_base + j] = val;
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -400,14 +421,23 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
     I8Args args;
     args.p_pad = p_pad;
     args.n_limbs = n_limbs;
-    args.tile_row0 = (int)(ep.row_begin / I8_BM);
     args.ep = ep;
-    const int tile_row1 = (int)((ep.row_end + I8_BM - 1) / I8_BM);
+    // two row tiles per CTA whenever one accumulator per row tile is enough
+    const int mt = n_limbs <= 1 ? 2 : 1;
+    const int64_t rows_per_tile = (int64_t)I8_BM * mt;
+    args.tile_row0 = (int)(ep.row_begin / rows_per_tile);
+    const int tile_row1 = (int)((ep.row_end + rows_per_tile - 1) / rows_per_tile);
     dim3 grid((unsigned)((ctx->N + I8_BN - 1) / I8_BN), (unsigned)(tile_row1 - args.tile_row0));
-    PC_CUDA(ctx, cudaFuncSetAttribute(i8_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      I8_SMEM_BYTES));
     PC_TRY(pc_stage_begin(ctx, PC_T_CONTRACT));
-    i8_contract_kernel<<<grid, I8_THREADS, I8_SMEM_BYTES, ctx->stream>>>(map_a, map_b, args);
+    if (mt == 2) {
+        PC_CUDA(ctx, cudaFuncSetAttribute(i8_contract_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          I8Cfg<2>::SMEM_BYTES));
+        i8_contract_kernel<2><<<grid, I8_THREADS, I8Cfg<2>::SMEM_BYTES, ctx->stream>>>(map_a, map_b, args);
+    } else {
+        PC_CUDA(ctx, cudaFuncSetAttribute(i8_contract_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          I8Cfg<1>::SMEM_BYTES));
+        i8_contract_kernel<1><<<grid, I8_THREADS, I8Cfg<1>::SMEM_BYTES, ctx->stream>>>(map_a, map_b, args);
+    }
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     ctx->contract_launches++;
