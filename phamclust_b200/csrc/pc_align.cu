@@ -32,17 +32,6 @@
 //     wavefronts to conflicts on a shared 8 KB table).
 #include "pc_common.cuh"
 
-// v2 bucket table: ref columns handled in one pass by each kernel config
-const int pc_nw_bucket_cap[PC_NW_BUCKETS] = {32, 64, 96, 128, 192, 256, 384, 512,
-                                             640, 768, 1024, 1 << 30};
-
-int pc_nw_bucket_of(int ref_len)
-{
-    for (int b = 0; b < PC_NW_BUCKETS; ++b)
-        if (ref_len <= pc_nw_bucket_cap[b]) return b;
-    return PC_NW_BUCKETS - 1;
-}
-
 #define NW_TAB_CODES 24       // codes of the replicated fast-path table
 
 template <int G, int K, bool MULTI, bool REPL, int THREADS>
@@ -67,6 +56,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
     __syncthreads();
 
     constexpr int SUBS = 32 / G;
+    constexpr bool STORE_Y = K <= 24;       // wide tiles recompute Y = X + ext to stay in registers
     constexpr int CAP = G * K;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int QSTRIDE = REPL ? NW_TAB_CODES * 32 : 32;   // int2 elements per query code
@@ -108,7 +98,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int col0 = chunk * CAP + sl * K;   // 0-based first column of this lane
             // per column: X = H - open, Y = X + ext, F, and the relative counters
-            int Xp[K], Yp[K], Fp[K], cHp[K], cFp[K], rc[K];
+            int Xp[K], Yp[STORE_Y ? K : 1], Fp[K], cHp[K], cFp[K], rc[K];
             // ref residues: K multiple of 4 and genes 16B aligned -> word loads
 #pragma unroll
             for (int w = 0; w < K / 4; ++w) {
@@ -124,7 +114,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
             for (int x = 0; x < K; ++x) {
                 const int j = col0 + x + 1;          // 1-based column
                 Xp[x] = -open - (j - 1) * ext - open;   // H[0][j] - open
-                Yp[x] = Xp[x] + ext;
+                if (STORE_Y) Yp[x] = Xp[x] + ext;
                 Fp[x] = PC_NEG_INF;                  // F[0][j]
                 cHp[x] = 0;                          // cH[0][j] = (0, j)  -> relative 0
                 cFp[x] = 0;
@@ -164,10 +154,12 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                         const int2 sc = trow[rc[x]];         // {score + open, (hit<<16) - 1}
                         // F: from above.  open branch = X[i-1][j]; strict > means ties extend
 #if PC_GAP_TIE_EXTENDS
-                        const bool pf = Yp[x] > Fp[x];       // H-open > F-ext
+                        const int yu = STORE_Y ? Yp[STORE_Y ? x : 0] : Xp[x] + ext;
+                        const bool pf = yu > Fp[x];          // H-open > F-ext
                         const bool pe = yl > el;
 #else
-                        const bool pf = Yp[x] >= Fp[x];
+                        const int yu = STORE_Y ? Yp[STORE_Y ? x : 0] : Xp[x] + ext;
+                        const bool pf = yu >= Fp[x];
                         const bool pe = yl >= el;
 #endif
                         const int f = __viaddmax_s32(Fp[x], -ext, Xp[x]);
@@ -186,7 +178,8 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                         cd = cHp[x];
                         xl = h - open;
                         yl = h - (open - ext);
-                        Xp[x] = xl; Yp[x] = yl; Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
+                        Xp[x] = xl; if (STORE_Y) Yp[STORE_Y ? x : 0] = yl;
+                        Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
                         el = e; cl = ch; ce = cee;
                     }
                     outX = xl; outE = el; outcH = cl; outcE = ce;
@@ -260,23 +253,42 @@ int pc_nw_multichunk_warps(pc_ctx *ctx)
     return ctx->sm_count * 8 * 2;      // 256-thread blocks, at most 2 per SM
 }
 
-int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int bucket)
+// K <= 16 fits 384-thread blocks (<= 168 registers); larger K needs 256 threads
+template <int G, int K, bool MULTI>
+static int launch_gk(pc_ctx *ctx, const NwArgs &args, bool repl)
+{
+    return launch_one<G, K, MULTI, (K <= 16 ? 384 : 256)>(ctx, args, repl);
+}
+
+template <int G>
+static int launch_k(pc_ctx *ctx, const NwArgs &args, bool repl, int K)
+{
+    switch (K) {
+    case 8: return launch_gk<G, 8, false>(ctx, args, repl);
+    case 12: return launch_gk<G, 12, false>(ctx, args, repl);
+    case 16: return launch_gk<G, 16, false>(ctx, args, repl);
+    case 20: return launch_gk<G, 20, false>(ctx, args, repl);
+    case 24: return launch_gk<G, 24, false>(ctx, args, repl);
+    }
+    return pc_fail(ctx, PC_EINVAL, "no DP kernel for G=%d K=%d", G, K);
+}
+
+int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg)
 {
     if (args.n_tasks <= 0) return PC_OK;
+    if (cfg < 0 || cfg >= PC_NW_NCFG) return pc_fail(ctx, PC_EINVAL, "bad DP config %d", cfg);
     const bool repl = ctx->n_codes <= NW_TAB_CODES;
-    switch (bucket) {
-    case 0: return launch_one<4, 8, false, 384>(ctx, args, repl);
-    case 1: return launch_one<8, 8, false, 384>(ctx, args, repl);
-    case 2: return launch_one<8, 12, false, 384>(ctx, args, repl);
-    case 3: return launch_one<8, 16, false, 384>(ctx, args, repl);
-    case 4: return launch_one<16, 12, false, 384>(ctx, args, repl);
-    case 5: return launch_one<16, 16, false, 384>(ctx, args, repl);
-    case 6: return launch_one<32, 12, false, 384>(ctx, args, repl);
-    case 7: return launch_one<32, 16, false, 384>(ctx, args, repl);
-    case 8: return launch_one<32, 20, false, 256>(ctx, args, repl);
-    case 9: return launch_one<32, 24, false, 256>(ctx, args, repl);
-    case 10: return launch_one<32, 32, false, 256>(ctx, args, repl);
-    case 11: return launch_one<32, 32, true, 256>(ctx, args, repl);
+    int G, K;
+    pc_nw_cfg(cfg, G, K);
+    if (cfg == PC_NW_MULTI) return launch_gk<32, 32, true>(ctx, args, repl);
+    switch (G) {
+    case 4: return launch_k<4>(ctx, args, repl, K);
+    case 8: return launch_k<8>(ctx, args, repl, K);
+    case 16: return launch_k<16>(ctx, args, repl, K);
+    case 32:
+        if (K == 28) return launch_gk<32, 28, false>(ctx, args, repl);
+        if (K == 32) return launch_gk<32, 32, false>(ctx, args, repl);
+        return launch_k<32>(ctx, args, repl, K);
     }
-    return pc_fail(ctx, PC_EINVAL, "bad NW bucket %d", bucket);
+    return pc_fail(ctx, PC_EINVAL, "bad DP config %d", cfg);
 }

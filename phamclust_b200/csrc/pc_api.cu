@@ -176,9 +176,9 @@ extern "C" int pc_init(int device_id, pc_ctx **out)
 
 static void free_plan(AlignPlan &p)
 {
-    devbuf_free(p.ph_mem_off); devbuf_free(p.ph_unit_off); devbuf_free(p.ph_task_off);
+    devbuf_free(p.ph_mem_off); devbuf_free(p.ph_unit_off);
     devbuf_free(p.mem_genome); devbuf_free(p.mem_first_gene); devbuf_free(p.mem_copies);
-    devbuf_free(p.mem_cprefix); devbuf_free(p.mem_rowoff);
+    devbuf_free(p.blk_counts); devbuf_free(p.cfg_info); devbuf_free(p.unit_task_off);
     p.part = p.n_parts = -1;
 }
 
@@ -581,83 +581,57 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
     AlignPlan &pl = ctx->plan;
     if (pl.part == part && pl.n_parts == n_parts) return PC_OK;
     HostTimer host_timer(ctx, PC_T_HOST_PLAN);
-    struct PhamInfo { int64_t pham; int bucket; double cost; };
+    struct PhamInfo { int64_t pham; double cost; };
     std::vector<PhamInfo> infos;
     for (int64_t p = 0; p < ctx->P; ++p) {
         const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
         if (e - b < 2) continue;              // cannot be shared by two genomes
-        int max_len = 0;
         double tot = 0;
         for (int64_t k = b; k < e; ++k) {
             const int64_t ent = ctx->h_pham_members[k];
-            for (int64_t g = ctx->h_entry_first_gene[ent]; g < ctx->h_entry_first_gene[ent + 1]; ++g) {
-                max_len = std::max(max_len, ctx->h_gene_len[g]);
-                tot += ctx->h_gene_len[g];
-            }
+            tot += ctx->h_len_sum[ent];
         }
-        infos.push_back({p, pc_nw_bucket_of(max_len), tot * tot});
+        infos.push_back({p, tot * tot});      // ~ sum of len_a * len_b over its member pairs
     }
-    // descending bucket (long first), then descending cost; deal round-robin
+    // descending cost (LPT), dealt round-robin over the partitions
     std::sort(infos.begin(), infos.end(), [](const PhamInfo &x, const PhamInfo &y) {
-        if (x.bucket != y.bucket) return x.bucket > y.bucket;
         if (x.cost != y.cost) return x.cost > y.cost;
         return x.pham < y.pham;
     });
-    std::vector<int64_t> ph_mem_off{0}, ph_unit_off{0}, ph_task_off{0};
-    std::vector<int32_t> mem_genome, mem_first_gene, mem_copies, mem_cprefix;
-    std::vector<int64_t> mem_rowoff;
-    std::vector<int64_t> bucket_tasks(PC_NW_BUCKETS, 0);
-    int32_t max_q_multi = 0;
+    std::vector<int64_t> ph_mem_off{0}, ph_unit_off{0};
+    std::vector<int32_t> mem_genome, mem_first_gene, mem_copies;
+    int64_t n_tasks = 0;
     for (size_t pos = 0; pos < infos.size(); ++pos) {
         if ((int)(pos % (size_t)n_parts) != part) continue;
         const int64_t p = infos[pos].pham;
         const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
         const int64_t m = e - b;
-        int64_t total_copies = 0;
-        for (int64_t k = b; k < e; ++k) total_copies += ctx->h_copies[ctx->h_pham_members[k]];
-        int64_t cprefix = 0, rowoff = 0;
+        int64_t sum_c = 0, sum_c2 = 0;
         for (int64_t k = b; k < e; ++k) {
             const int64_t ent = ctx->h_pham_members[k];
             const int64_t c = ctx->h_copies[ent];
             mem_genome.push_back(ctx->h_entry_genome[ent]);
             mem_first_gene.push_back((int32_t)ctx->h_entry_first_gene[ent]);
             mem_copies.push_back((int32_t)c);
-            mem_cprefix.push_back((int32_t)cprefix);
-            mem_rowoff.push_back(rowoff);
-            cprefix += c;
-            rowoff += c * (total_copies - cprefix);   // row a pairs with every later member
-            if (infos[pos].bucket == PC_NW_BUCKETS - 1)
-                for (int64_t g = ctx->h_entry_first_gene[ent]; g < ctx->h_entry_first_gene[ent + 1]; ++g)
-                    max_q_multi = std::max(max_q_multi, ctx->h_gene_len[g]);
+            sum_c += c;
+            sum_c2 += c * c;
         }
+        n_tasks += (sum_c * sum_c - sum_c2) / 2;          // sum over member pairs of ca * cb
         ph_mem_off.push_back(ph_mem_off.back() + m);
         ph_unit_off.push_back(ph_unit_off.back() + m * (m - 1) / 2);
-        ph_task_off.push_back(ph_task_off.back() + rowoff);
-        bucket_tasks[infos[pos].bucket] += rowoff;
     }
     pl.n_ph = (int64_t)ph_mem_off.size() - 1;
     pl.n_units = ph_unit_off.back();
-    pl.n_tasks = ph_task_off.back();
+    pl.n_tasks = n_tasks;
     pl.n_mem = (int64_t)mem_genome.size();
-    pl.max_qlen_multichunk = max_q_multi;
-    // launch order = storage order: buckets from the largest down
-    pl.bucket_task_off.assign(PC_NW_BUCKETS, 0);
-    pl.bucket_task_count = bucket_tasks;
-    {
-        int64_t off = 0;
-        for (int b = PC_NW_BUCKETS - 1; b >= 0; --b) {
-            pl.bucket_task_off[b] = off;         // start of bucket b
-            off += bucket_tasks[b];
-        }
-    }
+    int32_t max_len = 0;
+    for (int32_t v : ctx->h_gene_len) max_len = std::max(max_len, v);
+    pl.max_gene_len = max_len;
     PC_TRY(upload(ctx, pl.ph_mem_off, ph_mem_off.data(), ph_mem_off.size()));
     PC_TRY(upload(ctx, pl.ph_unit_off, ph_unit_off.data(), ph_unit_off.size()));
-    PC_TRY(upload(ctx, pl.ph_task_off, ph_task_off.data(), ph_task_off.size()));
     PC_TRY(upload(ctx, pl.mem_genome, mem_genome.data(), mem_genome.size()));
     PC_TRY(upload(ctx, pl.mem_first_gene, mem_first_gene.data(), mem_first_gene.size()));
     PC_TRY(upload(ctx, pl.mem_copies, mem_copies.data(), mem_copies.size()));
-    PC_TRY(upload(ctx, pl.mem_cprefix, mem_cprefix.data(), mem_cprefix.size()));
-    PC_TRY(upload(ctx, pl.mem_rowoff, mem_rowoff.data(), mem_rowoff.size()));
     PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // sources are locals
     pl.part = part;
     pl.n_parts = n_parts;
@@ -672,15 +646,15 @@ static void fill_nw_common(pc_ctx *ctx, NwArgs &a, int ppos)
     a.subtab = ctx->d_subtab[ppos ? 1 : 0].as<int2>();
     a.gap_open = PC_GAP_OPEN_DEFAULT;
     a.gap_extend = PC_GAP_EXTEND_DEFAULT;
-    a.cell_counter = ctx->d_counters.as<unsigned long long>() + PC_NW_BUCKETS;
+    a.cell_counter = ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG;
 }
 
-// counters layout: [0..PC_NW_BUCKETS) work counters, [PC_NW_BUCKETS] cumulative cells
+// counters layout: [0..PC_NW_NCFG) work counters, [PC_NW_NCFG] cumulative cells
 static int ensure_counters(pc_ctx *ctx)
 {
     if (!ctx->d_counters.p) {
-        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_BUCKETS + 1)));
-        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_BUCKETS + 1), ctx->stream));
+        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_NCFG + 1)));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_NCFG + 1), ctx->stream));
     }
     return PC_OK;
 }
@@ -709,24 +683,40 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     PC_TRY(devbuf_reserve(ctx, ctx->d_task_r, (size_t)pl.n_tasks * sizeof(int32_t)));
     PC_TRY(devbuf_reserve(ctx, ctx->d_hitlen, (size_t)pl.n_tasks * sizeof(uint32_t)));
     PC_TRY(ensure_counters(ctx));
-    PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_BUCKETS, ctx->stream));
+    PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_NCFG, ctx->stream));
 
     UnitArgs u;
     u.ph_mem_off = pl.ph_mem_off.as<int64_t>();
     u.ph_unit_off = pl.ph_unit_off.as<int64_t>();
-    u.ph_task_off = pl.ph_task_off.as<int64_t>();
     u.n_ph = pl.n_ph;
     u.n_units = pl.n_units;
     u.mem_genome = pl.mem_genome.as<int32_t>();
     u.mem_first_gene = pl.mem_first_gene.as<int32_t>();
     u.mem_copies = pl.mem_copies.as<int32_t>();
-    u.mem_cprefix = pl.mem_cprefix.as<int32_t>();
-    u.mem_rowoff = pl.mem_rowoff.as<int64_t>();
+    u.gene_len = ctx->d_gene_len.as<int32_t>();
     u.n_genomes = ctx->N;
+    {
+        int64_t blocks = (pl.n_units + 255) / 256;
+        blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)ctx->sm_count * 8));
+        u.units_per_block = ((pl.n_units + blocks - 1) / blocks + 255) / 256 * 256;
+        u.n_blocks = (int)((pl.n_units + u.units_per_block - 1) / u.units_per_block);
+    }
+    PC_TRY(devbuf_reserve(ctx, pl.blk_counts, sizeof(unsigned long long) * (size_t)u.n_blocks * PC_NW_NCFG));
+    PC_TRY(devbuf_reserve(ctx, pl.cfg_info, sizeof(unsigned long long) * 2 * PC_NW_NCFG));
+    PC_TRY(devbuf_reserve(ctx, pl.unit_task_off, sizeof(int64_t) * (size_t)pl.n_units));
+    u.blk_counts = pl.blk_counts.as<unsigned long long>();
+    u.cfg_total = pl.cfg_info.as<unsigned long long>();
+    u.cfg_base = u.cfg_total + PC_NW_NCFG;
+    u.unit_task_off = pl.unit_task_off.as<int64_t>();
 
+    // bucket the units by DP config on the device, then expand them into tasks
     PC_TRY(pc_stage_begin(ctx, PC_T_GATHER));
-    PC_TRY(pc_launch_expand_units(ctx, u, ctx->d_task_q.as<int32_t>(), ctx->d_task_r.as<int32_t>()));
+    PC_TRY(pc_launch_classify_units(ctx, u));
+    unsigned long long cfg_info[2 * PC_NW_NCFG];
+    PC_CUDA(ctx, cudaMemcpyAsync(cfg_info, pl.cfg_info.p, sizeof cfg_info, cudaMemcpyDeviceToHost, ctx->stream));
+    PC_TRY(pc_launch_scatter_units(ctx, u, ctx->d_task_q.as<int32_t>(), ctx->d_task_r.as<int32_t>()));
     PC_TRY(pc_stage_end(ctx));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // per-config task counts size the launches
 
     NwArgs a;
     memset(&a, 0, sizeof a);
@@ -737,14 +727,14 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     a.out_hitlen = ctx->d_hitlen.as<uint32_t>();
     a.out_score = nullptr;
     PC_TRY(pc_stage_begin(ctx, PC_T_ALIGN));
-    for (int b = PC_NW_BUCKETS - 1; b >= 0; --b) {
-        const int64_t count = pl.bucket_task_count[b];
+    for (int c = PC_NW_NCFG - 1; c >= 0; --c) {
+        const int64_t count = (int64_t)cfg_info[c];
         if (count == 0) continue;
-        a.task_base = pl.bucket_task_off[b];
+        a.task_base = (int64_t)cfg_info[PC_NW_NCFG + c];
         a.n_tasks = count;
-        a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
-        if (b == PC_NW_BUCKETS - 1) PC_TRY(ensure_spill(ctx, pl.max_qlen_multichunk, a));
-        PC_TRY(pc_launch_nw(ctx, a, b));
+        a.work_counter = ctx->d_counters.as<unsigned long long>() + c;
+        if (c == PC_NW_MULTI) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a));
+        PC_TRY(pc_launch_nw(ctx, a, c));
     }
     PC_TRY(pc_stage_end(ctx));
     ctx->alignments += pl.n_tasks;
@@ -873,19 +863,19 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
         return pc_fail(ctx, PC_EINVAL, "pc_alignment_identities: bad arguments");
     if (n_tasks == 0) return PC_OK;
     // processing order: by kernel config of the ref length, largest first
-    std::vector<int64_t> bucket_count(PC_NW_BUCKETS, 0);
+    std::vector<int64_t> bucket_count(PC_NW_NCFG, 0);
     std::vector<int> bucket(n_tasks);
     int32_t max_q_multi = 0;
     for (int64_t t = 0; t < n_tasks; ++t) {
         if (query_gene[t] < 0 || query_gene[t] >= ctx->n_genes || ref_gene[t] < 0 || ref_gene[t] >= ctx->n_genes)
             return pc_fail(ctx, PC_EINVAL, "task %lld names a gene outside [0,%lld)", (long long)t, (long long)ctx->n_genes);
-        bucket[t] = pc_nw_bucket_of(ctx->h_gene_len[ref_gene[t]]);
+        bucket[t] = pc_nw_choose_cfg(ctx->h_gene_len[query_gene[t]], ctx->h_gene_len[ref_gene[t]]);
         bucket_count[bucket[t]]++;
-        if (bucket[t] == PC_NW_BUCKETS - 1)
+        if (bucket[t] == PC_NW_MULTI)
             max_q_multi = std::max(max_q_multi, ctx->h_gene_len[query_gene[t]]);
     }
-    std::vector<int64_t> bucket_off(PC_NW_BUCKETS + 1, 0);
-    for (int b = 0; b < PC_NW_BUCKETS; ++b) bucket_off[b + 1] = bucket_off[b] + bucket_count[b];
+    std::vector<int64_t> bucket_off(PC_NW_NCFG + 1, 0);
+    for (int b = 0; b < PC_NW_NCFG; ++b) bucket_off[b + 1] = bucket_off[b] + bucket_count[b];
     std::vector<int64_t> perm(n_tasks);
     {
         std::vector<int64_t> cursor(bucket_off.begin(), bucket_off.end() - 1);
@@ -907,14 +897,14 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
     for (int ppos = 0; ppos < 2; ++ppos) {
         fill_nw_common(ctx, a, ppos);
         a.out_hitlen = ctx->d_hitlen.as<uint32_t>() + (size_t)ppos * n_tasks;
-        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_BUCKETS, ctx->stream));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_NCFG, ctx->stream));
         PC_TRY(pc_stage_begin(ctx, PC_T_ALIGN));
-        for (int b = PC_NW_BUCKETS - 1; b >= 0; --b) {
+        for (int b = PC_NW_NCFG - 1; b >= 0; --b) {
             if (bucket_count[b] == 0) continue;
             a.task_base = bucket_off[b];
             a.n_tasks = bucket_count[b];
             a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
-            if (b == PC_NW_BUCKETS - 1) PC_TRY(ensure_spill(ctx, max_q_multi, a));
+            if (b == PC_NW_MULTI) PC_TRY(ensure_spill(ctx, max_q_multi, a));
             PC_TRY(pc_launch_nw(ctx, a, b));
         }
         PC_TRY(pc_stage_end(ctx));
@@ -983,7 +973,7 @@ extern "C" int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
     unsigned long long cells = 0;
     if (ctx->d_counters.p) {
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_BUCKETS,
+        PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG,
                                 sizeof cells, cudaMemcpyDeviceToHost));
     }
     if (launches) *launches = ctx->launches;
@@ -1002,7 +992,7 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
     ctx->launches = ctx->contract_launches = ctx->align_launches = 0;
     ctx->alignments = 0;
     if (ctx->d_counters.p) {
-        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_BUCKETS, 0,
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG, 0,
                                      sizeof(unsigned long long), ctx->stream));
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }

@@ -84,16 +84,21 @@ struct UnitArgs {
     // per pham (processing order of this partition)
     const int64_t *ph_mem_off;   // [n_ph+1] into the member arrays
     const int64_t *ph_unit_off;  // [n_ph+1]
-    const int64_t *ph_task_off;  // [n_ph+1]
     int64_t n_ph;
     int64_t n_units;
     // per member, grouped by pham, ascending genome index
     const int32_t *mem_genome;
     const int32_t *mem_first_gene;
     const int32_t *mem_copies;
-    const int32_t *mem_cprefix;  // copies of earlier members of the same pham
-    const int64_t *mem_rowoff;   // tasks of earlier rows of the same pham
+    const int32_t *gene_len;
     int64_t n_genomes;
+    // device-side bucketing of the units by DP kernel config
+    int64_t units_per_block;     // contiguous units owned by one classify/scatter block
+    int n_blocks;
+    unsigned long long *blk_counts;   // [n_blocks][PC_NW_NCFG] tasks, then exclusive offsets
+    unsigned long long *cfg_total;    // [PC_NW_NCFG] tasks per config
+    unsigned long long *cfg_base;     // [PC_NW_NCFG] first task of each config
+    int64_t *unit_task_off;           // [n_units] first task of every unit
 };
 
 // ---------------------------------------------------------------------------
@@ -107,11 +112,10 @@ struct StageTimer {
 struct AlignPlan {           // host+device prep for one (part, n_parts)
     int part = -1, n_parts = -1;
     int64_t n_ph = 0, n_units = 0, n_tasks = 0, n_mem = 0;
-    std::vector<int64_t> bucket_task_off;   // first task of each NW bucket
-    std::vector<int64_t> bucket_task_count; // tasks in each NW bucket
-    int32_t max_qlen_multichunk = 0;
-    DevBuf ph_mem_off, ph_unit_off, ph_task_off;
-    DevBuf mem_genome, mem_first_gene, mem_copies, mem_cprefix, mem_rowoff;
+    int32_t max_gene_len = 0;
+    DevBuf ph_mem_off, ph_unit_off;
+    DevBuf mem_genome, mem_first_gene, mem_copies;
+    DevBuf blk_counts, cfg_info, unit_task_off;
 };
 
 struct pc_ctx {
@@ -183,9 +187,9 @@ int pc_launch_pack_bits(pc_ctx *ctx, int source /*0 presence,1 copies,2 len*/,
                         int plane, uint32_t *dst);
 int pc_launch_popc_contract(pc_ctx *ctx, const PopcTerm *d_terms, int n_terms,
                             const EpilogueArgs &ep);
-int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int bucket);
-int pc_launch_expand_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q,
-                           int32_t *task_r);
+int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg);
+int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u);
+int pc_launch_scatter_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r);
 int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen,
                            unsigned long long *acc);
 int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
@@ -198,10 +202,41 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
 int pc_i8_supported(const pc_ctx *ctx, int metric);
 
-// NW bucket table: capacity (ref columns per pass) of each kernel config
-#define PC_NW_BUCKETS 12
-extern const int pc_nw_bucket_cap[PC_NW_BUCKETS];
-int pc_nw_bucket_of(int ref_len);
+// DP kernel configs: a subgroup of G lanes per alignment, K ref columns per lane
+// (G*K columns per pass).  0..14: G in {4,8,16} x K in {8,12,16,20,24};
+// 15..21: G = 32, K in {8,...,32}; 22: multi-chunk (G = 32, K = 32, any length).
+#define PC_NW_NCFG 23
+#define PC_NW_MULTI (PC_NW_NCFG - 1)
+#define PC_NW_COST_PER_CELL 19      // SASS instructions per cell (see pc_align.cu)
+#define PC_NW_COST_PER_STEP 15      // per row-step overhead (shuffles, boundary, loop)
+
+#ifdef __CUDACC__
+#define PC_HD __host__ __device__
+#else
+#define PC_HD
+#endif
+PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
+{
+    if (c < 15) { G = 4 << (c / 5); K = 8 + 4 * (c % 5); }
+    else if (c < PC_NW_MULTI) { G = 32; K = 8 + 4 * (c - 15); }
+    else { G = 32; K = 32; }
+}
+
+// cheapest config able to hold n ref columns in one pass for an m-row query:
+// issue slots per alignment ~ (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp
+PC_HD inline int pc_nw_choose_cfg(int m, int n)
+{
+    int best = PC_NW_MULTI;
+    long long best_cost = -1;
+    for (int c = 0; c < PC_NW_MULTI; ++c) {
+        int G, K;
+        pc_nw_cfg(c, G, K);
+        if (G * K < n) continue;
+        const long long cost = (long long)(m + G - 1) * (K * PC_NW_COST_PER_CELL + PC_NW_COST_PER_STEP) * G;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
 
 // ---------------------------------------------------------------------------
 // device helpers

@@ -1,6 +1,7 @@
 // pc_gather.cu -- the kernels either side of the DP:
 //   * encode:  raw residue bytes -> 5-bit codes in a 16B-aligned arena
-//   * expand:  (pham, member a, member b) units -> ordered gene-pair tasks
+//   * classify / scatter: (pham, member a, member b) units -> ordered gene-pair
+//     tasks, bucketed on the device by DP kernel config
 //   * gather:  K5, best match per anchor gene -> per-genome-pair accumulators
 //   * epilogue: K6 for aai / peq
 // Reference semantics: /root/reference/src/phamclust/metrics.py:203-232 (aai),
@@ -48,13 +49,12 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
 }
 
 // ---------------------------------------------------------------------------
-// unit decoding shared by expand and gather
+// units: (pham, member a, member b) with a < b in ascending genome order
 // ---------------------------------------------------------------------------
 struct Unit {
     int ga, gb;              // genome indices, ga < gb
     int first_a, first_b;    // first gene of each member
     int ca, cb;              // copies
-    int64_t task_off;        // first task of this unit
 };
 
 __device__ __forceinline__ Unit decode_unit(const UnitArgs &u, int64_t unit)
@@ -84,33 +84,141 @@ __device__ __forceinline__ Unit decode_unit(const UnitArgs &u, int64_t unit)
     r.first_b = u.mem_first_gene[mem0 + b];
     r.ca = u.mem_copies[mem0 + a];
     r.cb = u.mem_copies[mem0 + b];
-    // tasks before this unit inside the pham: all rows a' < a, then the units
-    // (a, b') with b' < b, each worth ca * c_b'
-    const int64_t c_between = (int64_t)u.mem_cprefix[mem0 + b] -
-                              ((int64_t)u.mem_cprefix[mem0 + a] + r.ca);
-    r.task_off = u.ph_task_off[p] + u.mem_rowoff[mem0 + a] + (int64_t)r.ca * c_between;
     return r;
 }
 
 // Anchor = the member with FEWER copies, tie -> the lower genome index
 // (metrics.py:208-209; source index < target index by matrix.py:480-486).
-__global__ void expand_units_kernel(const UnitArgs u, int32_t *__restrict__ task_q,
-                                    int32_t *__restrict__ task_r)
+struct UnitShape {
+    int n_anchor, n_other, anchor0, other0;
+};
+
+__device__ __forceinline__ UnitShape unit_shape(const Unit &t)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-         unit < u.n_units; unit += stride) {
+    const bool swap = t.ca > t.cb;
+    UnitShape s;
+    s.n_anchor = swap ? t.cb : t.ca;
+    s.n_other = swap ? t.ca : t.cb;
+    s.anchor0 = swap ? t.first_b : t.first_a;
+    s.other0 = swap ? t.first_a : t.first_b;
+    return s;
+}
+
+// DP config of a unit: sized for its longest query (anchor gene) and ref (other gene)
+__device__ __forceinline__ int unit_cfg(const UnitArgs &u, const UnitShape &s)
+{
+    int m = 0, n = 0;
+    for (int x = 0; x < s.n_anchor; ++x) m = max(m, u.gene_len[s.anchor0 + x]);
+    for (int y = 0; y < s.n_other; ++y) n = max(n, u.gene_len[s.other0 + y]);
+    return pc_nw_choose_cfg(m, n);
+}
+
+#define UNIT_THREADS 256
+
+// pass A: tasks per (block, config)
+__global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const UnitArgs u)
+{
+    __shared__ unsigned long long s_cnt[PC_NW_NCFG];
+    if (threadIdx.x < PC_NW_NCFG) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t u0 = (int64_t)blockIdx.x * u.units_per_block;
+    const int64_t u1 = min(u0 + u.units_per_block, u.n_units);
+    for (int64_t unit = u0 + threadIdx.x; unit < u1; unit += UNIT_THREADS) {
         const Unit t = decode_unit(u, unit);
-        const bool swap = t.ca > t.cb;
-        const int n_anchor = swap ? t.cb : t.ca, n_other = swap ? t.ca : t.cb;
-        const int anchor0 = swap ? t.first_b : t.first_a;
-        const int other0 = swap ? t.first_a : t.first_b;
-        for (int x = 0; x < n_anchor; ++x)
-            for (int y = 0; y < n_other; ++y) {
-                const int64_t k = t.task_off + (int64_t)x * n_other + y;
-                task_q[k] = anchor0 + x;      // _align(anchor_gene, other_gene)
-                task_r[k] = other0 + y;
+        const UnitShape s = unit_shape(t);
+        atomicAdd(&s_cnt[unit_cfg(u, s)], (unsigned long long)(s.n_anchor * s.n_other));
+    }
+    __syncthreads();
+    if (threadIdx.x < PC_NW_NCFG)
+        u.blk_counts[(int64_t)blockIdx.x * PC_NW_NCFG + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// pass B: per config, exclusive scan over blocks; config bases in launch order
+__global__ void scan_blocks_kernel(const UnitArgs u)
+{
+    const int c = threadIdx.x;
+    if (c < PC_NW_NCFG) {
+        unsigned long long run = 0;
+        for (int b = 0; b < u.n_blocks; ++b) {
+            const unsigned long long v = u.blk_counts[(int64_t)b * PC_NW_NCFG + c];
+            u.blk_counts[(int64_t)b * PC_NW_NCFG + c] = run;
+            run += v;
+        }
+        u.cfg_total[c] = run;
+    }
+    __syncthreads();
+    if (c == 0) {
+        unsigned long long base = 0;
+        for (int k = PC_NW_NCFG - 1; k >= 0; --k) {      // long configs first in memory and in time
+            u.cfg_base[k] = base;
+            base += u.cfg_total[k];
+        }
+    }
+}
+
+// pass C: deterministic slot of every unit inside its config's task range,
+// then expansion into ordered (query, ref) gene pairs
+__global__ void __launch_bounds__(UNIT_THREADS)
+scatter_units_kernel(const UnitArgs u, int32_t *__restrict__ task_q, int32_t *__restrict__ task_r)
+{
+    __shared__ unsigned long long s_run[PC_NW_NCFG];
+    __shared__ unsigned int s_wtot[UNIT_THREADS / 32][PC_NW_NCFG];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < PC_NW_NCFG)
+        s_run[threadIdx.x] = u.cfg_base[threadIdx.x] +
+                             u.blk_counts[(int64_t)blockIdx.x * PC_NW_NCFG + threadIdx.x];
+    for (int x = threadIdx.x; x < (UNIT_THREADS / 32) * PC_NW_NCFG; x += UNIT_THREADS)
+        (&s_wtot[0][0])[x] = 0;
+    __syncthreads();
+    const int64_t u0 = (int64_t)blockIdx.x * u.units_per_block;
+    const int64_t u1 = min(u0 + u.units_per_block, u.n_units);
+    for (int64_t base = u0; base < u1; base += UNIT_THREADS) {
+        const int64_t unit = base + threadIdx.x;
+        const bool valid = unit < u1;
+        Unit t;
+        UnitShape s;
+        int cfg = -1;
+        unsigned int nt = 0;
+        if (valid) {
+            t = decode_unit(u, unit);
+            s = unit_shape(t);
+            cfg = unit_cfg(u, s);
+            nt = (unsigned int)(s.n_anchor * s.n_other);
+        }
+        // rank among the lanes of this warp that share the config
+        unsigned int pre = 0, tot = 0;
+        bool leader = true;
+        for (int l = 0; l < 32; ++l) {
+            const int cl = __shfl_sync(0xffffffffu, cfg, l);
+            const unsigned int vl = __shfl_sync(0xffffffffu, nt, l);
+            if (cl == cfg) {
+                tot += vl;
+                if (l < lane) { pre += vl; leader = false; }
             }
+        }
+        if (valid && leader) s_wtot[warp][cfg] = tot;
+        __syncthreads();
+        if (valid) {
+            unsigned long long off = s_run[cfg] + pre;
+            for (int w = 0; w < warp; ++w) off += s_wtot[w][cfg];
+            u.unit_task_off[unit] = (int64_t)off;
+            for (int x = 0; x < s.n_anchor; ++x)
+                for (int y = 0; y < s.n_other; ++y) {
+                    const int64_t k = (int64_t)off + (int64_t)x * s.n_other + y;
+                    task_q[k] = s.anchor0 + x;      // _align(anchor_gene, other_gene)
+                    task_r[k] = s.other0 + y;
+                }
+        }
+        __syncthreads();
+        if (threadIdx.x < PC_NW_NCFG) {
+            unsigned long long add = 0;
+            for (int w = 0; w < UNIT_THREADS / 32; ++w) {
+                add += s_wtot[w][threadIdx.x];
+                s_wtot[w][threadIdx.x] = 0;
+            }
+            s_run[threadIdx.x] += add;
+        }
+        __syncthreads();
     }
 }
 
@@ -126,14 +234,14 @@ __global__ void gather_units_kernel(const UnitArgs u, const uint32_t *__restrict
     for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
          unit < u.n_units; unit += stride) {
         const Unit t = decode_unit(u, unit);
-        const bool swap = t.ca > t.cb;
-        const int n_anchor = swap ? t.cb : t.ca, n_other = swap ? t.ca : t.cb;
+        const UnitShape s = unit_shape(t);
+        const int64_t task_off = u.unit_task_off[unit];
         unsigned long long sum_hit = 0, sum_len = 0;
-        for (int x = 0; x < n_anchor; ++x) {
+        for (int x = 0; x < s.n_anchor; ++x) {
             unsigned long long best_hit = 0, best_len = 0;
             bool have = false;
-            for (int y = 0; y < n_other; ++y) {
-                const uint32_t v = hitlen[t.task_off + (int64_t)x * n_other + y];
+            for (int y = 0; y < s.n_other; ++y) {
+                const uint32_t v = hitlen[task_off + (int64_t)x * s.n_other + y];
                 const unsigned long long hit = v >> 16, len = v & 0xffffu;
                 if (len == 0) continue;           // undefined upstream (0-length alignment)
                 if (!have || hit * best_len >= best_hit * len) {
@@ -148,18 +256,21 @@ __global__ void gather_units_kernel(const UnitArgs u, const uint32_t *__restrict
     }
 }
 
-static int unit_grid(pc_ctx *ctx, int64_t n_units)
-{
-    int64_t blocks = (n_units + 255) / 256;
-    int64_t cap = (int64_t)ctx->sm_count * 16;
-    int64_t g = blocks < cap ? blocks : cap;
-    return (int)(g < 1 ? 1 : g);
-}
-
-int pc_launch_expand_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r)
+int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u)
 {
     if (u.n_units <= 0) return PC_OK;
-    expand_units_kernel<<<unit_grid(ctx, u.n_units), 256, 0, ctx->stream>>>(u, task_q, task_r);
+    classify_units_kernel<<<u.n_blocks, UNIT_THREADS, 0, ctx->stream>>>(u);
+    PC_CUDA(ctx, cudaGetLastError());
+    scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(u);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return PC_OK;
+}
+
+int pc_launch_scatter_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r)
+{
+    if (u.n_units <= 0) return PC_OK;
+    scatter_units_kernel<<<u.n_blocks, UNIT_THREADS, 0, ctx->stream>>>(u, task_q, task_r);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return PC_OK;
@@ -169,7 +280,10 @@ int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitle
                            unsigned long long *acc)
 {
     if (u.n_units <= 0) return PC_OK;
-    gather_units_kernel<<<unit_grid(ctx, u.n_units), 256, 0, ctx->stream>>>(u, hitlen, acc);
+    int64_t blocks = (u.n_units + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    gather_units_kernel<<<grid < 1 ? 1 : grid, 256, 0, ctx->stream>>>(u, hitlen, acc);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return PC_OK;
