@@ -132,24 +132,31 @@ def pinned_copy(torch, arr):
 # --------------------------------------------------------------------------------------
 def cpu_reference_rate(table, metric, sample_genomes, cpus_list):
     """pairs/s of the oracle port of matrix_de_novo (one joblib task per pair,
-    exactly like matrix.py:471-491) on the first ``sample_genomes`` genomes."""
+    exactly like matrix.py:471-491) on the first ``sample_genomes`` genomes.
+    The worker count is picked on a small calibration sample (the reference's
+    per-pair joblib dispatch makes more workers SLOWER for the cheap metrics,
+    BASELINE.md section 2), then the sample is timed once with it."""
     from oracle import nw_c, pham_oracle as po
     from phamclust_b200.packing import unpack_genomes
     nw_c.build()
-    sub = table.subset(sample_genomes)
-    genomes = unpack_genomes(sub)
+    genomes = unpack_genomes(table.subset(sample_genomes))
     n = len(genomes)
     pairs = n * (n - 1) // 2
-    best = None
     runs = {}
-    for cpus in cpus_list:
-        t0 = time.perf_counter()
-        po.matrix_de_novo(genomes, po.METRICS[metric], cpus)
-        dt = time.perf_counter() - t0
-        runs[cpus] = pairs / dt
-        if best is None or runs[cpus] > best[1]:
-            best = (cpus, runs[cpus], dt)
-    return {"value": best[1], "cores": best[0], "seconds": best[2], "pairs": pairs,
+    if len(cpus_list) > 1:
+        calib = genomes[:min(n, 24 if metric in ALIGN_METRICS else 300)]
+        cp = len(calib) * (len(calib) - 1) // 2
+        for cpus in cpus_list:
+            t0 = time.perf_counter()
+            po.matrix_de_novo(calib, po.METRICS[metric], cpus)
+            runs[cpus] = cp / (time.perf_counter() - t0)
+        cpus = max(runs, key=runs.get)
+    else:
+        cpus = cpus_list[0]
+    t0 = time.perf_counter()
+    po.matrix_de_novo(genomes, po.METRICS[metric], cpus)
+    dt = time.perf_counter() - t0
+    return {"value": pairs / dt, "cores": cpus, "seconds": dt, "pairs": pairs,
             "runs": {str(k): v for k, v in runs.items()}, "n": n}
 
 
@@ -159,20 +166,23 @@ def run_reference(args):
         return 0
     table, workload = build_workload(args)
     n_cpus = os.cpu_count() or 1
-    sample = args.cpu_sample or (100 if args.metric in ALIGN_METRICS else 1500)
-    cpus_list = sorted({1, n_cpus})
-    for _ in range(args.warmup if args.warmup < 2 else 1):     # page the oracle in once
-        cpu_reference_rate(table, args.metric, min(sample, 30), [1])
+    sample = args.cpu_sample or (80 if args.metric in ALIGN_METRICS else 1000)
+    # warm-up: page the oracle in and pick the worker count once
+    cal = cpu_reference_rate(table, args.metric, min(sample, 40), sorted({1, n_cpus}))
+    cpus_list = [cal["cores"]]
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_reference_rate(table, args.metric, min(sample, 40), cpus_list)
     values, secs = [], []
     res = None
     for _ in range(args.steps):
         res = cpu_reference_rate(table, args.metric, sample, cpus_list)
         values.append(res["value"]); secs.append(res["seconds"])
+    res["runs"] = cal["runs"]
     value = float(np.mean(values))
     sample_txt = (f"first {res['n']} genomes of the workload ({res['pairs']} pairs) per step; oracle port "
                   f"of matrix_de_novo (one joblib task per pair) + C restatement of parasail NW "
-                  f"(not parasail's SIMD kernel); best of cpus={cpus_list}: "
-                  f"{ {k: round(v, 1) for k, v in res['runs'].items()} } pairs/s")
+                  f"(not parasail's SIMD kernel); cpus={res['cores']} chosen on a calibration sample, "
+                  f"pairs/s by cpus there: { {k: round(v, 1) for k, v in res['runs'].items()} }")
     line = {"impl": "reference", "metric": "genome_pairs_per_sec", "value": value,
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
@@ -397,13 +407,13 @@ def run_native(args):
             "checksum": checksum}
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         n_cpus = os.cpu_count() or 1
-        sample = args.cpu_sample or (100 if need_seqs else 1500)
+        sample = args.cpu_sample or (80 if need_seqs else 1000)
         res = cpu_reference_rate(table, metric, sample, sorted({1, n_cpus}))
         line["cpu_baseline"] = {
             "value": res["value"], "unit": "pairs/s", "cores": res["cores"], "kind": "port",
             "sample": (f"first {res['n']} genomes ({res['pairs']} pairs, {res['seconds']:.1f} s); oracle port of "
-                       f"matrix_de_novo (joblib task per pair) + C restatement of parasail NW; "
-                       f"pairs/s by cpus: { {k: round(v, 1) for k, v in res['runs'].items()} }")}
+                       f"matrix_de_novo (joblib task per pair) + C restatement of parasail NW; cpus chosen on a "
+                       f"calibration sample, pairs/s by cpus there: { {k: round(v, 1) for k, v in res['runs'].items()} }")}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
