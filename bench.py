@@ -36,9 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALIGN_METRICS = ("aai", "peq")
-# SASS instructions per DP cell: 304 per 16-cell row step of nw_kernel<16,16,...>
+# SASS instructions per DP cell: 286 per 16-cell row step of nw_kernel<16,16,...>
 # (cuobjdump -sass); issue-slot roofline below
-DP_INSTR_PER_CELL = 19.0
+DP_INSTR_PER_CELL = 17.9
 SM_COUNT = 148
 
 
@@ -368,14 +368,17 @@ def run_native(args):
         limbs = {"gcs": 1, "jc": 1, "pocp": 2, "af": 2 * af_limbs}[metric]     # K multiplier of the operand
         if engine in ("i8mma", "auto"):
             # algorithmic int8 ops: 2 * K * N(N+1)/2 with K = P (gcs/jc), 2P (pocp), 2P per af limb
-            ops = 2.0 * table.n_phams * limbs * _native.tri_len(n, r0, r1)   # this rank's row block
+            # K counts only phams held by >= 2 genomes: single-genome phams can never be
+            # shared and get no operand column (exact)
+            k_eff = int((np.bincount(table.pham_id, minlength=table.n_phams) >= 2).sum())
+            ops = 2.0 * k_eff * limbs * _native.tri_len(n, r0, r1)   # this rank's row block
             tops = ops / (per_launch_ms * 1e-3) / 1e12
             peak = 2.0 * peaks["bf16_tflops"]
             roofline = {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05 kind::i8 + fused epilogue)",
                         "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak,
                         "traffic": None, "kernel_ms_per_step": contract_ms / max(args.steps, 1),
                         "share_of_step": contract_ms / total_ms if total_ms else None,
-                        "algorithmic_ops_per_launch": ops,
+                        "algorithmic_ops_per_launch": ops, "k_columns": k_eff * limbs,
                         "peak_basis": (f"2 x MEASURED_PEAKS.json bf16_tflops ({peak_kind}; int8 dense is not "
                                        "measured by the driver: derived, nominal 4500 TOP/s)")}
         else:

@@ -20,8 +20,8 @@
 //
 // Instruction diet (the kernel is integer-issue bound, ncu r1: 87 % issue
 // active; see DESIGN.md "K4"):
-//   * state is kept as X = H - open and Y = X + ext, so the open branch of both
-//     gap states is a plain register and  F = VIADDMNMX(Fup, -ext, Xup);
+//   * state is kept as X = H - open, so the open branch of both gap states is a
+//     plain register:  F = VIADDMNMX(Fup, -ext, Xup), opened iff X + ext > Fup;
 //   * counters are stored RELATIVE to (i + j): gap steps then add nothing and a
 //     diagonal step adds (hit << 16) - 1, which comes out of the table; the
 //     true counter is recovered once at the end as d + (m + n);
@@ -39,7 +39,9 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 {
     extern __shared__ __align__(16) int2 s_tab[];
     const int lane = threadIdx.x & 31;
-    const int open = a.gap_open, ext = a.gap_extend;
+    // the reference never changes _align's defaults (metrics.py:160); compile-time
+    // constants let `X + ext > F` fold to `X >= F` and drop a register per column
+    constexpr int open = PC_GAP_OPEN_DEFAULT, ext = PC_GAP_EXTEND_DEFAULT;
     if (REPL) {
         // s_tab[(q*24 + r)*32 + lane] = {score(q,r) + open, (hit << 16) - 1}
         for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
@@ -56,7 +58,6 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
     __syncthreads();
 
     constexpr int SUBS = 32 / G;
-    constexpr bool STORE_Y = K <= 24;       // wide tiles recompute Y = X + ext to stay in registers
     constexpr int CAP = G * K;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int QSTRIDE = REPL ? NW_TAB_CODES * 32 : 32;   // int2 elements per query code
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int col0 = chunk * CAP + sl * K;   // 0-based first column of this lane
             // per column: X = H - open, Y = X + ext, F, and the relative counters
-            int Xp[K], Yp[STORE_Y ? K : 1], Fp[K], cHp[K], cFp[K], rc[K];
+            int Xp[K], Fp[K], cHp[K], cFp[K], rc[K];
             // ref residues: K multiple of 4 and genes 16B aligned -> word loads
 #pragma unroll
             for (int w = 0; w < K / 4; ++w) {
@@ -114,7 +115,6 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
             for (int x = 0; x < K; ++x) {
                 const int j = col0 + x + 1;          // 1-based column
                 Xp[x] = -open - (j - 1) * ext - open;   // H[0][j] - open
-                if (STORE_Y) Yp[x] = Xp[x] + ext;
                 Fp[x] = PC_NEG_INF;                  // F[0][j]
                 cHp[x] = 0;                          // cH[0][j] = (0, j)  -> relative 0
                 cFp[x] = 0;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                     int qc = (int)(__ldg(q + (i - 1)) & 31u);
                     if (REPL && qc >= NW_TAB_CODES) qc = 0;
                     const int2 *trow = tab_lane + qc * QSTRIDE;
-                    int xl = inX, yl = inX + ext, el = inE, cl = incH, ce = incE;
+                    int xl = inX, el = inE, cl = incH, ce = incE;
                     int xd = diagX, cd = diagC;
                     diagX = inX;
                     diagC = incH;
@@ -154,13 +154,11 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                         const int2 sc = trow[rc[x]];         // {score + open, (hit<<16) - 1}
                         // F: from above.  open branch = X[i-1][j]; strict > means ties extend
 #if PC_GAP_TIE_EXTENDS
-                        const int yu = STORE_Y ? Yp[STORE_Y ? x : 0] : Xp[x] + ext;
-                        const bool pf = yu > Fp[x];          // H-open > F-ext
-                        const bool pe = yl > el;
+                        const bool pf = Xp[x] + ext > Fp[x];   // H-open > F-ext (folds to X >= F)
+                        const bool pe = xl + ext > el;
 #else
-                        const int yu = STORE_Y ? Yp[STORE_Y ? x : 0] : Xp[x] + ext;
-                        const bool pf = yu >= Fp[x];
-                        const bool pe = yl >= el;
+                        const bool pf = Xp[x] + ext >= Fp[x];
+                        const bool pe = xl + ext >= el;
 #endif
                         const int f = __viaddmax_s32(Fp[x], -ext, Xp[x]);
                         const int e = __viaddmax_s32(el, -ext, xl);
@@ -177,9 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                         xd = Xp[x];
                         cd = cHp[x];
                         xl = h - open;
-                        yl = h - (open - ext);
-                        Xp[x] = xl; if (STORE_Y) Yp[STORE_Y ? x : 0] = yl;
-                        Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
+                        Xp[x] = xl; Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
                         el = e; cl = ch; ce = cee;
                     }
                     outX = xl; outE = el; outcH = cl; outcE = ce;
@@ -250,14 +246,17 @@ static int launch_one(pc_ctx *ctx, const NwArgs &args, bool repl)
 // upper bound on the warps a launch of the multi-chunk config keeps resident
 int pc_nw_multichunk_warps(pc_ctx *ctx)
 {
-    return ctx->sm_count * 8 * 2;      // 256-thread blocks, at most 2 per SM
+    return ctx->sm_count * 8 * 2;      // 256-thread blocks, at most 2 per SM (non-replicated table)
 }
 
-// K <= 16 fits 384-thread blocks (<= 168 registers); larger K needs 256 threads
+// one CTA per SM (the replicated table takes 144 KB); as many warps as the
+// per-thread state of K columns leaves room for in the register file
 template <int G, int K, bool MULTI>
 static int launch_gk(pc_ctx *ctx, const NwArgs &args, bool repl)
 {
-    return launch_one<G, K, MULTI, (K <= 16 ? 384 : 256)>(ctx, args, repl);
+    // (registers are split per SM sub-partition: 4/3/2 warps each -> 128/168/255 per thread)
+    constexpr int THREADS = K <= 12 ? 512 : K <= 20 ? 384 : 256;
+    return launch_one<G, K, MULTI, THREADS>(ctx, args, repl);
 }
 
 template <int G>

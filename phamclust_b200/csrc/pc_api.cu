@@ -187,7 +187,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_copies, &ctx->d_len_sum,
+    DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_pham_col, &ctx->d_copies, &ctx->d_len_sum,
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
                       &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_codes,
                       &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_subtab[0],
@@ -325,12 +325,20 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     ctx->have_seqs = false;
     ctx->planes_kind = -1; ctx->i8_kind = -1;
     ctx->plan.part = ctx->plan.n_parts = -1;
-    const int64_t words = (n_phams + 31) / 32;
+    // operand columns: a pham held by a single genome can never be shared, so it
+    // gets no column (exact; orphams are common in phage tables)
+    std::vector<int32_t> pham_col(std::max<int64_t>(n_phams, 1), -1);
+    int64_t p_eff = 0;
+    for (int64_t p = 0; p < n_phams; ++p)
+        if (ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p] >= 2) pham_col[p] = (int32_t)p_eff++;
+    ctx->P_eff = p_eff;
+    const int64_t words = (p_eff + 31) / 32;
     ctx->W = std::max<int64_t>(32, (words + 31) / 32 * 32);
 
     PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
     PC_TRY(upload(ctx, ctx->d_entry_genome, ctx->h_entry_genome.data(), nnz));
     PC_TRY(upload(ctx, ctx->d_pham_id, ctx->h_pham_id.data(), nnz));
+    PC_TRY(upload(ctx, ctx->d_pham_col, pham_col.data(), pham_col.size()));
     PC_TRY(upload(ctx, ctx->d_copies, ctx->h_copies.data(), nnz));
     PC_TRY(upload(ctx, ctx->d_len_sum, ctx->h_len_sum.data(), nnz));
     PC_TRY(upload(ctx, ctx->d_den_phams, den_phams.data(), n_genomes));

@@ -129,6 +129,7 @@ struct pc_ctx {
     // ---- table (host copies kept for the host-side planning) ----
     bool have_table = false, have_seqs = false;
     int64_t N = 0, P = 0, nnz = 0;
+    int64_t P_eff = 0;                    // phams held by >= 2 genomes (the only ones that can be shared)
     std::vector<int64_t> h_genome_ptr;
     std::vector<int32_t> h_pham_id;
     std::vector<uint32_t> h_copies, h_len_sum;
@@ -141,6 +142,7 @@ struct pc_ctx {
 
     // ---- device: table ----
     DevBuf d_entry_genome, d_pham_id, d_copies, d_len_sum;
+    DevBuf d_pham_col;                             // pham id -> operand column, -1 = dropped
     DevBuf d_den_phams, d_den_genes, d_den_len;   // int32 [N]
     int64_t W = 0;                                 // words per bit row (multiple of 32)
     DevBuf d_bits;                                 // presence bit rows [N][W]
@@ -207,7 +209,7 @@ int pc_i8_supported(const pc_ctx *ctx, int metric);
 // 15..21: G = 32, K in {8,...,32}; 22: multi-chunk (G = 32, K = 32, any length).
 #define PC_NW_NCFG 23
 #define PC_NW_MULTI (PC_NW_NCFG - 1)
-#define PC_NW_COST_PER_CELL 19      // SASS instructions per cell (see pc_align.cu)
+#define PC_NW_COST_PER_CELL 18      // SASS instructions per cell (see pc_align.cu)
 #define PC_NW_COST_PER_STEP 15      // per row-step overhead (shuffles, boundary, loop)
 
 #ifdef __CUDACC__

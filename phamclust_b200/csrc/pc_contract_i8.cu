@@ -334,13 +334,15 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // ---------------------------------------------------------------------------
 __global__ void pack_i8_kernel(const int32_t *__restrict__ entry_genome,
                                const int32_t *__restrict__ pham_id,
+                               const int32_t *__restrict__ pham_col,
                                const uint32_t *__restrict__ weight, int n_limbs, int64_t p_pad,
                                int64_t row_bytes, int64_t nnz, uint8_t *__restrict__ dst)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
         uint8_t *row = dst + (int64_t)entry_genome[e] * row_bytes;
-        const int32_t p = pham_id[e];
+        const int32_t p = pham_col[pham_id[e]];
+        if (p < 0) continue;                     // held by one genome only: never shared
         const uint32_t w = weight ? weight[e] : 0;
         for (int t = 0; t < n_limbs; ++t) row[(int64_t)t * p_pad + p] = (uint8_t)((w >> (8 * t)) & 0xffu);
         row[(int64_t)n_limbs * p_pad + p] = 1;
@@ -392,7 +394,7 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
     int n_limbs = 0;
     if (kind == 1) n_limbs = 1;
     if (kind == 2) n_limbs = ctx->max_len_sum > 255 ? 2 : 1;
-    const int64_t p_pad = std::max<int64_t>(I8_BK, (ctx->P + I8_BK - 1) / I8_BK * I8_BK);
+    const int64_t p_pad = std::max<int64_t>(I8_BK, (ctx->P_eff + I8_BK - 1) / I8_BK * I8_BK);
     const int64_t row_bytes = p_pad * (n_limbs + 1);
     const int64_t rows_pad = (ctx->N + I8_BN - 1) / I8_BN * I8_BN;
     if (ctx->i8_kind != kind || ctx->i8_K != row_bytes) {
@@ -406,7 +408,8 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
             int64_t blocks = (ctx->nnz + 255) / 256;
             int64_t cap = (int64_t)ctx->sm_count * 16;
             pack_i8_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
-                ctx->d_entry_genome.as<int32_t>(), ctx->d_pham_id.as<int32_t>(), w, n_limbs, p_pad,
+                ctx->d_entry_genome.as<int32_t>(), ctx->d_pham_id.as<int32_t>(), ctx->d_pham_col.as<int32_t>(), w,
+                n_limbs, p_pad,
                 row_bytes, ctx->nnz, ctx->d_i8.as<uint8_t>());
             PC_CUDA(ctx, cudaGetLastError());
             ctx->launches++;

@@ -29,6 +29,7 @@
 // ---------------------------------------------------------------------------
 __global__ void pack_bits_kernel(const int32_t *__restrict__ entry_genome,
                                  const int32_t *__restrict__ pham_id,
+                                 const int32_t *__restrict__ pham_col,
                                  const uint32_t *__restrict__ weight, int plane,
                                  int64_t nnz, int64_t words_per_row,
                                  uint32_t *__restrict__ dst)
@@ -36,7 +37,8 @@ __global__ void pack_bits_kernel(const int32_t *__restrict__ entry_genome,
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
         if (weight && !((weight[e] >> plane) & 1u)) continue;
-        const int32_t p = pham_id[e];
+        const int32_t p = pham_col[pham_id[e]];
+        if (p < 0) continue;                     // held by one genome only: never shared
         atomicOr(dst + (int64_t)entry_genome[e] * words_per_row + (p >> 5), 1u << (p & 31));
     }
 }
@@ -52,7 +54,7 @@ int pc_launch_pack_bits(pc_ctx *ctx, int source, int plane, uint32_t *dst)
     int64_t cap = (int64_t)ctx->sm_count * 16;
     int grid = (int)(blocks < cap ? blocks : cap);
     pack_bits_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_entry_genome.as<int32_t>(),
-                                                   ctx->d_pham_id.as<int32_t>(), w, plane,
+                                                   ctx->d_pham_id.as<int32_t>(), ctx->d_pham_col.as<int32_t>(), w, plane,
                                                    ctx->nnz, ctx->W, dst);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
