@@ -3,7 +3,9 @@
 Usage: python -m phamclust_b200.build_native [--force]
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
+import os
 import pathlib
+import shlex
 import shutil
 import subprocess
 import sys
@@ -27,7 +29,8 @@ def build(force=False, verbose=False):
     if not force and OUT.exists() and OUT.stat().st_mtime >= _newest_source_mtime():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(OUT), *[str(CSRC / s) for s in SOURCES]]
+    extra = shlex.split(os.environ.get("PC_NVCC_EXTRA", ""))      # e.g. -DPC_NW_XL_FMA (experiments)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(OUT), *[str(CSRC / s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -34,6 +34,18 @@
 
 #define NW_TAB_CODES 24       // codes of the replicated fast-path table
 
+// ncu (r1, profiles/): the DP is bound by the ALU pipe (SEL / ISETP / VIADD /
+// VIMNMX, 16 lanes/clk/SMSP, 90 % busy) while the FMA pipe idles at 24 %.  An add
+// written as a*one+b with `one` a run-time 1 cannot be folded by ptxas and
+// issues as IMAD on the FMA pipe.  (Steering the selects the same way, as
+// predicated IMADs, was measured 6 % SLOWER: real IMADs are not cheap either.)
+__device__ __forceinline__ int fma_add(int a, int one, int b)
+{
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+
 template <int G, int K, bool MULTI, bool REPL, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 {
@@ -42,6 +54,9 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
     // the reference never changes _align's defaults (metrics.py:160); compile-time
     // constants let `X + ext > F` fold to `X >= F` and drop a register per column
     constexpr int open = PC_GAP_OPEN_DEFAULT, ext = PC_GAP_EXTEND_DEFAULT;
+#ifdef PC_NW_XL_FMA
+    const int one = a.gap_extend;      // == 1 at run time, opaque to ptxas
+#endif
     if (REPL) {
         // s_tab[(q*24 + r)*32 + lane] = {score(q,r) + open, (hit << 16) - 1}
         for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
@@ -174,7 +189,11 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 #endif
                         xd = Xp[x];
                         cd = cHp[x];
+#ifdef PC_NW_XL_FMA
+                        xl = fma_add(h, one, -open);
+#else
                         xl = h - open;
+#endif
                         Xp[x] = xl; Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
                         el = e; cl = ch; ce = cee;
                     }
