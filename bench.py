@@ -195,7 +195,7 @@ def run_reference(args):
                              "kind": "port", "sample": sample_txt},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -435,13 +435,26 @@ def run_native(args):
                        f"matrix_de_novo (joblib task per pair) + C restatement of parasail NW; cpus chosen on a "
                        f"calibration sample, pairs/s by cpus there: { {k: round(v, 1) for k, v in res['runs'].items()} }")}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints
+    (e.g. NCCL's version banner) was re-routed to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
