@@ -194,6 +194,27 @@ int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
                 int64_t *align_launches);
 int pc_reset_counters(pc_ctx *ctx);
 
+/* -------- host-side text formats (no GPU) -------- */
+/*
+ * Writers of matrix.py:517-533 (adjacency), :624-651 (squareform / lower
+ * triangle) straight from the packed micro-unit triangle; byte-identical
+ * output ('%.6f').  order[k] = storage index of the k-th node in traversal
+ * order; names = blob + offsets in storage order.  mode 0: squareform,
+ * 1: lower triangle (the pipeline's cache, scripts/phamclust.py:254-262),
+ * 2: adjacency, 3: adjacency with skip_zero.
+ */
+int pc_write_matrix(const char *path, int64_t n, const int32_t *micro,
+                    const int64_t *order, const char *names,
+                    const int64_t *name_off, int mode);
+/* Reader of matrix.py:564-621 over a file already in memory. */
+int pc_parse_squareform(const char *buf, int64_t len, int64_t n,
+                        int32_t *micro_out, int64_t *name_begin,
+                        int64_t *name_end);
+/* Field scanner for the 2/3-column TSV of scripts/phamclust.py:21-47. */
+int64_t pc_scan_tsv(const char *buf, int64_t len, int64_t max_rows,
+                    int64_t *fields);
+const char *pc_io_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ from phamclust_b200.metrics import (METRICS, alignment_fraction, average_aminoac
                                     gene_content_similarity, jaccard_coefficient,
                                     percentage_of_conserved_proteins,
                                     proteomic_equivalence_quotient)
-from phamclust_b200.packing import PackedTable, pack_genomes
+from phamclust_b200.packing import PackedTable, pack_genomes, table_from_tsv
 from phamclust_b200.parsers import load_genomes_from_fasta_dir, load_genomes_from_tsv
 
 __version__ = "0.1.0"

@@ -19,7 +19,8 @@ STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h",
 EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_stream",
            "pc_set_engine", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",
            "pc_matrix_rows", "pc_align_accumulate", "pc_numerators",
-           "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters")
+           "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters",
+           "pc_write_matrix", "pc_parse_squareform", "pc_scan_tsv", "pc_io_last_error")
 
 _lib = None
 
@@ -55,6 +56,12 @@ def load_library():
     lib.pc_timings.argtypes = [vp, vp, i32]
     lib.pc_counters.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.pc_reset_counters.argtypes = [vp]
+    lib.pc_write_matrix.argtypes = [ctypes.c_char_p, i64, vp, vp, ctypes.c_char_p, vp, i32]
+    lib.pc_parse_squareform.argtypes = [ctypes.c_char_p, i64, i64, vp, vp, vp]
+    lib.pc_scan_tsv.argtypes = [ctypes.c_char_p, i64, i64, vp]
+    lib.pc_scan_tsv.restype = ctypes.c_int64
+    lib.pc_io_last_error.argtypes = []
+    lib.pc_io_last_error.restype = ctypes.c_char_p
     _lib = lib
     return lib
 

@@ -1,0 +1,184 @@
+// pc_io.cu -- host-side text formats of the matrix (no GPU work): the
+// squareform / lower-triangle / adjacency writers and the squareform reader of
+// /root/reference/src/phamclust/matrix.py:500-670, operating directly on the
+// packed int32 micro-unit triangle ("%.6f" of n/1e6 is pure integer -> text).
+// without this the hand-off of a 10k-genome matrix spends
+// minutes in per-value Python formatting.  The lower-triangle form is the
+// pipeline's on-disk cache (scripts/phamclust.py:254-268) and stays byte-identical.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phamclust_b200.h"
+
+static thread_local std::string g_io_error;
+
+extern "C" const char *pc_io_last_error(void) { return g_io_error.c_str(); }
+
+static inline int64_t tri(int64_t n, int64_t i, int64_t j)
+{
+    if (i > j) { const int64_t t = i; i = j; j = t; }
+    return i * n - (i * (i - 1)) / 2 + (j - i);
+}
+
+// "%.6f" of micro/1e6 for 0 <= micro <= 1e6 (the only values a SymMatrix holds)
+static inline char *put_micro(char *p, int32_t micro)
+{
+    *p++ = (char)('0' + micro / 1000000);
+    *p++ = '.';
+    int32_t frac = micro % 1000000;
+    for (int d = 100000; d >= 1; d /= 10) { *p++ = (char)('0' + frac / d); frac %= d; }
+    return p;
+}
+
+// mode 0: squareform with header names, 1: lower triangle, 2: adjacency, 3: adjacency skipping zeros.
+// order[k] = storage index of the k-th node in traversal order; names are a blob + offsets (storage order).
+extern "C" int pc_write_matrix(const char *path, int64_t n, const int32_t *micro, const int64_t *order,
+                               const char *names, const int64_t *name_off, int mode)
+{
+    if (!path || n < 0 || (n > 0 && (!micro || !order || !names || !name_off)) || mode < 0 || mode > 3) {
+        g_io_error = "pc_write_matrix: bad arguments";
+        return PC_EINVAL;
+    }
+    for (int64_t k = 0; k < n; ++k)
+        if (order[k] < 0 || order[k] >= n) { g_io_error = "pc_write_matrix: bad traversal order"; return PC_EINVAL; }
+    FILE *f = fopen(path, "wb");
+    if (!f) { g_io_error = std::string("cannot open ") + path; return PC_EINVAL; }
+    std::vector<char> buf;
+    auto name_of = [&](int64_t k, const char *&s, size_t &len) {
+        const int64_t g = order[k];
+        s = names + name_off[g];
+        len = (size_t)(name_off[g + 1] - name_off[g]);
+    };
+    if (mode <= 1) {
+        std::string header = std::to_string(n);
+        if (mode == 0)
+            for (int64_t k = 0; k < n; ++k) {
+                const char *s; size_t len;
+                name_of(k, s, len);
+                header += '\t';
+                header.append(s, len);
+            }
+        header += '\n';
+        fwrite(header.data(), 1, header.size(), f);
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const char *s; size_t len;
+        name_of(i, s, len);
+        if (mode <= 1) {
+            const int64_t cols = mode == 1 ? i + 1 : n;
+            buf.resize(len + (size_t)cols * 9 + 2);
+            char *p = buf.data();
+            memcpy(p, s, len); p += len;
+            for (int64_t j = 0; j < cols; ++j) {
+                const int32_t v = micro[tri(n, order[i], order[j])];
+                if (v < 0 || v > 1000000) { fclose(f); g_io_error = "unset or out-of-range weight"; return PC_EINVAL; }
+                *p++ = '\t';
+                p = put_micro(p, v);
+            }
+            *p++ = '\n';
+            fwrite(buf.data(), 1, (size_t)(p - buf.data()), f);
+        } else {
+            for (int64_t j = i; j < n; ++j) {
+                const int32_t v = micro[tri(n, order[i], order[j])];
+                if (v < 0 || v > 1000000) { fclose(f); g_io_error = "unset or out-of-range weight"; return PC_EINVAL; }
+                if (mode == 3 && v == 0) continue;
+                const char *t; size_t tl;
+                name_of(j, t, tl);
+                buf.resize(len + tl + 12);
+                char *p = buf.data();
+                memcpy(p, s, len); p += len; *p++ = '\t';
+                memcpy(p, t, tl); p += tl; *p++ = '\t';
+                p = put_micro(p, v);
+                *p++ = '\n';
+                fwrite(buf.data(), 1, (size_t)(p - buf.data()), f);
+            }
+        }
+    }
+    if (fclose(f) != 0) { g_io_error = "write failed"; return PC_EINVAL; }
+    return PC_OK;
+}
+
+// CPython's round(x, 6) * 1e6 on the host (same recipe as the device epilogue)
+static inline long long round6_micro_host(double x)
+{
+    const double hi = x * 1e6;
+    const double lo = std::fma(x, 1e6, -hi);
+    double r = std::nearbyint(hi);
+    if (std::fabs(hi - r) == 0.5) {
+        const double fl = std::floor(hi);
+        if (lo > 0.0) r = fl + 1.0; else if (lo < 0.0) r = fl;
+    }
+    return (long long)r;
+}
+
+// Parse a squareform / lower-triangle file held in memory (matrix.py:564-621):
+// line 0 = size (+ names, ignored); row i = name TAB v0 TAB v1 ...; only the
+// first i+1 values of row i are used.  micro_out is the packed triangle in FILE
+// order; name_begin/name_end give each row name's byte range in buf.
+extern "C" int pc_parse_squareform(const char *buf, int64_t len, int64_t n, int32_t *micro_out,
+                                   int64_t *name_begin, int64_t *name_end)
+{
+    if (!buf || n < 0 || (n > 0 && (!micro_out || !name_begin || !name_end))) {
+        g_io_error = "pc_parse_squareform: bad arguments";
+        return PC_EINVAL;
+    }
+    int64_t pos = 0;
+    while (pos < len && buf[pos] != '\n') ++pos;      // skip the size line
+    ++pos;
+    for (int64_t i = 0; i < n; ++i) {
+        if (pos >= len) { g_io_error = "squareform file has fewer rows than its header says"; return PC_EINVAL; }
+        int64_t eol = pos;
+        while (eol < len && buf[eol] != '\n') ++eol;
+        int64_t p = pos;
+        while (p < eol && buf[p] != '\t') ++p;
+        name_begin[i] = pos;
+        name_end[i] = p;
+        for (int64_t j = 0; j <= i; ++j) {
+            if (p >= eol) { g_io_error = "squareform row is too short"; return PC_EINVAL; }
+            ++p;                                      // the tab
+            char *endp = nullptr;
+            const double v = strtod(buf + p, &endp);
+            if (endp == buf + p) { g_io_error = "could not convert string to float"; return PC_EINVAL; }
+            p = endp - buf;
+            if (!(v >= 0.0 && v <= 1.0)) { g_io_error = "weight not in [0.0, 1.0]"; return PC_EINVAL; }
+            micro_out[tri(n, j, i)] = (int32_t)round6_micro_host(v);
+        }
+        pos = eol + 1;
+    }
+    return PC_OK;
+}
+
+// One pass over a 2/3-column TSV held in memory (scripts/phamclust.py:21-47):
+// per row the byte ranges of name / pham / translation (translation range empty
+// for 2-column rows -> "M").  Returns the number of rows, or -1 on a malformed
+// row (anything but 2 or 3 columns after rstrip()).
+extern "C" int64_t pc_scan_tsv(const char *buf, int64_t len, int64_t max_rows, int64_t *fields /* 6 per row */)
+{
+    int64_t rows = 0, pos = 0;
+    while (pos < len) {
+        int64_t eol = pos;
+        while (eol < len && buf[eol] != '\n') ++eol;
+        int64_t end = eol;                            // rstrip(): trailing whitespace incl. tabs
+        while (end > pos && (buf[end - 1] == ' ' || buf[end - 1] == '\t' || buf[end - 1] == '\r' ||
+                             buf[end - 1] == '\n' || buf[end - 1] == '\v' || buf[end - 1] == '\f'))
+            --end;
+        int64_t t1 = -1, t2 = -1, tabs = 0;
+        for (int64_t p = pos; p < end; ++p)
+            if (buf[p] == '\t') { if (tabs == 0) t1 = p; else if (tabs == 1) t2 = p; ++tabs; }
+        if (tabs < 1 || tabs > 2) { g_io_error = "input file must either 2 or 3 columns"; return -1; }
+        if (rows < max_rows) {
+            int64_t *f = fields + 6 * rows;
+            f[0] = pos; f[1] = t1;
+            f[2] = t1 + 1; f[3] = tabs == 2 ? t2 : end;
+            f[4] = tabs == 2 ? t2 + 1 : end; f[5] = end;
+            if (tabs == 1) f[4] = f[5] = -1;
+        }
+        ++rows;
+        pos = eol + 1;
+    }
+    return rows;
+}

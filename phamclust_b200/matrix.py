@@ -422,7 +422,31 @@ def _fmt6(micro):
     return f"{micro // 1000000}.{micro % 1000000:06d}"
 
 
+def _native_write(matrix, filepath, mode):
+    """Write through libphamclust_b200's host-side formatter (pc_write_matrix):
+    integer micro-units -> '%.6f' text, no per-value Python.  Returns False when
+    the matrix is not array-backed or holds unset weights (caller falls back to
+    the plain Python writer, which then fails exactly like the reference)."""
+    if not isinstance(matrix, SymMatrix) or (matrix._micro == _UNSET).any():
+        return False
+    import ctypes
+    lib = _native.load_library()
+    names = [x.encode() for x in matrix._store]
+    off = np.zeros(len(names) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in names], out=off[1:])
+    blob = b"".join(names)
+    order = np.fromiter((matrix._index[x] for x in matrix._nodes), dtype=np.int64, count=len(matrix._nodes))
+    micro = np.ascontiguousarray(matrix._micro, dtype=np.int32)
+    rc = lib.pc_write_matrix(str(filepath).encode(), len(names), micro.ctypes.data, order.ctypes.data,
+                             ctypes.c_char_p(blob), off.ctypes.data, mode)
+    if rc:
+        raise ValueError(lib.pc_io_last_error().decode())
+    return True
+
+
 def matrix_to_adjacency(matrix, filepath, skip_zero=False):
+    if _native_write(matrix, filepath, 3 if skip_zero else 2):
+        return filepath
     with open(filepath, "w") as handle:
         for source, target, weight in matrix:
             if skip_zero and not weight:
@@ -440,6 +464,35 @@ def read_squareform(filepath):
 
 
 def matrix_from_squareform(filepath):
+    """Squareform / lower-triangle reader (matrix.py:564-603): the whole file is
+    parsed by pc_parse_squareform into the packed triangle; diagonal checks as
+    upstream."""
+    with open(filepath, "rb") as handle:
+        data = handle.read()
+    first = data.split(b"\n", 1)[0].split(b"\t")[0]
+    n = int(first)
+    lib = _native.load_library()
+    micro = np.empty(n * (n + 1) // 2, dtype=np.int32)
+    nb = np.empty(max(n, 1), dtype=np.int64)
+    ne = np.empty(max(n, 1), dtype=np.int64)
+    rc = lib.pc_parse_squareform(data, len(data), n, micro.ctypes.data, nb.ctypes.data, ne.ctypes.data)
+    if rc:
+        raise ValueError(lib.pc_io_last_error().decode())
+    names = [data[nb[i]:ne[i]].decode() for i in range(n)]
+    diag = micro[_tri_offsets(n)[:-1]] if n else micro
+    if len(set(diag.tolist())) > 1:
+        raise ValueError("values on matrix diagonal should be identical")
+    if n and int(diag[0]) == 0:
+        is_distance = True
+    elif n and int(diag[0]) == 1000000:
+        is_distance = False
+    else:
+        raise ValueError("values on matrix diagonal can only be 0.0 or 1.0")
+    return SymMatrix(names, is_distance=is_distance, _micro=micro)
+
+
+def _matrix_from_squareform_python(filepath):
+    """The reference's two-pass reader, kept for cross-checking the native parser."""
     names, diagonal = [], set()
     for i, (target, row) in enumerate(read_squareform(filepath)):
         names.append(target)
@@ -463,6 +516,8 @@ def matrix_to_squareform(matrix, filepath, lower_triangle=False):
     """Squareform / lower-triangle writer; the lower-triangle form is the
     pipeline's on-disk cache (scripts/phamclust.py:254-262) and must stay
     byte-identical: '%.6f', tab separated."""
+    if _native_write(matrix, filepath, 1 if lower_triangle else 0):
+        return filepath
     with open(filepath, "w") as handle:
         header = f"{len(matrix)}"
         if not lower_triangle:

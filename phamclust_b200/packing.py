@@ -104,3 +104,67 @@ def unpack_genomes(table):
                 gene += 1
         genomes.append(genome)
     return genomes
+
+
+def table_from_tsv(filepath, with_sequences=True):
+    """2/3-column TSV straight into a PackedTable, without materialising Genome
+    dicts.  Same semantics as ``load_genomes_from_tsv``
+    (scripts/phamclust.py:21-47) followed by ``pack_genomes``: genomes and phams
+    in first-seen order, paralogs in file order, 2 columns -> translation "M",
+    ``rstrip()`` eats a trailing empty third column."""
+    from phamclust_b200 import _native
+    lib = _native.load_library()
+    with open(filepath, "rb") as handle:
+        data = handle.read()
+    max_rows = data.count(b"\n") + 1
+    fields = np.empty((max_rows, 6), dtype=np.int64)
+    rows = int(lib.pc_scan_tsv(data, len(data), max_rows, fields.ctypes.data))
+    if rows < 0:
+        raise ValueError(lib.pc_io_last_error().decode())
+    fields = fields[:rows]
+    genome_of, entry_of = {}, {}
+    names, vocab = [], {}
+    row_entry = np.empty(rows, dtype=np.int64)
+    entry_genome, entry_pham = [], []
+    for r, (n0, n1, p0, p1) in enumerate(fields[:, :4].tolist()):
+        name, pham = data[n0:n1], data[p0:p1]
+        g = genome_of.get(name)
+        if g is None:
+            g = genome_of[name] = len(names)
+            names.append(name.decode())
+        key = (g, pham)
+        e = entry_of.get(key)
+        if e is None:
+            e = entry_of[key] = len(entry_genome)
+            entry_genome.append(g)
+            entry_pham.append(pham)
+        row_entry[r] = e
+    entry_genome = np.asarray(entry_genome, dtype=np.int64)
+    # CSR order: by genome (first seen), then by first appearance of the pham in it
+    order = np.argsort(entry_genome, kind="stable")
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order))
+    row_slot = rank[row_entry]
+    row_order = np.argsort(row_slot, kind="stable")          # genes in CSR-entry order, file order inside
+    copies = np.bincount(row_slot, minlength=len(order)).astype(np.uint32)
+    t0, t1 = fields[:, 4], fields[:, 5]
+    lens = np.where(t0 < 0, 1, t1 - t0)
+    len_sum = np.bincount(row_slot, weights=lens, minlength=len(order)).astype(np.uint32)
+    ptr = np.zeros(len(names) + 1, dtype=np.int64)
+    np.cumsum(np.bincount(entry_genome, minlength=len(names)), out=ptr[1:])
+    # pham ids in the order pack_genomes would meet them (genome by genome)
+    pham_id = np.fromiter((vocab.setdefault(entry_pham[e], len(vocab)) for e in order.tolist()),
+                          dtype=np.int32, count=len(order))
+    table = PackedTable(names, [p.decode() for p in vocab], ptr, pham_id, copies, len_sum)
+    if with_sequences:
+        glen = lens[row_order]
+        table.seq_off = np.concatenate(([0], np.cumsum(glen))).astype(np.int64)
+        raw = np.frombuffer(data, dtype=np.uint8)
+        res = np.empty(int(table.seq_off[-1]), dtype=np.uint8)
+        starts = t0[row_order]
+        # gather every translation's bytes ("M" for 2-column rows)
+        idx = np.repeat(np.where(starts < 0, 0, starts) - table.seq_off[:-1], glen) + np.arange(len(res))
+        res[:] = raw[idx] if len(res) else res
+        res[np.repeat(starts < 0, glen)] = ord("M")
+        table.residues = res
+    return table

@@ -21,7 +21,7 @@ from phamclust_b200.packing import unpack_genomes
 # ----------------------------------------------------------------------------- library
 def test_library_exports_every_declared_symbol():
     header = (ROOT / "include" / "phamclust_b200.h").read_text()
-    declared = set(re.findall(r"^\s*(?:int|void|const char \*)\s*\**(pc_\w+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^\s*(?:int64_t|int|void|const char \*)\s*\**(pc_\w+)\s*\(", header, re.M))
     assert declared == set(_native.EXPORTS)
     lib = ctypes.CDLL(str(_native.LIB_PATH))
     for name in declared:
@@ -111,6 +111,23 @@ def test_pack_round_trip():
     assert [g.phams for g in back] == [g.phams for g in genomes]
     sub = t.subset(3)
     assert [g.phams for g in unpack_genomes(sub)] == [g.phams for g in genomes[:3]]
+
+
+def test_direct_tsv_loader_equals_genome_path(tmp_path):
+    import random
+    from phamclust_b200.packing import table_from_tsv
+    rows = testdata.genome_rows(seed=3, n_genomes=9, n_phams=9, paralog_p=0.5)
+    random.Random(1).shuffle(rows)           # paralogs and genomes interleaved in the file
+    tsv = tmp_path / "x.tsv"
+    tsv.write_text("".join(f"{a}\t{b}\t{c}\n" for a, b, c in rows) + "zz\tq1\nzz\tq2\t\nzz\tq1\tMKT\n")
+    a, b = pack_genomes(load_genomes_from_tsv(tsv)), table_from_tsv(tsv)
+    assert a.names == b.names and a.phams == b.phams
+    for f in ("genome_ptr", "pham_id", "copies", "len_sum", "seq_off", "residues"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    bad = tmp_path / "bad.tsv"
+    bad.write_text("a\tb\tc\td\n")
+    with pytest.raises(ValueError):
+        table_from_tsv(bad)
 
 
 def test_synthetic_tables_are_deterministic_and_consistent():
@@ -223,6 +240,39 @@ def test_file_formats_match_reference_bytes(reference, tmp_path):
     a = matrix_to_adjacency(mine, tmp_path / "a.adj", skip_zero=True)
     b = reference.matrix.matrix_to_adjacency(ref, tmp_path / "b.adj", skip_zero=True)
     assert pathlib.Path(a).read_bytes() == pathlib.Path(b).read_bytes()
+
+
+def test_native_writers_and_reader_match_the_python_reference_formats(reference, tmp_path):
+    """pc_write_matrix / pc_parse_squareform against the verbatim reference's own
+    writers and readers, after a reorder (traversal != storage order)."""
+    from phamclust_b200.matrix import _matrix_from_squareform_python
+    names = [f"node {k} x" if k % 3 else f"n{k}" for k in range(23)]
+    mine = _filled(SymMatrix, names, True, seed=5)
+    ref = _filled(reference.matrix.SymMatrix, names, True, seed=5)
+    order = names[::2] + names[1::2]
+    mine.reorder(list(order))
+    ref.reorder(list(order))
+    for lower in (True, False):
+        a = matrix_to_squareform(mine, tmp_path / "a.tsv", lower_triangle=lower)
+        b = reference.matrix.matrix_to_squareform(ref, tmp_path / "b.tsv", lower_triangle=lower)
+        assert pathlib.Path(a).read_bytes() == pathlib.Path(b).read_bytes()
+        back = matrix_from_squareform(a)
+        theirs = reference.matrix.matrix_from_squareform(b)
+        assert list(back) == list(theirs) and back.is_distance == theirs.is_distance
+        assert list(_matrix_from_squareform_python(a)) == list(back)
+    for skip in (True, False):
+        a = matrix_to_adjacency(mine, tmp_path / "a.adj", skip_zero=skip)
+        b = reference.matrix.matrix_to_adjacency(ref, tmp_path / "b.adj", skip_zero=skip)
+        assert pathlib.Path(a).read_bytes() == pathlib.Path(b).read_bytes()
+    sim = _filled(SymMatrix, names[:5], False, seed=6)
+    path = matrix_to_squareform(sim, tmp_path / "s.tsv", lower_triangle=True)
+    assert not matrix_from_squareform(path).is_distance
+    # values with more than six decimals are rounded exactly like set_weight does
+    (tmp_path / "odd.tsv").write_text("2\nx\t0.0\ny\t0.1234565\t0.0\n")
+    assert matrix_from_squareform(tmp_path / "odd.tsv").get_weight("x", "y") == round(0.1234565, 6)
+    (tmp_path / "bad.tsv").write_text("2\nx\t0.0\ny\t1.5\t0.0\n")
+    with pytest.raises(ValueError):
+        matrix_from_squareform(tmp_path / "bad.tsv")
 
 
 def test_clustering_on_golden_matrix_gives_golden_partitions():
