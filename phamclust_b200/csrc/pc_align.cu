@@ -265,7 +265,7 @@ static int launch_one(pc_ctx *ctx, const NwArgs &args, bool repl)
 // upper bound on the warps a launch of the multi-chunk config keeps resident
 int pc_nw_multichunk_warps(pc_ctx *ctx)
 {
-    return ctx->sm_count * 8 * 2;      // 256-thread blocks, at most 2 per SM (non-replicated table)
+    return ctx->sm_count * 12 * 2;     // <= 384-thread blocks, at most 2 per SM (non-replicated table)
 }
 
 // one CTA per SM (the replicated table takes 144 KB); as many warps as the
@@ -298,7 +298,14 @@ int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg)
     const bool repl = ctx->n_codes <= NW_TAB_CODES;
     int G, K;
     pc_nw_cfg(cfg, G, K);
-    if (cfg == PC_NW_MULTI) return launch_gk<32, 32, true>(ctx, args, repl);
+    if (cfg >= PC_NW_MULTI0) {
+        switch (K) {
+        case 20: return launch_gk<32, 20, true>(ctx, args, repl);
+        case 24: return launch_gk<32, 24, true>(ctx, args, repl);
+        case 28: return launch_gk<32, 28, true>(ctx, args, repl);
+        default: return launch_gk<32, 32, true>(ctx, args, repl);
+        }
+    }
     switch (G) {
     case 4: return launch_k<4>(ctx, args, repl, K);
     case 8: return launch_k<8>(ctx, args, repl, K);

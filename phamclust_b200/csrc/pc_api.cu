@@ -741,7 +741,7 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
         a.task_base = (int64_t)cfg_info[PC_NW_NCFG + c];
         a.n_tasks = count;
         a.work_counter = ctx->d_counters.as<unsigned long long>() + c;
-        if (c == PC_NW_MULTI) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a));
+        if (c >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a));
         PC_TRY(pc_launch_nw(ctx, a, c));
     }
     PC_TRY(pc_stage_end(ctx));
@@ -879,7 +879,7 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
             return pc_fail(ctx, PC_EINVAL, "task %lld names a gene outside [0,%lld)", (long long)t, (long long)ctx->n_genes);
         bucket[t] = pc_nw_choose_cfg(ctx->h_gene_len[query_gene[t]], ctx->h_gene_len[ref_gene[t]]);
         bucket_count[bucket[t]]++;
-        if (bucket[t] == PC_NW_MULTI)
+        if (bucket[t] >= PC_NW_MULTI0)
             max_q_multi = std::max(max_q_multi, ctx->h_gene_len[query_gene[t]]);
     }
     std::vector<int64_t> bucket_off(PC_NW_NCFG + 1, 0);
@@ -912,7 +912,7 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
             a.task_base = bucket_off[b];
             a.n_tasks = bucket_count[b];
             a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
-            if (b == PC_NW_MULTI) PC_TRY(ensure_spill(ctx, max_q_multi, a));
+            if (b >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, max_q_multi, a));
             PC_TRY(pc_launch_nw(ctx, a, b));
         }
         PC_TRY(pc_stage_end(ctx));

@@ -206,9 +206,10 @@ int pc_i8_supported(const pc_ctx *ctx, int metric);
 
 // DP kernel configs: a subgroup of G lanes per alignment, K ref columns per lane
 // (G*K columns per pass).  0..14: G in {4,8,16} x K in {8,12,16,20,24};
-// 15..21: G = 32, K in {8,...,32}; 22: multi-chunk (G = 32, K = 32, any length).
-#define PC_NW_NCFG 23
-#define PC_NW_MULTI (PC_NW_NCFG - 1)
+// 15..21: G = 32, K in {8,...,32}; 22..25: multi-chunk (G = 32, K in
+// {20,24,28,32}: the ref is cut into ceil(n / 32K) column chunks, any length).
+#define PC_NW_NCFG 26
+#define PC_NW_MULTI0 22             // first multi-chunk config
 #define PC_NW_COST_PER_CELL 18      // SASS instructions per cell (see pc_align.cu)
 #define PC_NW_COST_PER_STEP 15      // per row-step overhead (shuffles, boundary, loop)
 
@@ -220,21 +221,28 @@ int pc_i8_supported(const pc_ctx *ctx, int metric);
 PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
 {
     if (c < 15) { G = 4 << (c / 5); K = 8 + 4 * (c % 5); }
-    else if (c < PC_NW_MULTI) { G = 32; K = 8 + 4 * (c - 15); }
-    else { G = 32; K = 32; }
+    else if (c < PC_NW_MULTI0) { G = 32; K = 8 + 4 * (c - 15); }
+    else { G = 32; K = 20 + 4 * (c - PC_NW_MULTI0); }
 }
 
-// cheapest config able to hold n ref columns in one pass for an m-row query:
-// issue slots per alignment ~ (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp
+// cheapest config for an m-row query against n ref columns: issue slots per
+// alignment ~ chunks x (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp
 PC_HD inline int pc_nw_choose_cfg(int m, int n)
 {
-    int best = PC_NW_MULTI;
+    int best = PC_NW_NCFG - 1;
     long long best_cost = -1;
-    for (int c = 0; c < PC_NW_MULTI; ++c) {
+    for (int c = 0; c < PC_NW_NCFG; ++c) {
         int G, K;
         pc_nw_cfg(c, G, K);
-        if (G * K < n) continue;
-        const long long cost = (long long)(m + G - 1) * (K * PC_NW_COST_PER_CELL + PC_NW_COST_PER_STEP) * G;
+        long long chunks = 1;
+        if (c < PC_NW_MULTI0) {
+            if (G * K < n) continue;
+        } else {
+            chunks = (n + G * K - 1) / (G * K);
+            if (chunks < 2) continue;             // single-pass configs cover it without the spill
+        }
+        const long long cost = chunks * (long long)(m + G - 1) *
+                               (K * PC_NW_COST_PER_CELL + PC_NW_COST_PER_STEP) * G;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
