@@ -149,12 +149,12 @@ def test_golden_alignment_vectors(gpu_ctx):
 
 
 def test_random_alignments_bit_exact_all_kernel_configs(gpu_ctx):
-    """Lengths chosen to land in every NW bucket (32..512 columns and the
-    multi-chunk config), tie-rich alphabets included."""
+    """Lengths chosen to land in every DP config (32..1024 columns per pass and
+    the multi-chunk configs with 2-4 column chunks), tie-rich alphabets included."""
     rng = random.Random(77)
     seqs = []
     for cap in (8, 30, 33, 64, 65, 96, 100, 128, 150, 192, 200, 256, 300, 384, 400, 512, 513,
-                700, 1100, 1600):
+                700, 1100, 1600, 2100, 2650, 3300):
         for alpha in ("AG", testdata.AA):
             a = testdata.random_protein(rng, max(1, cap - 6), cap, alpha)
             seqs += [a, testdata.mutate(rng, a, 0.25, alpha), testdata.mutate(rng, a, 0.6, alpha)]
@@ -257,6 +257,41 @@ def test_edge_cases(gpu_ctx):
     long_gene.add("x", "A" * 40000)
     with pytest.raises(ValueError):
         METRICS["aai"](a, long_gene)
+
+
+def test_empty_genomes_heavy_paralogy_and_big_phams(gpu_ctx):
+    """An empty genome, 6-copy paralog families with exact duplicates (the
+    'last maximum wins' tie of metrics.py:223), and one pham shared by 70 genomes."""
+    rng = random.Random(5)
+    genomes = [Genome("empty")]
+    anc = testdata.random_protein(rng, 40, 60)
+    for g in range(70):
+        x = Genome(f"g{g:02d}")
+        x.add("everyone", testdata.mutate(rng, anc, 0.3))
+        if g % 7 == 0:
+            fam = testdata.random_protein(rng, 25, 45)
+            copies = [testdata.mutate(rng, fam, 0.2) for _ in range(3)]
+            for s in copies + copies[:2] + [copies[0]]:      # 6 copies, duplicates included
+                x.add("family", s)
+        if g % 5 == 0:
+            x.add("pairwise", anc[:30])
+            x.add("pairwise", anc[:30])
+        genomes.append(x)
+    genomes.append(Genome("empty2"))
+    _load(gpu_ctx, pack_genomes(genomes))
+    n = len(genomes)
+    for key in ALL:
+        got = gpu_ctx.matrix(key, as_distance=True).astype(np.int64)
+        want = _oracle_triangle(genomes, key, True)
+        tol = 0 if key in CHEAP else FLOAT_TOL_MICRO
+        assert np.abs(got - want).max() <= tol, key
+    hit, length = gpu_ctx.numerators("aai")
+    k = 0
+    for i in range(n):
+        for j in range(i, n):
+            if i != j and (i % 9 == 1 or j == n - 1 or i == 0):
+                assert (hit[k], length[k]) == po.aai_parts(genomes[i], genomes[j]), (i, j)
+            k += 1
 
 
 def test_ragged_sizes_cross_tile_boundaries(gpu_ctx):
