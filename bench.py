@@ -290,7 +290,7 @@ def run_native(args):
     # ---- e2e: host buffers in, host buffer out, through the C ABI, every step ----
     e2e = None
     if world == 1:
-        host_out = np.empty(tri, dtype=np.int32)
+        host_out = torch.empty(tri, dtype=torch.int32).pin_memory().numpy()     # pinned result buffer
         arrays = [table.genome_ptr, table.pham_id, table.copies, table.len_sum]
         if need_seqs:
             arrays += [table.seq_off, table.residues]

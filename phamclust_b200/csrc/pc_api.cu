@@ -199,6 +199,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     for (auto &t : ctx->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -303,13 +304,9 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     if (gene_cursor >= (1ll << 31))
         return pc_fail(ctx, PC_EINVAL, "too many genes (%lld)", (long long)gene_cursor);
 
-    // CSC by stable counting sort: members of a pham in ascending genome order
+    // per-pham member counts -> CSC pointers; the member lists themselves are only
+    // needed by the alignment planner and are built there on demand
     for (int64_t p = 0; p < n_phams; ++p) pham_count[p + 1] += pham_count[p];
-    std::vector<int64_t> members(nnz);
-    {
-        std::vector<int64_t> cursor(pham_count.begin(), pham_count.end() - 1);
-        for (int64_t k = 0; k < nnz; ++k) members[cursor[pham_id[k]]++] = k;
-    }
 
     ctx->N = n_genomes; ctx->P = n_phams; ctx->nnz = nnz;
     ctx->h_genome_ptr.assign(genome_ptr, genome_ptr + n_genomes + 1);
@@ -319,7 +316,8 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     ctx->h_entry_genome.swap(entry_genome);
     ctx->h_entry_first_gene.swap(entry_first_gene);
     ctx->h_pham_ptr.swap(pham_count);
-    ctx->h_pham_members.swap(members);
+    ctx->h_pham_members.clear();
+    ctx->bits_ready = false;
     ctx->max_copies = max_copies; ctx->max_len_sum = max_len;
     ctx->n_genes_total = gene_cursor;
     ctx->have_seqs = false;
@@ -346,10 +344,6 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     PC_TRY(upload(ctx, ctx->d_den_len, den_len.data(), n_genomes));
     PC_TRY(pc_stage_end(ctx));
     // den_* are stack-owned vectors: the copies above must finish before return
-    PC_TRY(devbuf_reserve(ctx, ctx->d_bits, (size_t)n_genomes * ctx->W * sizeof(uint32_t)));
-    PC_TRY(pc_stage_begin(ctx, PC_T_PACK));
-    PC_TRY(pc_launch_pack_bits(ctx, 0, 0, ctx->d_bits.as<uint32_t>()));
-    PC_TRY(pc_stage_end(ctx));
     PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_table = true;
     return PC_OK;
@@ -512,6 +506,13 @@ static int bit_length(uint32_t v)
 static int prepare_terms(pc_ctx *ctx, int metric, int *n_terms_out)
 {
     std::vector<PopcTerm> terms;
+    if (!ctx->bits_ready) {          // presence bit rows are only packed when this engine runs
+        PC_TRY(devbuf_reserve(ctx, ctx->d_bits, (size_t)ctx->N * ctx->W * sizeof(uint32_t)));
+        PC_TRY(pc_stage_begin(ctx, PC_T_PACK));
+        PC_TRY(pc_launch_pack_bits(ctx, 0, 0, ctx->d_bits.as<uint32_t>()));
+        PC_TRY(pc_stage_end(ctx));
+        ctx->bits_ready = true;
+    }
     const uint32_t *bits = ctx->d_bits.as<uint32_t>();
     if (metric == PC_GCS || metric == PC_JC) {
         terms.push_back({bits, bits, 1});
@@ -589,6 +590,13 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
     AlignPlan &pl = ctx->plan;
     if (pl.part == part && pl.n_parts == n_parts) return PC_OK;
     HostTimer host_timer(ctx, PC_T_HOST_PLAN);
+    if (ctx->h_pham_members.size() != (size_t)ctx->nnz) {
+        // CSC by stable counting sort: members of a pham in ascending genome order
+        ctx->h_pham_members.assign(ctx->nnz, 0);
+        std::vector<int64_t> cursor(ctx->h_pham_ptr.begin(), ctx->h_pham_ptr.end() - 1);
+        for (int64_t k = 0; k < ctx->nnz; ++k)
+            ctx->h_pham_members[cursor[ctx->h_pham_id[k]]++] = k;
+    }
     struct PhamInfo { int64_t pham; double cost; };
     std::vector<PhamInfo> infos;
     for (int64_t p = 0; p < ctx->P; ++p) {
@@ -796,6 +804,50 @@ extern "C" int pc_matrix_rows(pc_ctx *ctx, int metric, int as_distance, int ppos
     if (!out_on_device) {
         PC_TRY(devbuf_reserve(ctx, ctx->d_out, (size_t)count * sizeof(int32_t)));
         out_dev = ctx->d_out.as<int32_t>();
+    }
+    if (metric <= PC_AF && !out_on_device && count > (int64_t(1) << 22)) {
+        // host output of a large slice: compute row blocks (whole 256-row tiles, about
+        // equal pair counts) and ship each finished block on a second stream while
+        // the next one is computed -- the D2H of 4 B/pair otherwise dominates
+        if (!ctx->copy_stream)
+            PC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        const int n_blocks = (int)std::min<int64_t>(16, std::max<int64_t>(2, count >> 22));
+        std::vector<int64_t> bounds{row_begin};
+        for (int b = 1; b < n_blocks; ++b) {
+            const int64_t want = pc_tri_index(ctx->N, row_begin, row_begin) + count * b / n_blocks;
+            int64_t lo = bounds.back(), hi = row_end;
+            while (lo < hi) {                       // smallest row whose block start >= want
+                const int64_t mid = (lo + hi) / 2;
+                if (pc_tri_index(ctx->N, mid, mid) >= want) hi = mid; else lo = mid + 1;
+            }
+            lo = std::min(row_end, (lo + 255) / 256 * 256);
+            if (lo > bounds.back() && lo < row_end) bounds.push_back(lo);
+        }
+        bounds.push_back(row_end);
+        cudaEvent_t ev = nullptr, c0 = nullptr, c1 = nullptr;
+        PC_TRY(take_event(ctx, &ev));
+        PC_TRY(take_event(ctx, &c0));
+        PC_TRY(take_event(ctx, &c1));
+        for (size_t b = 0; b + 1 < bounds.size(); ++b) {
+            const int64_t off = slice_len(ctx, row_begin, bounds[b]);
+            const int64_t len = slice_len(ctx, bounds[b], bounds[b + 1]);
+            PC_TRY(contract_rows(ctx, metric, as_distance, 0, bounds[b], bounds[b + 1], out_dev + off));
+            PC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+            PC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+            if (b == 0) PC_CUDA(ctx, cudaEventRecord(c0, ctx->copy_stream));
+            PC_CUDA(ctx, cudaMemcpyAsync(out + off, out_dev + off, (size_t)len * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        PC_CUDA(ctx, cudaEventRecord(c1, ctx->copy_stream));
+        PC_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        PC_CUDA(ctx, cudaEventElapsedTime(&ms, c0, c1));
+        ctx->stage_ms[PC_T_D2H] += ms;
+        ctx->event_pool.push_back(ev);
+        ctx->event_pool.push_back(c0);
+        ctx->event_pool.push_back(c1);
+        return maybe_collect(ctx);
     }
     if (metric <= PC_AF) {
         PC_TRY(contract_rows(ctx, metric, as_distance, 0, row_begin, row_end, out_dev));

@@ -122,6 +122,7 @@ struct pc_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // D2H of finished row blocks, overlapped with compute
     cudaStream_t stream = nullptr;
     std::string err;
     int engine = PC_ENGINE_AUTO;
@@ -145,7 +146,8 @@ struct pc_ctx {
     DevBuf d_pham_col;                             // pham id -> operand column, -1 = dropped
     DevBuf d_den_phams, d_den_genes, d_den_len;   // int32 [N]
     int64_t W = 0;                                 // words per bit row (multiple of 32)
-    DevBuf d_bits;                                 // presence bit rows [N][W]
+    DevBuf d_bits;                                 // presence bit rows [N][W] (popc engine, lazy)
+    bool bits_ready = false;
     DevBuf d_planes;                               // weight bit planes
     int planes_kind = -1, planes_count = 0;        // what d_planes currently holds
     DevBuf d_terms;

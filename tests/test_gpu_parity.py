@@ -335,6 +335,13 @@ def test_checksums_at_benchmark_size_c3(gpu_ctx):
     jc = gpu_ctx.matrix("jc").astype(np.int64)
     gcs = gpu_ctx.matrix("gcs").astype(np.int64)
     assert jc.min() >= 0 and jc.max() <= 1000000 and (jc >= gcs).all()   # jc sim <= gcs sim
+    # the pipelined host path (row blocks shipped while the next is computed) equals
+    # the single-launch device path
+    import torch
+    out = torch.empty(tri_len(n), dtype=torch.int32, device=torch.device("cuda", gpu_ctx.device))
+    gpu_ctx.matrix_rows("jc", True, 0, n, out_device_ptr=out.data_ptr())
+    gpu_ctx.sync()
+    assert np.array_equal(out.cpu().numpy().astype(np.int64), jc)
 
 
 def test_peq_properties_on_phage_table(gpu_ctx):
