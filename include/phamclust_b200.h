@@ -193,6 +193,13 @@ int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
                 int64_t *alignments, int64_t *contract_launches,
                 int64_t *align_launches);
 int pc_reset_counters(pc_ctx *ctx);
+enum {
+    PC_STAT_LOGICAL_ALIGNMENTS = 0, /* _align calls the reference would make (metrics.py:215)   */
+    PC_STAT_UNIQUE_GENES = 1,       /* distinct translations among the loaded genes              */
+    PC_STAT_OPERAND_COLUMNS = 2,    /* phams held by >= 2 genomes (contraction K)                */
+    PC_STAT_GENES = 3
+};
+int pc_stat(pc_ctx *ctx, int which, int64_t *out);
 
 /* -------- host-side text formats (no GPU) -------- */
 /*

@@ -19,7 +19,7 @@ STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h",
 EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_stream",
            "pc_set_engine", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",
            "pc_matrix_rows", "pc_align_accumulate", "pc_numerators",
-           "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters",
+           "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters", "pc_stat",
            "pc_write_matrix", "pc_parse_squareform", "pc_scan_tsv", "pc_io_last_error")
 
 _lib = None
@@ -56,6 +56,7 @@ def load_library():
     lib.pc_timings.argtypes = [vp, vp, i32]
     lib.pc_counters.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.pc_reset_counters.argtypes = [vp]
+    lib.pc_stat.argtypes = [vp, i32, vp]
     lib.pc_write_matrix.argtypes = [ctypes.c_char_p, i64, vp, vp, ctypes.c_char_p, vp, i32]
     lib.pc_parse_squareform.argtypes = [ctypes.c_char_p, i64, i64, vp, vp, vp]
     lib.pc_scan_tsv.argtypes = [ctypes.c_char_p, i64, i64, vp]
@@ -211,6 +212,14 @@ class Context:
         self._check(self._lib.pc_counters(self._h, *[ctypes.byref(v) for v in vals]))
         keys = ("launches", "dp_cells", "alignments", "contract_launches", "align_launches")
         return {k: v.value for k, v in zip(keys, vals)}
+
+    def stats(self):
+        out = {}
+        for which, key in enumerate(("logical_alignments", "unique_genes", "operand_columns", "genes")):
+            v = ctypes.c_int64()
+            self._check(self._lib.pc_stat(self._h, which, ctypes.byref(v)))
+            out[key] = v.value
+        return out
 
     def reset_counters(self):
         self._check(self._lib.pc_reset_counters(self._h))

@@ -98,7 +98,11 @@ struct UnitArgs {
     unsigned long long *blk_counts;   // [n_blocks][PC_NW_NCFG] tasks, then exclusive offsets
     unsigned long long *cfg_total;    // [PC_NW_NCFG] tasks per config
     unsigned long long *cfg_base;     // [PC_NW_NCFG] first task of each config
-    int64_t *unit_task_off;           // [n_units] first task of every unit
+    // task table (open addressing): key = canon_q << 32 | canon_r
+    const int32_t *canon;             // gene -> canonical gene (same translation)
+    unsigned long long *ht_keys;
+    unsigned long long *ht_vals;
+    uint64_t ht_mask;                 // capacity - 1 (power of two)
 };
 
 // ---------------------------------------------------------------------------
@@ -115,7 +119,7 @@ struct AlignPlan {           // host+device prep for one (part, n_parts)
     int32_t max_gene_len = 0;
     DevBuf ph_mem_off, ph_unit_off;
     DevBuf mem_genome, mem_first_gene, mem_copies;
-    DevBuf blk_counts, cfg_info, unit_task_off;
+    DevBuf blk_counts, cfg_info, ht_keys, ht_vals;
 };
 
 struct pc_ctx {
@@ -160,6 +164,9 @@ struct pc_ctx {
     int64_t n_genes = 0;
     std::vector<int32_t> h_gene_len;
     DevBuf d_codes, d_gene_off, d_gene_len, d_raw, d_raw_off, d_lut;
+    DevBuf d_canon;                                // gene -> smallest gene with the same translation
+    DevBuf d_dedup[8];                             // scratch of pc_build_canonical_genes (kept: cudaFree stalls)
+    int64_t n_unique_genes = 0;
     DevBuf d_subtab[2];                            // [0] identity, [1] ppos
     int code_of_byte[256];
     int n_codes = 0;
@@ -176,7 +183,7 @@ struct pc_ctx {
     std::vector<cudaEvent_t> event_pool;
     double stage_ms[PC_T_COUNT] = {0};
     int64_t launches = 0, contract_launches = 0, align_launches = 0;
-    int64_t dp_cells = 0, alignments = 0;
+    int64_t dp_cells = 0, alignments = 0, logical_alignments = 0;
 };
 
 // stage timing helpers (events on ctx->stream)
@@ -205,6 +212,7 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
                      const uint8_t *code_lut, int64_t n_genes, uint8_t *codes);
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
 int pc_i8_supported(const pc_ctx *ctx, int metric);
+int pc_build_canonical_genes(pc_ctx *ctx);
 
 // DP kernel configs: a subgroup of G lanes per alignment, K ref columns per lane
 // (G*K columns per pass).  0..14: G in {4,8,16} x K in {8,12,16,20,24};

@@ -1,11 +1,14 @@
 // pc_gather.cu -- the kernels either side of the DP:
 //   * encode:  raw residue bytes -> 5-bit codes in a 16B-aligned arena
-//   * classify / scatter: (pham, member a, member b) units -> ordered gene-pair
-//     tasks, bucketed on the device by DP kernel config
+//   * classify / scan / finalize: (pham, member a, member b) units -> one DP task
+//     per DISTINCT ordered pair of sequences (hash table over canonical gene
+//     ids), bucketed on the device by DP kernel config
 //   * gather:  K5, best match per anchor gene -> per-genome-pair accumulators
 //   * epilogue: K6 for aai / peq
 // Reference semantics: /root/reference/src/phamclust/metrics.py:203-232 (aai),
 // :235-253 (peq), statistics.py:22 (length-weighted mean).
+#include <algorithm>
+
 #include "pc_common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -104,21 +107,53 @@ __device__ __forceinline__ UnitShape unit_shape(const Unit &t)
     return s;
 }
 
-// DP config of a unit: sized for its longest query (anchor gene) and ref (other gene)
-__device__ __forceinline__ int unit_cfg(const UnitArgs &u, const UnitShape &s)
+// ---------------------------------------------------------------------------
+// task table: one DP task per DISTINCT ordered pair of canonical genes
+// (query sequence, ref sequence).  Open-addressing hash table keyed by
+// (canon_q << 32) | canon_r; the value first holds (config, block, rank inside
+// the block) of the thread that inserted the key, then the final task index.
+// ---------------------------------------------------------------------------
+#define HT_EMPTY 0xffffffffffffffffull
+
+__device__ __forceinline__ uint64_t ht_mix(uint64_t k)
 {
-    int m = 0, n = 0;
-    for (int x = 0; x < s.n_anchor; ++x) m = max(m, u.gene_len[s.anchor0 + x]);
-    for (int y = 0; y < s.n_other; ++y) n = max(n, u.gene_len[s.other0 + y]);
-    return pc_nw_choose_cfg(m, n);
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+
+// returns the slot of `key`; *inserted tells whether this call created it
+__device__ __forceinline__ uint64_t ht_insert(unsigned long long *keys, uint64_t mask, uint64_t key, bool *inserted)
+{
+    uint64_t h = ht_mix(key) & mask;
+    for (;;) {
+        const unsigned long long cur = keys[h];
+        if (cur == key) { *inserted = false; return h; }
+        if (cur == HT_EMPTY) {
+            const unsigned long long prev = atomicCAS(keys + h, HT_EMPTY, (unsigned long long)key);
+            if (prev == HT_EMPTY) { *inserted = true; return h; }
+            if (prev == key) { *inserted = false; return h; }
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ uint64_t ht_find(const unsigned long long *keys, uint64_t mask, uint64_t key)
+{
+    uint64_t h = ht_mix(key) & mask;
+    while (keys[h] != key) h = (h + 1) & mask;
+    return h;
 }
 
 #define UNIT_THREADS 256
 
-// pass A: tasks per (block, config)
+// pass A: insert every alignment's (canonical query, canonical ref) pair; the
+// inserting thread picks the DP config of the pair and takes a rank inside
+// (block, config)
 __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const UnitArgs u)
 {
-    __shared__ unsigned long long s_cnt[PC_NW_NCFG];
+    __shared__ unsigned int s_cnt[PC_NW_NCFG];
     if (threadIdx.x < PC_NW_NCFG) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int64_t u0 = (int64_t)blockIdx.x * u.units_per_block;
@@ -126,7 +161,18 @@ __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const Unit
     for (int64_t unit = u0 + threadIdx.x; unit < u1; unit += UNIT_THREADS) {
         const Unit t = decode_unit(u, unit);
         const UnitShape s = unit_shape(t);
-        atomicAdd(&s_cnt[unit_cfg(u, s)], (unsigned long long)(s.n_anchor * s.n_other));
+        for (int x = 0; x < s.n_anchor; ++x)
+            for (int y = 0; y < s.n_other; ++y) {
+                const uint32_t cq = (uint32_t)u.canon[s.anchor0 + x];   // _align(anchor_gene, other_gene)
+                const uint32_t cr = (uint32_t)u.canon[s.other0 + y];
+                bool inserted;
+                const uint64_t h = ht_insert(u.ht_keys, u.ht_mask, ((uint64_t)cq << 32) | cr, &inserted);
+                if (inserted) {
+                    const int cfg = pc_nw_choose_cfg(u.gene_len[cq], u.gene_len[cr]);
+                    const unsigned int rank = atomicAdd(&s_cnt[cfg], 1u);
+                    u.ht_vals[h] = ((unsigned long long)cfg << 56) | ((unsigned long long)blockIdx.x << 32) | rank;
+                }
+            }
     }
     __syncthreads();
     if (threadIdx.x < PC_NW_NCFG)
@@ -156,69 +202,22 @@ __global__ void scan_blocks_kernel(const UnitArgs u)
     }
 }
 
-// pass C: deterministic slot of every unit inside its config's task range,
-// then expansion into ordered (query, ref) gene pairs
-__global__ void __launch_bounds__(UNIT_THREADS)
-scatter_units_kernel(const UnitArgs u, int32_t *__restrict__ task_q, int32_t *__restrict__ task_r)
+// pass C: every occupied slot becomes a task at config base + block offset + rank
+__global__ void finalize_tasks_kernel(const UnitArgs u, int32_t *__restrict__ task_q,
+                                      int32_t *__restrict__ task_r)
 {
-    __shared__ unsigned long long s_run[PC_NW_NCFG];
-    __shared__ unsigned int s_wtot[UNIT_THREADS / 32][PC_NW_NCFG];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < PC_NW_NCFG)
-        s_run[threadIdx.x] = u.cfg_base[threadIdx.x] +
-                             u.blk_counts[(int64_t)blockIdx.x * PC_NW_NCFG + threadIdx.x];
-    for (int x = threadIdx.x; x < (UNIT_THREADS / 32) * PC_NW_NCFG; x += UNIT_THREADS)
-        (&s_wtot[0][0])[x] = 0;
-    __syncthreads();
-    const int64_t u0 = (int64_t)blockIdx.x * u.units_per_block;
-    const int64_t u1 = min(u0 + u.units_per_block, u.n_units);
-    for (int64_t base = u0; base < u1; base += UNIT_THREADS) {
-        const int64_t unit = base + threadIdx.x;
-        const bool valid = unit < u1;
-        Unit t;
-        UnitShape s;
-        int cfg = -1;
-        unsigned int nt = 0;
-        if (valid) {
-            t = decode_unit(u, unit);
-            s = unit_shape(t);
-            cfg = unit_cfg(u, s);
-            nt = (unsigned int)(s.n_anchor * s.n_other);
-        }
-        // rank among the lanes of this warp that share the config
-        unsigned int pre = 0, tot = 0;
-        bool leader = true;
-        for (int l = 0; l < 32; ++l) {
-            const int cl = __shfl_sync(0xffffffffu, cfg, l);
-            const unsigned int vl = __shfl_sync(0xffffffffu, nt, l);
-            if (cl == cfg) {
-                tot += vl;
-                if (l < lane) { pre += vl; leader = false; }
-            }
-        }
-        if (valid && leader) s_wtot[warp][cfg] = tot;
-        __syncthreads();
-        if (valid) {
-            unsigned long long off = s_run[cfg] + pre;
-            for (int w = 0; w < warp; ++w) off += s_wtot[w][cfg];
-            u.unit_task_off[unit] = (int64_t)off;
-            for (int x = 0; x < s.n_anchor; ++x)
-                for (int y = 0; y < s.n_other; ++y) {
-                    const int64_t k = (int64_t)off + (int64_t)x * s.n_other + y;
-                    task_q[k] = s.anchor0 + x;      // _align(anchor_gene, other_gene)
-                    task_r[k] = s.other0 + y;
-                }
-        }
-        __syncthreads();
-        if (threadIdx.x < PC_NW_NCFG) {
-            unsigned long long add = 0;
-            for (int w = 0; w < UNIT_THREADS / 32; ++w) {
-                add += s_wtot[w][threadIdx.x];
-                s_wtot[w][threadIdx.x] = 0;
-            }
-            s_run[threadIdx.x] += add;
-        }
-        __syncthreads();
+    const uint64_t cap = u.ht_mask + 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += stride) {
+        const unsigned long long key = u.ht_keys[h];
+        if (key == HT_EMPTY) continue;
+        const unsigned long long v = u.ht_vals[h];
+        const int cfg = (int)(v >> 56);
+        const int64_t blk = (int64_t)((v >> 32) & 0xffffffull);
+        const unsigned long long idx = u.cfg_base[cfg] + u.blk_counts[blk * PC_NW_NCFG + cfg] + (v & 0xffffffffull);
+        task_q[idx] = (int32_t)(key >> 32);
+        task_r[idx] = (int32_t)(key & 0xffffffffull);
+        u.ht_vals[h] = idx;
     }
 }
 
@@ -235,13 +234,15 @@ __global__ void gather_units_kernel(const UnitArgs u, const uint32_t *__restrict
          unit < u.n_units; unit += stride) {
         const Unit t = decode_unit(u, unit);
         const UnitShape s = unit_shape(t);
-        const int64_t task_off = u.unit_task_off[unit];
         unsigned long long sum_hit = 0, sum_len = 0;
         for (int x = 0; x < s.n_anchor; ++x) {
             unsigned long long best_hit = 0, best_len = 0;
             bool have = false;
+            const uint32_t cq = (uint32_t)u.canon[s.anchor0 + x];
             for (int y = 0; y < s.n_other; ++y) {
-                const uint32_t v = hitlen[task_off + (int64_t)x * s.n_other + y];
+                const uint32_t cr = (uint32_t)u.canon[s.other0 + y];
+                const uint64_t slot = ht_find(u.ht_keys, u.ht_mask, ((uint64_t)cq << 32) | cr);
+                const uint32_t v = hitlen[u.ht_vals[slot]];
                 const unsigned long long hit = v >> 16, len = v & 0xffffu;
                 if (len == 0) continue;           // undefined upstream (0-length alignment)
                 if (!have || hit * best_len >= best_hit * len) {
@@ -259,6 +260,7 @@ __global__ void gather_units_kernel(const UnitArgs u, const uint32_t *__restrict
 int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u)
 {
     if (u.n_units <= 0) return PC_OK;
+    PC_CUDA(ctx, cudaMemsetAsync(u.ht_keys, 0xff, sizeof(unsigned long long) * (u.ht_mask + 1), ctx->stream));
     classify_units_kernel<<<u.n_blocks, UNIT_THREADS, 0, ctx->stream>>>(u);
     PC_CUDA(ctx, cudaGetLastError());
     scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(u);
@@ -270,7 +272,9 @@ int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u)
 int pc_launch_scatter_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r)
 {
     if (u.n_units <= 0) return PC_OK;
-    scatter_units_kernel<<<u.n_blocks, UNIT_THREADS, 0, ctx->stream>>>(u, task_q, task_r);
+    const uint64_t cap = u.ht_mask + 1;
+    const int grid = (int)std::min<uint64_t>((cap + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    finalize_tasks_kernel<<<grid, 256, 0, ctx->stream>>>(u, task_q, task_r);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return PC_OK;

@@ -408,6 +408,38 @@ def test_row_blocks_and_pham_partitions_recompose(gpu_ctx):
         assert np.array_equal(out.cpu().numpy(), full)
 
 
+def test_identical_sequences_are_aligned_once(gpu_ctx):
+    """Duplicate-rich table: 40 genomes drawing their genes from 3 variants per
+    pham -> few distinct ordered sequence pairs, same integers as the oracle."""
+    rng = random.Random(9)
+    variants = {f"ph{p}": [testdata.random_protein(rng, 60, 90)] for p in range(6)}
+    for p, v in variants.items():
+        v += [testdata.mutate(rng, v[0], 0.15), testdata.mutate(rng, v[0], 0.3)]
+    genomes = []
+    for g in range(40):
+        x = Genome(f"g{g:02d}")
+        for p, v in variants.items():
+            if rng.random() < 0.8:
+                x.add(p, rng.choice(v))
+                if rng.random() < 0.2:
+                    x.add(p, rng.choice(v))
+        genomes.append(x)
+    _load(gpu_ctx, pack_genomes(genomes))
+    gpu_ctx.reset_counters()
+    hit, length = gpu_ctx.numerators("aai")
+    c, st = gpu_ctx.counters(), gpu_ctx.stats()
+    assert st["unique_genes"] <= 18 and st["genes"] > 150
+    assert c["alignments"] <= 6 * 9 and st["logical_alignments"] > 2000
+    n, k = len(genomes), 0
+    for i in range(n):
+        for j in range(i, n):
+            if i != j and (i + j) % 5 == 0:
+                assert (hit[k], length[k]) == po.aai_parts(genomes[i], genomes[j]), (i, j)
+            k += 1
+    got = gpu_ctx.matrix("peq").astype(np.int64)
+    assert np.abs(got - _oracle_triangle(genomes, "peq", True)).max() <= FLOAT_TOL_MICRO
+
+
 def test_counters_report_kernel_launches(gpu_ctx):
     table = synthetic.phage_table(40, seed=3)
     _load(gpu_ctx, table)
