@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 }
 
 template <int G, int K, bool MULTI, bool REPL, int THREADS>
-static int launch_cfg(pc_ctx *ctx, const NwArgs &args)
+static int launch_cfg(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
 {
     const size_t smem = REPL ? (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int2)
                              : (size_t)32 * 32 * sizeof(int2);
@@ -248,7 +248,7 @@ static int launch_cfg(pc_ctx *ctx, const NwArgs &args)
     const int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;   // persistent: one resident wave
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, THREADS, smem, ctx->stream>>>(args);
+    kern<<<grid, THREADS, smem, stream>>>(args);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     ctx->align_launches++;
@@ -256,10 +256,10 @@ static int launch_cfg(pc_ctx *ctx, const NwArgs &args)
 }
 
 template <int G, int K, bool MULTI, int THREADS>
-static int launch_one(pc_ctx *ctx, const NwArgs &args, bool repl)
+static int launch_one(pc_ctx *ctx, const NwArgs &args, bool repl, cudaStream_t stream)
 {
-    return repl ? launch_cfg<G, K, MULTI, true, THREADS>(ctx, args)
-                : launch_cfg<G, K, MULTI, false, THREADS>(ctx, args);
+    return repl ? launch_cfg<G, K, MULTI, true, THREADS>(ctx, args, stream)
+                : launch_cfg<G, K, MULTI, false, THREADS>(ctx, args, stream);
 }
 
 // upper bound on the warps a launch of the multi-chunk config keeps resident
@@ -271,27 +271,27 @@ int pc_nw_multichunk_warps(pc_ctx *ctx)
 // one CTA per SM (the replicated table takes 144 KB); as many warps as the
 // per-thread state of K columns leaves room for in the register file
 template <int G, int K, bool MULTI>
-static int launch_gk(pc_ctx *ctx, const NwArgs &args, bool repl)
+static int launch_gk(pc_ctx *ctx, const NwArgs &args, bool repl, cudaStream_t stream)
 {
     // (registers are split per SM sub-partition: 4/3/2 warps each -> 128/168/255 per thread)
     constexpr int THREADS = K <= 12 ? 512 : K <= 20 ? 384 : 256;
-    return launch_one<G, K, MULTI, THREADS>(ctx, args, repl);
+    return launch_one<G, K, MULTI, THREADS>(ctx, args, repl, stream);
 }
 
 template <int G>
-static int launch_k(pc_ctx *ctx, const NwArgs &args, bool repl, int K)
+static int launch_k(pc_ctx *ctx, const NwArgs &args, bool repl, int K, cudaStream_t stream)
 {
     switch (K) {
-    case 8: return launch_gk<G, 8, false>(ctx, args, repl);
-    case 12: return launch_gk<G, 12, false>(ctx, args, repl);
-    case 16: return launch_gk<G, 16, false>(ctx, args, repl);
-    case 20: return launch_gk<G, 20, false>(ctx, args, repl);
-    case 24: return launch_gk<G, 24, false>(ctx, args, repl);
+    case 8: return launch_gk<G, 8, false>(ctx, args, repl, stream);
+    case 12: return launch_gk<G, 12, false>(ctx, args, repl, stream);
+    case 16: return launch_gk<G, 16, false>(ctx, args, repl, stream);
+    case 20: return launch_gk<G, 20, false>(ctx, args, repl, stream);
+    case 24: return launch_gk<G, 24, false>(ctx, args, repl, stream);
     }
     return pc_fail(ctx, PC_EINVAL, "no DP kernel for G=%d K=%d", G, K);
 }
 
-int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg)
+int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream)
 {
     if (args.n_tasks <= 0) return PC_OK;
     if (cfg < 0 || cfg >= PC_NW_NCFG) return pc_fail(ctx, PC_EINVAL, "bad DP config %d", cfg);
@@ -300,20 +300,20 @@ int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg)
     pc_nw_cfg(cfg, G, K);
     if (cfg >= PC_NW_MULTI0) {
         switch (K) {
-        case 20: return launch_gk<32, 20, true>(ctx, args, repl);
-        case 24: return launch_gk<32, 24, true>(ctx, args, repl);
-        case 28: return launch_gk<32, 28, true>(ctx, args, repl);
-        default: return launch_gk<32, 32, true>(ctx, args, repl);
+        case 20: return launch_gk<32, 20, true>(ctx, args, repl, stream);
+        case 24: return launch_gk<32, 24, true>(ctx, args, repl, stream);
+        case 28: return launch_gk<32, 28, true>(ctx, args, repl, stream);
+        default: return launch_gk<32, 32, true>(ctx, args, repl, stream);
         }
     }
     switch (G) {
-    case 4: return launch_k<4>(ctx, args, repl, K);
-    case 8: return launch_k<8>(ctx, args, repl, K);
-    case 16: return launch_k<16>(ctx, args, repl, K);
+    case 4: return launch_k<4>(ctx, args, repl, K, stream);
+    case 8: return launch_k<8>(ctx, args, repl, K, stream);
+    case 16: return launch_k<16>(ctx, args, repl, K, stream);
     case 32:
-        if (K == 28) return launch_gk<32, 28, false>(ctx, args, repl);
-        if (K == 32) return launch_gk<32, 32, false>(ctx, args, repl);
-        return launch_k<32>(ctx, args, repl, K);
+        if (K == 28) return launch_gk<32, 28, false>(ctx, args, repl, stream);
+        if (K == 32) return launch_gk<32, 32, false>(ctx, args, repl, stream);
+        return launch_k<32>(ctx, args, repl, K, stream);
     }
     return pc_fail(ctx, PC_EINVAL, "bad DP config %d", cfg);
 }

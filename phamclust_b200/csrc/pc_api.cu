@@ -119,6 +119,8 @@ int pc_collect_timers(pc_ctx *ctx)
         ctx->event_pool.push_back(t.stop);
     }
     ctx->timers.clear();
+    for (cudaEvent_t ev : ctx->deferred_events) ctx->event_pool.push_back(ev);
+    ctx->deferred_events.clear();
     return PC_OK;
 }
 
@@ -201,6 +203,8 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (cudaStream_t st : ctx->dp_streams) if (st) cudaStreamDestroy(st);
+    for (auto ev : ctx->deferred_events) cudaEventDestroy(ev);
     delete ctx;
 }
 
@@ -652,7 +656,10 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
     std::vector<int32_t> mem_genome, mem_first_gene, mem_copies;
     int64_t n_tasks = 0;
     for (size_t pos = 0; pos < infos.size(); ++pos) {
-        if ((int)(pos % (size_t)n_parts) != part) continue;
+        // snake order (0..P-1, P-1..0, ...): plain round-robin would hand partition 0 the
+        // largest pham of every group of P
+        const size_t lap = pos / (size_t)n_parts, in_lap = pos % (size_t)n_parts;
+        if ((int)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap) != part) continue;
         const int64_t p = infos[pos].pham;
         const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
         const int64_t m = e - b;
@@ -709,12 +716,14 @@ static int ensure_counters(pc_ctx *ctx)
     return PC_OK;
 }
 
-static int ensure_spill(pc_ctx *ctx, int max_qlen, NwArgs &a)
+// every multi-chunk config gets its own spill region (they may run side by side)
+static int ensure_spill(pc_ctx *ctx, int max_qlen, NwArgs &a, int cfg)
 {
     a.spill_stride = (int64_t)max_qlen + 2;
     const int64_t warps = pc_nw_multichunk_warps(ctx);
-    PC_TRY(devbuf_reserve(ctx, ctx->d_spill, (size_t)warps * a.spill_stride * sizeof(int4)));
-    a.spill = ctx->d_spill.as<int4>();
+    const int n_multi = PC_NW_NCFG - PC_NW_MULTI0;
+    PC_TRY(devbuf_reserve(ctx, ctx->d_spill, (size_t)n_multi * warps * a.spill_stride * sizeof(int4)));
+    a.spill = ctx->d_spill.as<int4>() + (size_t)(cfg - PC_NW_MULTI0) * warps * a.spill_stride;
     return PC_OK;
 }
 
@@ -782,17 +791,38 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     a.perm = nullptr;
     a.out_hitlen = ctx->d_hitlen.as<uint32_t>();
     a.out_score = nullptr;
+    // the configs are independent: fork them over a few streams (long ones first) so
+    // that one config's tail (its last, longest alignments) overlaps the next config
     PC_TRY(pc_stage_begin(ctx, PC_T_ALIGN));
+    constexpr int N_DP_STREAMS = 4;
+    cudaEvent_t fork = nullptr, join[N_DP_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    PC_TRY(take_event(ctx, &fork));
+    PC_CUDA(ctx, cudaEventRecord(fork, ctx->stream));
+    for (int k = 0; k < N_DP_STREAMS; ++k) {
+        if (!ctx->dp_streams[k])
+            PC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->dp_streams[k], cudaStreamNonBlocking));
+        PC_TRY(take_event(ctx, &join[k]));
+        PC_CUDA(ctx, cudaStreamWaitEvent(ctx->dp_streams[k], fork, 0));
+    }
+    for (int c = PC_NW_MULTI0; c < PC_NW_NCFG; ++c)       // size the shared spill buffer once
+        if (cfg_info[c]) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
+    int next = 0;
     for (int c = PC_NW_NCFG - 1; c >= 0; --c) {
         const int64_t count = (int64_t)cfg_info[c];
         if (count == 0) continue;
         a.task_base = (int64_t)cfg_info[PC_NW_NCFG + c];
         a.n_tasks = count;
         a.work_counter = ctx->d_counters.as<unsigned long long>() + c;
-        if (c >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a));
-        PC_TRY(pc_launch_nw(ctx, a, c));
+        if (c >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
+        PC_TRY(pc_launch_nw(ctx, a, c, ctx->dp_streams[next++ % N_DP_STREAMS]));
+    }
+    for (int k = 0; k < N_DP_STREAMS; ++k) {
+        PC_CUDA(ctx, cudaEventRecord(join[k], ctx->dp_streams[k]));
+        PC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, join[k], 0));
     }
     PC_TRY(pc_stage_end(ctx));
+    ctx->deferred_events.push_back(fork);
+    for (int k = 0; k < N_DP_STREAMS; ++k) ctx->deferred_events.push_back(join[k]);
     for (int c = 0; c < PC_NW_NCFG; ++c) ctx->alignments += (int64_t)cfg_info[c];   // distinct sequence pairs
     ctx->logical_alignments += pl.n_tasks;
 
@@ -1005,8 +1035,8 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
             a.task_base = bucket_off[b];
             a.n_tasks = bucket_count[b];
             a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
-            if (b >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, max_q_multi, a));
-            PC_TRY(pc_launch_nw(ctx, a, b));
+            if (b >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, max_q_multi, a, b));
+            PC_TRY(pc_launch_nw(ctx, a, b, ctx->stream));
         }
         PC_TRY(pc_stage_end(ctx));
         ctx->alignments += n_tasks;

@@ -127,6 +127,7 @@ struct pc_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // D2H of finished row blocks, overlapped with compute
+    cudaStream_t dp_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // DP configs run side by side
     cudaStream_t stream = nullptr;
     std::string err;
     int engine = PC_ENGINE_AUTO;
@@ -181,6 +182,7 @@ struct pc_ctx {
     // ---- measurement ----
     std::vector<StageTimer> timers;
     std::vector<cudaEvent_t> event_pool;
+    std::vector<cudaEvent_t> deferred_events;      // in flight; recycled after the next stream sync
     double stage_ms[PC_T_COUNT] = {0};
     int64_t launches = 0, contract_launches = 0, align_launches = 0;
     int64_t dp_cells = 0, alignments = 0, logical_alignments = 0;
@@ -198,7 +200,7 @@ int pc_launch_pack_bits(pc_ctx *ctx, int source /*0 presence,1 copies,2 len*/,
                         int plane, uint32_t *dst);
 int pc_launch_popc_contract(pc_ctx *ctx, const PopcTerm *d_terms, int n_terms,
                             const EpilogueArgs &ep);
-int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg);
+int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream);
 int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u);
 int pc_launch_scatter_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r);
 int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen,
