@@ -366,7 +366,7 @@ def run_native(args):
         issue_peak = SM_COUNT * 128 * sm_mhz * 1e6 / DP_INSTR_PER_CELL / 1e9
         roofline = {"bound": "int-alu-pipe", "kernel": "nw_kernel<G,K> (global-alignment DP, 23 configs)",
                     "achieved": gcups, "peak": peak, "unit": "GCUPS", "frac": gcups / peak,
-                    "traffic": 4.5e6, "cells_per_step": cells / max(args.steps, 1),
+                    "traffic": 4.0e6, "cells_per_step": cells / max(args.steps, 1),
                     "kernel_ms_per_step": align_ms / max(args.steps, 1),
                     "launches_per_step": launches / max(args.steps, 1),
                     "share_of_step": align_ms / total_ms if total_ms else None,
@@ -393,7 +393,10 @@ def run_native(args):
             peak = 2.0 * peaks["bf16_tflops"]
             roofline = {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05 kind::i8 + fused epilogue)",
                         "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak,
-                        "traffic": None, "kernel_ms_per_step": contract_ms / max(args.steps, 1),
+                        # dram__bytes_read+write of one launch, ncu --set full (profiles/): only
+                        # captured for the C3 jc launch on one GPU
+                        "traffic": 3.35e9 if (args.workload == "c3" and metric == "jc" and world == 1
+                                              and n == 10000) else None, "kernel_ms_per_step": contract_ms / max(args.steps, 1),
                         "share_of_step": contract_ms / total_ms if total_ms else None,
                         "algorithmic_ops_per_launch": ops, "k_columns": k_eff * limbs,
                         "peak_basis": (f"2 x MEASURED_PEAKS.json bf16_tflops ({peak_kind}; int8 dense is not "

@@ -120,21 +120,21 @@ popc_contract_kernel(const PopcTerm *__restrict__ terms, int n_terms, int64_t wo
             }
             __syncthreads();
             if (kb + 1 < n_k) load_stage(kb + 1);
-#pragma unroll
-            for (int k4 = 0; k4 < PB_K / 4; ++k4) {
-                uint4 a[8], b[8];
+#pragma unroll 4
+            for (int k2 = 0; k2 < PB_K / 2; ++k2) {
+                // two words of K at a time: 32 operand registers instead of 64 (no spills)
+                uint2 a[8], b[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                    a[u] = *reinterpret_cast<const uint4 *>(As + (ty + 16 * u) * PB_LD + 4 * k4);
+                    a[u] = *reinterpret_cast<const uint2 *>(As + (ty + 16 * u) * PB_LD + 2 * k2);
 #pragma unroll
                 for (int v = 0; v < 8; ++v)
-                    b[v] = *reinterpret_cast<const uint4 *>(Bs + (tx + 16 * v) * PB_LD + 4 * k4);
+                    b[v] = *reinterpret_cast<const uint2 *>(Bs + (tx + 16 * v) * PB_LD + 2 * k2);
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
-                        const int c = __popc(a[u].x & b[v].x) + __popc(a[u].y & b[v].y) +
-                                      __popc(a[u].z & b[v].z) + __popc(a[u].w & b[v].w);
+                        const int c = __popc(a[u].x & b[v].x) + __popc(a[u].y & b[v].y);
                         acc[u][v] += c * mult;
                     }
             }
