@@ -19,9 +19,9 @@
 // instruction, cta_group::1; MT = 2 row tiles sharing one column tile whenever a
 // single accumulator per row tile suffices -- r1 ncu showed the 128x256 tile at
 // 55 % tensor / 55 % L2 throughput, i.e. limited by operand traffic from L2, and
-// the taller tile moves 1.5x fewer bytes per MAC), 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
-// elected lane each), warps 2-5 = epilogue (tcgen05.ld 32x32b, one TMEM lane
-// quadrant per warp).  4-stage 48 KB smem ring (128B-swizzled 128-byte K
+// the taller tile moves 1.5x fewer bytes per MAC), 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected lane each), warps 2-9 = epilogue (tcgen05.ld 32x32b; a warp may only
+// touch TMEM lane quadrant warp%4, two warps share a quadrant and split the columns).  4-stage 48 KB smem ring (128B-swizzled 128-byte K
 // slabs), mbarrier full/empty pairs, tcgen05.commit releases the slots.
 // Tensor-pipe bound: 2*K*128*256 int8 ops per tile.
 #include <cuda.h>
@@ -31,7 +31,10 @@
 #define I8_BM 128
 #define I8_BN 256
 #define I8_BK 128                 // bytes (= int8 elements) per stage
-#define I8_THREADS 192
+#ifndef I8_EPI_WARPS
+#define I8_EPI_WARPS 12           // three warps per TMEM lane quadrant, each drains a share of the columns
+#endif
+#define I8_THREADS (64 + 32 * I8_EPI_WARPS)
 #define I8_A_BYTES (I8_BM * I8_BK)
 #define I8_B_BYTES (I8_BN * I8_BK)
 #define I8_MAX_STAGES 4
@@ -273,13 +276,16 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
-        const int et = threadIdx.x - 64;              // 0..127
+        const int et = threadIdx.x - 64;              // 0 .. 32*I8_EPI_WARPS-1
+        constexpr int EPI_GROUPS = I8_EPI_WARPS / 4;  // warps sharing one TMEM lane quadrant
+        const int grp = (warp - 2) >> 2;              // this warp's share of the 8 column chunks
+        const int c_begin = grp * (I8_BN / 32) / EPI_GROUPS, c_end = (grp + 1) * (I8_BN / 32) / EPI_GROUPS;
         const EpilogueArgs &ep = a.ep;
         const int64_t n = ep.n;
         const int64_t col0 = (int64_t)bj * I8_BN;
         if (!ep.raw)
-            for (int x = et; x < I8_BN; x += 128) s_den[x] = (col0 + x < n) ? ep.den[col0 + x] : 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+            for (int x = et; x < I8_BN; x += 32 * I8_EPI_WARPS) s_den[x] = (col0 + x < n) ? ep.den[col0 + x] : 0;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");      // epilogue warps only
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -293,7 +299,7 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int64_t row_base = row_ok ? pc_tri_index(n, i, i) - out_base - i : 0;
             // column chunks entirely left of this warp's rows hold nothing to write
             const int64_t warp_row0 = ((int64_t)bi * MT + u) * I8_BM + quad * 32;
-            for (int c = 0; c < I8_BN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 if (col0 + c * 32 + 31 < warp_row0) continue;          // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(lane_addr + (uint32_t)((MT == 1 ? 0 : u) * I8_BN + c * 32), v);
