@@ -287,6 +287,8 @@ static int launch_k(pc_ctx *ctx, const NwArgs &args, bool repl, int K, cudaStrea
     case 16: return launch_gk<G, 16, false>(ctx, args, repl, stream);
     case 20: return launch_gk<G, 20, false>(ctx, args, repl, stream);
     case 24: return launch_gk<G, 24, false>(ctx, args, repl, stream);
+    case 28: return launch_gk<G, 28, false>(ctx, args, repl, stream);
+    case 32: return launch_gk<G, 32, false>(ctx, args, repl, stream);
     }
     return pc_fail(ctx, PC_EINVAL, "no DP kernel for G=%d K=%d", G, K);
 }
@@ -310,10 +312,7 @@ int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream)
     case 4: return launch_k<4>(ctx, args, repl, K, stream);
     case 8: return launch_k<8>(ctx, args, repl, K, stream);
     case 16: return launch_k<16>(ctx, args, repl, K, stream);
-    case 32:
-        if (K == 28) return launch_gk<32, 28, false>(ctx, args, repl, stream);
-        if (K == 32) return launch_gk<32, 32, false>(ctx, args, repl, stream);
-        return launch_k<32>(ctx, args, repl, K, stream);
+    case 32: return launch_k<32>(ctx, args, repl, K, stream);
     }
     return pc_fail(ctx, PC_EINVAL, "bad DP config %d", cfg);
 }

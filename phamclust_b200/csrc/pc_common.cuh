@@ -217,11 +217,11 @@ int pc_i8_supported(const pc_ctx *ctx, int metric);
 int pc_build_canonical_genes(pc_ctx *ctx);
 
 // DP kernel configs: a subgroup of G lanes per alignment, K ref columns per lane
-// (G*K columns per pass).  0..14: G in {4,8,16} x K in {8,12,16,20,24};
-// 15..21: G = 32, K in {8,...,32}; 22..25: multi-chunk (G = 32, K in
-// {20,24,28,32}: the ref is cut into ceil(n / 32K) column chunks, any length).
-#define PC_NW_NCFG 26
-#define PC_NW_MULTI0 22             // first multi-chunk config
+// (G*K columns per pass).  0..27: G in {4,8,16,32} x K in {8,12,...,32};
+// 28..31: multi-chunk (G = 32, K in {20,24,28,32}: the ref is cut into
+// ceil(n / 32K) column chunks, any length).
+#define PC_NW_NCFG 32
+#define PC_NW_MULTI0 28             // first multi-chunk config
 #define PC_NW_COST_PER_CELL 18      // SASS instructions per cell (see pc_align.cu)
 #define PC_NW_COST_PER_STEP 15      // per row-step overhead (shuffles, boundary, loop)
 
@@ -232,8 +232,7 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #endif
 PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
 {
-    if (c < 15) { G = 4 << (c / 5); K = 8 + 4 * (c % 5); }
-    else if (c < PC_NW_MULTI0) { G = 32; K = 8 + 4 * (c - 15); }
+    if (c < PC_NW_MULTI0) { G = 4 << (c / 7); K = 8 + 4 * (c % 7); }
     else { G = 32; K = 20 + 4 * (c - PC_NW_MULTI0); }
 }
 
