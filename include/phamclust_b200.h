@@ -79,6 +79,13 @@ int pc_version(void);
  * legacy default stream); external == 0 restores the ctx's own stream.      */
 int pc_set_stream(pc_ctx *ctx, void *cuda_stream, int external);
 int pc_set_engine(pc_ctx *ctx, int engine);
+/* Which global-alignment DP kernels aai/peq may use.  Both produce the same
+ * (matched, columns, score) for every alignment; AUTO picks per alignment.  */
+enum {
+    PC_DP_AUTO = 0,     /* LEX kernel where its 32-bit word provably fits    */
+    PC_DP_CLASSIC = 1   /* always the separate-counter kernel                */
+};
+int pc_set_dp_mode(pc_ctx *ctx, int mode);
 int pc_sync(pc_ctx *ctx);
 
 /* -------- inputs -------------------------------------------------------- */
@@ -197,7 +204,8 @@ enum {
     PC_STAT_LOGICAL_ALIGNMENTS = 0, /* _align calls the reference would make (metrics.py:215)   */
     PC_STAT_UNIQUE_GENES = 1,       /* distinct translations among the loaded genes              */
     PC_STAT_OPERAND_COLUMNS = 2,    /* phams held by >= 2 genomes (contraction K)                */
-    PC_STAT_GENES = 3
+    PC_STAT_GENES = 3,
+    PC_STAT_LEX_ALIGNMENTS = 4      /* DP tasks run by the LEX kernel since pc_reset_counters    */
 };
 int pc_stat(pc_ctx *ctx, int which, int64_t *out);
 

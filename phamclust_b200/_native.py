@@ -4,20 +4,23 @@ There is no CPU fallback anywhere in this package: if the shared library is
 missing, or no sm_100 GPU is visible, the calls below raise.
 """
 import ctypes
+import os
 import pathlib
 
 import numpy as np
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libphamclust_b200.so"
+# PHAMCLUST_B200_LIB: an alternative build of the same library (kernel experiments)
+LIB_PATH = pathlib.Path(os.environ.get("PHAMCLUST_B200_LIB") or _HERE / "libphamclust_b200.so")
 
 METRIC_IDS = {"gcs": 0, "jc": 1, "pocp": 2, "af": 3, "aai": 4, "peq": 5}
 ENGINE_IDS = {"auto": 0, "popc": 1, "i8mma": 2}
+DP_MODE_IDS = {"auto": 0, "classic": 1}
 STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h",
           "host_table", "host_seqs", "host_plan")
 
 EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_stream",
-           "pc_set_engine", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",
+           "pc_set_engine", "pc_set_dp_mode", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",
            "pc_matrix_rows", "pc_align_accumulate", "pc_numerators",
            "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters", "pc_stat",
            "pc_write_matrix", "pc_parse_squareform", "pc_scan_tsv", "pc_io_last_error")
@@ -44,6 +47,7 @@ def load_library():
     lib.pc_version.argtypes = []
     lib.pc_set_stream.argtypes = [vp, vp, i32]
     lib.pc_set_engine.argtypes = [vp, i32]
+    lib.pc_set_dp_mode.argtypes = [vp, i32]
     lib.pc_sync.argtypes = [vp]
     lib.pc_load_table.argtypes = [vp, i64, i64, vp, vp, vp, vp]
     lib.pc_load_sequences.argtypes = [vp, i64, vp, vp]
@@ -127,6 +131,10 @@ class Context:
 
     def set_engine(self, engine):
         self._check(self._lib.pc_set_engine(self._h, ENGINE_IDS.get(engine, engine)))
+
+    def set_dp_mode(self, mode):
+        """"auto": LEX DP kernel where its 32-bit word provably fits; "classic": never."""
+        self._check(self._lib.pc_set_dp_mode(self._h, DP_MODE_IDS.get(mode, mode)))
 
     def sync(self):
         self._check(self._lib.pc_sync(self._h))
@@ -215,7 +223,8 @@ class Context:
 
     def stats(self):
         out = {}
-        for which, key in enumerate(("logical_alignments", "unique_genes", "operand_columns", "genes")):
+        for which, key in enumerate(("logical_alignments", "unique_genes", "operand_columns", "genes",
+                                     "lex_alignments")):
             v = ctypes.c_int64()
             self._check(self._lib.pc_stat(self._h, which, ctypes.byref(v)))
             out[key] = v.value

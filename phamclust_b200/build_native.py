@@ -26,9 +26,16 @@ def _newest_source_mtime():
     return max(f.stat().st_mtime for f in files)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
+    """``out``: build a variant (PC_NVCC_EXTRA defines) next to the product library."""
+    if out is not None:
+        return _compile(pathlib.Path(out), verbose, log=False)
     if not force and OUT.exists() and OUT.stat().st_mtime >= _newest_source_mtime():
         return OUT
+    return _compile(OUT, verbose, log=True)
+
+
+def _compile(OUT, verbose, log):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     extra = shlex.split(os.environ.get("PC_NVCC_EXTRA", ""))      # e.g. -DPC_NW_XL_FMA (experiments)
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(OUT), *[str(CSRC / s) for s in SOURCES]]
@@ -37,9 +44,11 @@ def build(force=False, verbose=False):
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode:
         raise RuntimeError("nvcc failed building libphamclust_b200.so")
-    (HERE / "build.log").write_text(proc.stdout + proc.stderr)
+    if log:
+        (HERE / "build.log").write_text(proc.stdout + proc.stderr)
     return OUT
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    variant = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose=True, out=variant[0] if variant else None))

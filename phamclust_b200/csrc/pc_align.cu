@@ -233,6 +233,218 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// LEX kernel: the same recurrences with the counters riding INSIDE the score
+// word, for alignments whose scores and counters fit 32 bits together
+// (pc_nw_lex_ok: min(m, n) < 2^B and a proven score range < 2^S).
+//
+//   word = score << (2B+2)  |  prio << 2B  |  diag steps << B  |  matched
+//
+// A signed max over such words picks the higher score; equal scores are
+// decided by the 2-bit priority field, which encodes exactly the tie rules of
+// Appendix A: stored H carries 0, E carries 1 and F carries 2 (so an extension
+// beats an opening of equal score, and F beats E inside H's max), the diagonal
+// candidate gets 3 from the table.  The three candidates of a max always
+// differ in (score, prio), so the payload never takes part in a decision: it
+// is simply carried by the winner -- no ISETP/SEL per cell, 9 ALU-pipe
+// instructions instead of 12, two shuffles per row step instead of four.
+// The payload counts diagonal steps d and matches; columns = m + n - d.
+//   E = (viaddmax(E, -ext, Xleft)) | PRIO_E      F likewise from above
+//   H = vimax3(Xdiag + T[q][r], F, E)            T = (s + open, prio 3, d+1, hit)
+//   X = (H & ~PRIO) - open
+// Scores are biased per alignment so that the proven range
+// [-3 open - (m + n), min(rowmax-sum(q), rowmax-sum(r))] sits inside S bits;
+// cells of padding columns may wrap, nothing flows from them to real cells.
+// ---------------------------------------------------------------------------
+template <int G, int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
+{
+    extern __shared__ __align__(16) int s_lex[];
+    const int lane = threadIdx.x & 31;
+    constexpr int open = PC_GAP_OPEN_DEFAULT, ext = PC_GAP_EXTEND_DEFAULT;
+    constexpr int B = PC_NW_LEX_BITS, SH = PC_NW_LEX_SHIFT, S = 32 - SH;
+    constexpr int U = 1 << SH;                       // one score unit
+    constexpr int CMASK = (1 << B) - 1;
+    constexpr int PRIO_E = (PC_H_PRIORITY_DIAG_DEL_INS ? 1 : 2) << (2 * B);
+    constexpr int PRIO_F = (PC_H_PRIORITY_DIAG_DEL_INS ? 2 : 1) << (2 * B);
+    constexpr int PRIO_D = 3 << (2 * B);
+    constexpr int PMASK = 3 << (2 * B);
+    constexpr int OPENU = open * U, EXTU = ext * U;
+    constexpr int NEG = (-(1 << (S - 1)) + 2) * U;   // below every real word, survives one -ext
+    static_assert(PC_GAP_TIE_EXTENDS, "the LEX priorities encode 'ties extend'");
+#ifdef PC_NW_LEX_FMA
+    const int one = a.gap_extend;                    // == 1 at run time, opaque to ptxas
+#endif
+
+    // s_lex[(q*24 + r)*32 + lane] = (score + open, prio 3, one diagonal step, hit)
+    for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
+        const int e = x >> 5;
+        const int2 v = a.subtab[(e / NW_TAB_CODES) * 32 + (e % NW_TAB_CODES)];
+        s_lex[x] = (v.x + open) * U + PRIO_D + (1 << B) + (v.y >> 16);
+    }
+    __syncthreads();
+
+    constexpr int SUBS = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int QSTRIDE = NW_TAB_CODES * 32;
+    const int sub = lane / G;
+    const int sl = lane % G;
+    const int *tab_lane = s_lex + lane;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)SUBS);
+        base = __shfl_sync(FULL, base, 0);
+        if ((int64_t)base >= a.n_tasks) break;
+
+        const int64_t t = (int64_t)base + sub;
+        const bool valid = t < a.n_tasks;
+        int m = 0, n = 0;
+        int64_t slot = 0;
+        const uint8_t *q = a.codes, *r = a.codes;
+        if (valid) {
+            slot = a.task_base + t;
+            if (a.perm) slot = a.perm[slot];
+            const int qg = a.task_q[slot], rg = a.task_r[slot];
+            m = a.gene_len[qg];
+            n = a.gene_len[rg];
+            q = a.codes + a.gene_off[qg];
+            r = a.codes + a.gene_off[rg];
+        }
+        if (valid && sl == 0 && a.cell_counter)
+            atomicAdd(a.cell_counter, (unsigned long long)m * (unsigned long long)n);
+        const int steps = __reduce_max_sync(FULL, m) + G - 1;
+        // H[0][0] = bias puts the lowest reachable word just above NEG (pc_nw_lex_ok)
+        const int bias = -(1 << (S - 1)) + PC_NW_LEX_FLOOR + (m + n);
+
+        const int col0 = sl * K;
+        int Xp[K], Fp[K], rc[K];
+#pragma unroll
+        for (int w = 0; w < K / 4; ++w) {
+            const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(r + col0) + w);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int code = (int)((word >> (8 * b)) & 31u);
+                if (code >= NW_TAB_CODES) code = 0;      // padding past the gene only
+                rc[4 * w + b] = code << 5;
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < K; ++x) {
+            const int j = col0 + x + 1;                  // 1-based column
+            Xp[x] = (bias - open - (j - 1) * ext - open) * U;   // H[0][j] - open, no diagonal steps yet
+            Fp[x] = NEG;
+        }
+        int diagX = (bias + ((col0 == 0) ? 0 : -open - (col0 - 1) * ext) - open) * U;
+        int outX = 0, outE = NEG;
+
+        for (int s = 1; s <= steps; ++s) {
+            int inX = __shfl_up_sync(FULL, outX, 1, G);
+            int inE = __shfl_up_sync(FULL, outE, 1, G);
+            const int i = s - sl;
+            const bool active = (i >= 1) && (i <= m);
+            if (sl == 0) {
+                inX = (bias - open - (i - 1) * ext - open) * U;  // H[i][0] - open
+                inE = NEG;
+            }
+            if (active) {
+                int qc = (int)(__ldg(q + (i - 1)) & 31u);
+                if (qc >= NW_TAB_CODES) qc = 0;
+                const int *trow = tab_lane + qc * QSTRIDE;
+                int xl = inX, el = inE;
+                int xd = diagX;
+                diagX = inX;
+#pragma unroll
+                for (int x = 0; x < K; ++x) {
+                    const int tw = trow[rc[x]];
+                    const int f = __viaddmax_s32(Fp[x], -EXTU, Xp[x]) | PRIO_F;
+                    const int e = __viaddmax_s32(el, -EXTU, xl) | PRIO_E;
+#ifdef PC_NW_LEX_FMA
+                    const int hd = fma_add(xd, one, tw);
+#else
+                    const int hd = xd + tw;
+#endif
+                    const int h = __vimax3_s32(hd, f, e);
+                    xd = Xp[x];
+#ifdef PC_NW_LEX_FMA
+                    xl = fma_add(h & ~PMASK, one, -OPENU);
+#else
+                    xl = (h & ~PMASK) - OPENU;
+#endif
+                    Xp[x] = xl; Fp[x] = f;
+                    el = e;
+                }
+                outX = xl; outE = el;
+            }
+        }
+        if (valid) {
+            bool owner;
+            int score, matched, columns;
+            if (n == 0) {            // no DP columns: the answer is a boundary cell
+                owner = (sl == 0);
+                score = (m == 0) ? 0 : -open - (m - 1) * ext;
+                matched = 0;
+                columns = m;
+            } else {
+                const int last = n - 1;
+                owner = (sl == last / K);
+                const int xs = last % K;
+                int word = 0;
+#pragma unroll
+                for (int x = 0; x < K; ++x)
+                    if (x == xs) word = Xp[x];
+                score = (word >> SH) + open - bias;
+                matched = word & CMASK;
+                columns = m + n - ((word >> B) & CMASK);
+            }
+            if (owner) {
+                a.out_hitlen[slot] = ((uint32_t)matched << 16) | (uint32_t)columns;
+                if (a.out_score) a.out_score[slot] = score;
+            }
+        }
+    }
+}
+
+template <int G, int K>
+static int launch_lex(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
+{
+    // 3 words of state per column: more warps fit than in the classic kernel
+    // (registers per thread by ptxas: 57 / 71 / 86 / 101 / 117 / 133 / 148 for K = 8 .. 32)
+    constexpr int THREADS = K <= 12 ? 768 : K <= 24 ? 512 : 384;
+    const size_t smem = (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int);
+    auto kern = nw_lex_kernel<G, K, THREADS>;
+    PC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 0;
+    PC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const int64_t groups = (args.n_tasks + (32 / G) - 1) / (32 / G);
+    const int64_t want = (groups + (THREADS / 32) - 1) / (THREADS / 32);
+    const int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, THREADS, smem, stream>>>(args);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->align_launches++;
+    return PC_OK;
+}
+
+template <int G>
+static int launch_lex_k(pc_ctx *ctx, const NwArgs &args, int K, cudaStream_t stream)
+{
+    switch (K) {
+    case 8: return launch_lex<G, 8>(ctx, args, stream);
+    case 12: return launch_lex<G, 12>(ctx, args, stream);
+    case 16: return launch_lex<G, 16>(ctx, args, stream);
+    case 20: return launch_lex<G, 20>(ctx, args, stream);
+    case 24: return launch_lex<G, 24>(ctx, args, stream);
+    case 28: return launch_lex<G, 28>(ctx, args, stream);
+    case 32: return launch_lex<G, 32>(ctx, args, stream);
+    }
+    return pc_fail(ctx, PC_EINVAL, "no LEX DP kernel for G=%d K=%d", G, K);
+}
+
 template <int G, int K, bool MULTI, bool REPL, int THREADS>
 static int launch_cfg(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
 {
@@ -300,6 +512,15 @@ int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream)
     const bool repl = ctx->n_codes <= NW_TAB_CODES;
     int G, K;
     pc_nw_cfg(cfg, G, K);
+    if (cfg >= PC_NW_LEX0) {
+        if (!repl) return pc_fail(ctx, PC_EINVAL, "LEX DP config %d needs the 24-code table", cfg);
+        switch (G) {
+        case 4: return launch_lex_k<4>(ctx, args, K, stream);
+        case 8: return launch_lex_k<8>(ctx, args, K, stream);
+        case 16: return launch_lex_k<16>(ctx, args, K, stream);
+        default: return launch_lex_k<32>(ctx, args, K, stream);
+        }
+    }
     if (cfg >= PC_NW_MULTI0) {
         switch (K) {
         case 20: return launch_gk<32, 20, true>(ctx, args, repl, stream);

@@ -172,6 +172,8 @@ extern "C" int pc_init(int device_id, pc_ctx **out)
         return pc_fail(nullptr, PC_ECUDA, "cudaStreamCreate failed");
     }
     ctx->stream = ctx->own_stream;
+    if (const char *mode = getenv("PC_DP_MODE"))        // measurement aid: "classic" = never the LEX DP kernel
+        ctx->dp_mode = strcmp(mode, "classic") == 0 ? PC_DP_CLASSIC : PC_DP_AUTO;
     *out = ctx;
     return PC_OK;
 }
@@ -192,7 +194,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_pham_col, &ctx->d_copies, &ctx->d_len_sum,
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
                       &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_codes,
-                      &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_canon, &ctx->d_subtab[0],
+                      &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_canon, &ctx->d_gene_hi, &ctx->d_subtab[0],
                       &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
                       &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
                       &ctx->d_acc, &ctx->d_out};
@@ -229,6 +231,15 @@ extern "C" int pc_set_engine(pc_ctx *ctx, int engine)
     if (engine < PC_ENGINE_AUTO || engine > PC_ENGINE_I8MMA)
         return pc_fail(ctx, PC_EINVAL, "unknown engine %d", engine);
     ctx->engine = engine;
+    return PC_OK;
+}
+
+extern "C" int pc_set_dp_mode(pc_ctx *ctx, int mode)
+{
+    PC_ENTER(ctx);
+    if (mode != PC_DP_AUTO && mode != PC_DP_CLASSIC)
+        return pc_fail(ctx, PC_EINVAL, "unknown DP mode %d", mode);
+    ctx->dp_mode = mode;
     return PC_OK;
 }
 
@@ -523,6 +534,19 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     dbg_mark("seqs: synced");
     PC_TRY(pc_stage_begin(ctx, PC_T_PACK));
     PC_TRY(pc_build_canonical_genes(ctx));
+    ctx->h_gene_hi.clear();
+    if (ctx->n_codes <= 24) {
+        // per-residue best substitution score, >= 0 (the 24-code table only)
+        int rowmax[32];
+        for (int a = 0; a < 32; ++a) {
+            int best = 0;
+            for (int b = 0; b < 24; ++b)
+                best = std::max(best, (int)PC_BLOSUM62[ctx->code_matrix_index[a < 24 ? a : 23]][ctx->code_matrix_index[b]]);
+            rowmax[a] = best;
+        }
+        PC_TRY(devbuf_reserve(ctx, ctx->d_gene_hi, (size_t)std::max<int64_t>(n_genes, 1) * sizeof(int32_t)));
+        PC_TRY(pc_launch_gene_bound(ctx, rowmax, ctx->d_gene_hi.as<int32_t>()));
+    }
     PC_TRY(pc_stage_end(ctx));
     dbg_mark("seqs: canonical ids");
     ctx->plan.part = ctx->plan.n_parts = -1;
@@ -706,6 +730,12 @@ static void fill_nw_common(pc_ctx *ctx, NwArgs &a, int ppos)
     a.cell_counter = ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG;
 }
 
+// the LEX DP kernel needs the 24-code replicated table and the per-gene bounds
+static bool lex_allowed(const pc_ctx *ctx)
+{
+    return PC_NW_LEX_ENABLED && ctx->dp_mode == PC_DP_AUTO && ctx->n_codes <= 24 && ctx->d_gene_hi.p;
+}
+
 // counters layout: [0..PC_NW_NCFG) work counters, [PC_NW_NCFG] cumulative cells
 static int ensure_counters(pc_ctx *ctx)
 {
@@ -721,7 +751,7 @@ static int ensure_spill(pc_ctx *ctx, int max_qlen, NwArgs &a, int cfg)
 {
     a.spill_stride = (int64_t)max_qlen + 2;
     const int64_t warps = pc_nw_multichunk_warps(ctx);
-    const int n_multi = PC_NW_NCFG - PC_NW_MULTI0;
+    const int n_multi = PC_NW_LEX0 - PC_NW_MULTI0;
     PC_TRY(devbuf_reserve(ctx, ctx->d_spill, (size_t)n_multi * warps * a.spill_stride * sizeof(int4)));
     a.spill = ctx->d_spill.as<int4>() + (size_t)(cfg - PC_NW_MULTI0) * warps * a.spill_stride;
     return PC_OK;
@@ -753,6 +783,7 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     u.mem_first_gene = pl.mem_first_gene.as<int32_t>();
     u.mem_copies = pl.mem_copies.as<int32_t>();
     u.gene_len = ctx->d_gene_len.as<int32_t>();
+    u.gene_hi = lex_allowed(ctx) ? ctx->d_gene_hi.as<int32_t>() : nullptr;
     u.n_genomes = ctx->N;
     {
         int64_t blocks = (pl.n_units + 255) / 256;
@@ -804,7 +835,7 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
         PC_TRY(take_event(ctx, &join[k]));
         PC_CUDA(ctx, cudaStreamWaitEvent(ctx->dp_streams[k], fork, 0));
     }
-    for (int c = PC_NW_MULTI0; c < PC_NW_NCFG; ++c)       // size the shared spill buffer once
+    for (int c = PC_NW_MULTI0; c < PC_NW_LEX0; ++c)       // size the shared spill buffer once
         if (cfg_info[c]) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
     int next = 0;
     for (int c = PC_NW_NCFG - 1; c >= 0; --c) {
@@ -813,7 +844,7 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
         a.task_base = (int64_t)cfg_info[PC_NW_NCFG + c];
         a.n_tasks = count;
         a.work_counter = ctx->d_counters.as<unsigned long long>() + c;
-        if (c >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
+        if (c >= PC_NW_MULTI0 && c < PC_NW_LEX0) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
         PC_TRY(pc_launch_nw(ctx, a, c, ctx->dp_streams[next++ % N_DP_STREAMS]));
     }
     for (int k = 0; k < N_DP_STREAMS; ++k) {
@@ -824,6 +855,7 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     ctx->deferred_events.push_back(fork);
     for (int k = 0; k < N_DP_STREAMS; ++k) ctx->deferred_events.push_back(join[k]);
     for (int c = 0; c < PC_NW_NCFG; ++c) ctx->alignments += (int64_t)cfg_info[c];   // distinct sequence pairs
+    for (int c = PC_NW_LEX0; c < PC_NW_NCFG; ++c) ctx->lex_alignments += (int64_t)cfg_info[c];
     ctx->logical_alignments += pl.n_tasks;
 
     PC_TRY(pc_stage_begin(ctx, PC_T_GATHER));
@@ -993,6 +1025,13 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
     if (n_tasks < 0 || (n_tasks > 0 && (!query_gene || !ref_gene || !out)))
         return pc_fail(ctx, PC_EINVAL, "pc_alignment_identities: bad arguments");
     if (n_tasks == 0) return PC_OK;
+    const bool use_lex = lex_allowed(ctx);
+    if (use_lex && (int64_t)ctx->h_gene_hi.size() != ctx->n_genes) {
+        ctx->h_gene_hi.resize((size_t)ctx->n_genes);
+        PC_CUDA(ctx, cudaMemcpyAsync(ctx->h_gene_hi.data(), ctx->d_gene_hi.p, (size_t)ctx->n_genes * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     // processing order: by kernel config of the ref length, largest first
     std::vector<int64_t> bucket_count(PC_NW_NCFG, 0);
     std::vector<int> bucket(n_tasks);
@@ -1000,9 +1039,11 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
     for (int64_t t = 0; t < n_tasks; ++t) {
         if (query_gene[t] < 0 || query_gene[t] >= ctx->n_genes || ref_gene[t] < 0 || ref_gene[t] >= ctx->n_genes)
             return pc_fail(ctx, PC_EINVAL, "task %lld names a gene outside [0,%lld)", (long long)t, (long long)ctx->n_genes);
-        bucket[t] = pc_nw_choose_cfg(ctx->h_gene_len[query_gene[t]], ctx->h_gene_len[ref_gene[t]]);
+        const int lq = ctx->h_gene_len[query_gene[t]], lr = ctx->h_gene_len[ref_gene[t]];
+        const bool lex = use_lex && pc_nw_lex_ok(lq, lr, ctx->h_gene_hi[query_gene[t]], ctx->h_gene_hi[ref_gene[t]]);
+        bucket[t] = pc_nw_choose_cfg(lq, lr, lex);
         bucket_count[bucket[t]]++;
-        if (bucket[t] >= PC_NW_MULTI0)
+        if (bucket[t] >= PC_NW_MULTI0 && bucket[t] < PC_NW_LEX0)
             max_q_multi = std::max(max_q_multi, ctx->h_gene_len[query_gene[t]]);
     }
     std::vector<int64_t> bucket_off(PC_NW_NCFG + 1, 0);
@@ -1035,11 +1076,12 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
             a.task_base = bucket_off[b];
             a.n_tasks = bucket_count[b];
             a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
-            if (b >= PC_NW_MULTI0) PC_TRY(ensure_spill(ctx, max_q_multi, a, b));
+            if (b >= PC_NW_MULTI0 && b < PC_NW_LEX0) PC_TRY(ensure_spill(ctx, max_q_multi, a, b));
             PC_TRY(pc_launch_nw(ctx, a, b, ctx->stream));
         }
         PC_TRY(pc_stage_end(ctx));
         ctx->alignments += n_tasks;
+        for (int b = PC_NW_LEX0; b < PC_NW_NCFG; ++b) ctx->lex_alignments += bucket_count[b];
     }
     std::vector<uint32_t> hl((size_t)n_tasks * 2);
     std::vector<int32_t> score(n_tasks);
@@ -1124,6 +1166,7 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
     case PC_STAT_UNIQUE_GENES: *out = ctx->n_unique_genes; break;
     case PC_STAT_OPERAND_COLUMNS: *out = ctx->P_eff; break;
     case PC_STAT_GENES: *out = ctx->n_genes; break;
+    case PC_STAT_LEX_ALIGNMENTS: *out = ctx->lex_alignments; break;
     default: return pc_fail(ctx, PC_EINVAL, "pc_stat: unknown statistic %d", which);
     }
     return PC_OK;
@@ -1137,6 +1180,7 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
     ctx->launches = ctx->contract_launches = ctx->align_launches = 0;
     ctx->alignments = 0;
     ctx->logical_alignments = 0;
+    ctx->lex_alignments = 0;
     if (ctx->d_counters.p) {
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG, 0,
                                      sizeof(unsigned long long), ctx->stream));

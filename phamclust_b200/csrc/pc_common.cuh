@@ -91,6 +91,7 @@ struct UnitArgs {
     const int32_t *mem_first_gene;
     const int32_t *mem_copies;
     const int32_t *gene_len;
+    const int32_t *gene_hi;      // per-gene score bound; NULL = never use the LEX DP kernel
     int64_t n_genomes;
     // device-side bucketing of the units by DP kernel config
     int64_t units_per_block;     // contiguous units owned by one classify/scatter block
@@ -166,6 +167,9 @@ struct pc_ctx {
     std::vector<int32_t> h_gene_len;
     DevBuf d_codes, d_gene_off, d_gene_len, d_raw, d_raw_off, d_lut;
     DevBuf d_canon;                                // gene -> smallest gene with the same translation
+    DevBuf d_gene_hi;                              // per-gene upper bound of any DP score (LEX eligibility)
+    std::vector<int32_t> h_gene_hi;                // host copy, fetched on demand (test hook)
+    int dp_mode = PC_DP_AUTO;
     DevBuf d_dedup[8];                             // scratch of pc_build_canonical_genes (kept: cudaFree stalls)
     int64_t n_unique_genes = 0;
     DevBuf d_subtab[2];                            // [0] identity, [1] ppos
@@ -185,7 +189,7 @@ struct pc_ctx {
     std::vector<cudaEvent_t> deferred_events;      // in flight; recycled after the next stream sync
     double stage_ms[PC_T_COUNT] = {0};
     int64_t launches = 0, contract_launches = 0, align_launches = 0;
-    int64_t dp_cells = 0, alignments = 0, logical_alignments = 0;
+    int64_t dp_cells = 0, alignments = 0, logical_alignments = 0, lex_alignments = 0;
 };
 
 // stage timing helpers (events on ctx->stream)
@@ -212,6 +216,7 @@ int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
 int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
                      const int64_t *gene_off, const int32_t *gene_len,
                      const uint8_t *code_lut, int64_t n_genes, uint8_t *codes);
+int pc_launch_gene_bound(pc_ctx *ctx, const int *rowmax32, int32_t *gene_hi);
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
 int pc_i8_supported(const pc_ctx *ctx, int metric);
 int pc_build_canonical_genes(pc_ctx *ctx);
@@ -219,11 +224,22 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 // DP kernel configs: a subgroup of G lanes per alignment, K ref columns per lane
 // (G*K columns per pass).  0..27: G in {4,8,16,32} x K in {8,12,...,32};
 // 28..31: multi-chunk (G = 32, K in {20,24,28,32}: the ref is cut into
-// ceil(n / 32K) column chunks, any length).
-#define PC_NW_NCFG 32
+// ceil(n / 32K) column chunks, any length); 32..59: the same single-pass G x K
+// grid on the LEX kernel (counters inside the score word, pc_align.cu) for the
+// alignments pc_nw_lex_ok admits.
+#define PC_NW_NCFG 60
 #define PC_NW_MULTI0 28             // first multi-chunk config
+#define PC_NW_LEX0 32               // first LEX config
 #define PC_NW_COST_PER_CELL 18      // SASS instructions per cell (see pc_align.cu)
 #define PC_NW_COST_PER_STEP 15      // per row-step overhead (shuffles, boundary, loop)
+#define PC_NW_LEX_COST_PER_CELL 12  // ALU-pipe bound: 9 half-rate instructions vs 12
+#define PC_NW_LEX_COST_PER_STEP 10
+
+// LEX word: score << SHIFT | prio << 2*BITS | diagonal steps << BITS | matched
+#define PC_NW_LEX_BITS 9
+#define PC_NW_LEX_SHIFT (2 * PC_NW_LEX_BITS + 2)
+#define PC_NW_LEX_FLOOR 40          // H[0][0] sits FLOOR + m + n above the most negative score
+#define PC_NW_LEX_ENABLED PC_GAP_TIE_EXTENDS
 
 #ifdef __CUDACC__
 #define PC_HD __host__ __device__
@@ -232,28 +248,50 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #endif
 PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
 {
+    if (c >= PC_NW_LEX0) c -= PC_NW_LEX0;
     if (c < PC_NW_MULTI0) { G = 4 << (c / 7); K = 8 + 4 * (c % 7); }
     else { G = 32; K = 20 + 4 * (c - PC_NW_MULTI0); }
 }
 
+// May the (m-row query, n-column ref) alignment run on the LEX kernel?  Both
+// counters are bounded by min(m, n); every real H/E/F/X value lies in
+// [-3 open - (m + n), hi] with hi = min over the two sequences of the summed
+// per-residue best substitution score (rowmax >= 0 for every residue), and the
+// kernel biases scores by 2^(S-1) - FLOOR - (m + n).
+PC_HD inline bool pc_nw_lex_ok(int m, int n, int hi_q, int hi_r)
+{
+#if PC_NW_LEX_ENABLED
+    const int mn = m < n ? m : n;
+    const long long hi = hi_q < hi_r ? hi_q : hi_r;
+    return mn < (1 << PC_NW_LEX_BITS) &&
+           hi + m + n + PC_NW_LEX_FLOOR + 24 < (1ll << (32 - PC_NW_LEX_SHIFT));
+#else
+    return false;
+#endif
+}
+
 // cheapest config for an m-row query against n ref columns: issue slots per
 // alignment ~ chunks x (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp
-PC_HD inline int pc_nw_choose_cfg(int m, int n)
+PC_HD inline int pc_nw_choose_cfg(int m, int n, bool lex)
 {
-    int best = PC_NW_NCFG - 1;
+    int best = PC_NW_LEX0 - 1;
     long long best_cost = -1;
     for (int c = 0; c < PC_NW_NCFG; ++c) {
         int G, K;
         pc_nw_cfg(c, G, K);
         long long chunks = 1;
-        if (c < PC_NW_MULTI0) {
+        long long per_cell = PC_NW_COST_PER_CELL, per_step = PC_NW_COST_PER_STEP;
+        if (c >= PC_NW_LEX0) {
+            if (!lex || G * K < n) continue;
+            per_cell = PC_NW_LEX_COST_PER_CELL;
+            per_step = PC_NW_LEX_COST_PER_STEP;
+        } else if (c < PC_NW_MULTI0) {
             if (G * K < n) continue;
         } else {
             chunks = (n + G * K - 1) / (G * K);
             if (chunks < 2) continue;             // single-pass configs cover it without the spill
         }
-        const long long cost = chunks * (long long)(m + G - 1) *
-                               (K * PC_NW_COST_PER_CELL + PC_NW_COST_PER_STEP) * G;
+        const long long cost = chunks * (long long)(m + G - 1) * (K * per_cell + per_step) * G;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;

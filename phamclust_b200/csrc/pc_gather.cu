@@ -51,6 +51,47 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
     return PC_OK;
 }
 
+// per gene: sum over its residues of the best substitution score the residue
+// can ever get (rowmax >= 0) -- the upper bound of every DP value of an
+// alignment the gene takes part in (pc_nw_lex_ok)
+struct RowMax { int v[32]; };
+
+__global__ void gene_bound_kernel(const uint8_t *__restrict__ codes,
+                                  const int64_t *__restrict__ gene_off,
+                                  const int32_t *__restrict__ gene_len, RowMax rm,
+                                  int64_t n_genes, int32_t *__restrict__ gene_hi)
+{
+    __shared__ int s_rm[32];
+    if (threadIdx.x < 32) s_rm[threadIdx.x] = rm.v[threadIdx.x];
+    __syncthreads();
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t g = warp; g < n_genes; g += n_warps) {
+        const uint8_t *src = codes + gene_off[g];
+        const int len = gene_len[g];
+        int sum = 0;
+        for (int x = lane; x < len; x += 32) sum += s_rm[src[x] & 31];
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) gene_hi[g] = sum;
+    }
+}
+
+int pc_launch_gene_bound(pc_ctx *ctx, const int *rowmax32, int32_t *gene_hi)
+{
+    if (ctx->n_genes <= 0) return PC_OK;
+    RowMax rm;
+    for (int k = 0; k < 32; ++k) rm.v[k] = rowmax32[k];
+    int64_t blocks = (ctx->n_genes * 32 + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    gene_bound_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_codes.as<uint8_t>(), ctx->d_gene_off.as<int64_t>(),
+                                                    ctx->d_gene_len.as<int32_t>(), rm, ctx->n_genes, gene_hi);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PC_OK;
+}
+
 // ---------------------------------------------------------------------------
 // units: (pham, member a, member b) with a < b in ascending genome order
 // ---------------------------------------------------------------------------
@@ -168,7 +209,9 @@ __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const Unit
                 bool inserted;
                 const uint64_t h = ht_insert(u.ht_keys, u.ht_mask, ((uint64_t)cq << 32) | cr, &inserted);
                 if (inserted) {
-                    const int cfg = pc_nw_choose_cfg(u.gene_len[cq], u.gene_len[cr]);
+                    const int lq = u.gene_len[cq], lr = u.gene_len[cr];
+                    const bool lex = u.gene_hi && pc_nw_lex_ok(lq, lr, u.gene_hi[cq], u.gene_hi[cr]);
+                    const int cfg = pc_nw_choose_cfg(lq, lr, lex);
                     const unsigned int rank = atomicAdd(&s_cnt[cfg], 1u);
                     u.ht_vals[h] = ((unsigned long long)cfg << 56) | ((unsigned long long)blockIdx.x << 32) | rank;
                 }
@@ -180,6 +223,7 @@ __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const Unit
 }
 
 // pass B: per config, exclusive scan over blocks; config bases in launch order
+static_assert(PC_NW_NCFG <= 64, "scan_blocks_kernel runs one thread per config in a 64-thread block");
 __global__ void scan_blocks_kernel(const UnitArgs u)
 {
     const int c = threadIdx.x;
@@ -263,7 +307,7 @@ int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u)
     PC_CUDA(ctx, cudaMemsetAsync(u.ht_keys, 0xff, sizeof(unsigned long long) * (u.ht_mask + 1), ctx->stream));
     classify_units_kernel<<<u.n_blocks, UNIT_THREADS, 0, ctx->stream>>>(u);
     PC_CUDA(ctx, cudaGetLastError());
-    scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(u);
+    scan_blocks_kernel<<<1, 64, 0, ctx->stream>>>(u);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     return PC_OK;

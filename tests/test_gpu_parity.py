@@ -134,7 +134,16 @@ def _genes_table(seqs):
                        np.ones(n, dtype=np.uint32), np.diff(off).astype(np.uint32), off, res)
 
 
-def test_golden_alignment_vectors(gpu_ctx):
+@pytest.fixture(params=["auto", "classic"])
+def dp_mode(request, gpu_ctx):
+    """Both DP kernels: "auto" routes every alignment whose word fits to the LEX
+    kernel (counters inside the score word), "classic" never does."""
+    gpu_ctx.set_dp_mode(request.param)
+    yield request.param
+    gpu_ctx.set_dp_mode("auto")
+
+
+def test_golden_alignment_vectors(gpu_ctx, dp_mode):
     cases = load_golden("alignments.json")
     seqs, q, r = [], [], []
     for c in cases:
@@ -148,7 +157,7 @@ def test_golden_alignment_vectors(gpu_ctx):
                            for k in bad[:3]]
 
 
-def test_random_alignments_bit_exact_all_kernel_configs(gpu_ctx):
+def test_random_alignments_bit_exact_all_kernel_configs(gpu_ctx, dp_mode):
     """Lengths chosen to land in every DP config (32..1024 columns per pass and
     the multi-chunk configs with 2-4 column chunks), tie-rich alphabets included."""
     rng = random.Random(77)
@@ -171,7 +180,45 @@ def test_random_alignments_bit_exact_all_kernel_configs(gpu_ctx):
                            for k in bad[:5]]
 
 
-def test_non_standard_residues_and_case(gpu_ctx):
+def test_lex_kernel_at_the_edges_of_its_word(gpu_ctx):
+    """The LEX DP kernel packs score | priority | diagonal steps | matches into 32
+    bits (9-bit counters, 12-bit biased score).  Lengths around 511, score bounds
+    around the admission limit (W scores 11 against itself), one very long partner
+    (the m + n floor), all-gap and tie-heavy inputs: every alignment must equal the
+    explicit-traceback oracle whichever kernel pc_nw_lex_ok routes it to."""
+    rng = random.Random(511)
+    seqs = ["W" * k for k in (200, 250, 262, 263, 264, 270, 300, 372, 511, 512)]
+    seqs += ["A" * k for k in (100, 509, 510, 511, 512, 513)]
+    seqs += ["AG" * 255, "GA" * 255 + "A", "AG" * 256, "P" * 511, "C" * 400]
+    for cap in (500, 505, 509, 510, 511, 512, 513, 520):
+        for alpha in ("AG", "WC", testdata.AA):
+            a = testdata.random_protein(rng, cap, cap, alpha)
+            seqs += [a, testdata.mutate(rng, a, 0.1, alpha), testdata.mutate(rng, a, 0.7, alpha)]
+    for cap in (60, 100, 300, 511):
+        seqs.append(testdata.random_protein(rng, cap, cap, testdata.AA))
+    seqs += [testdata.random_protein(rng, k, k, testdata.AA) for k in (1400, 2300, 3100)]
+    n = len(seqs)
+    q = [rng.randrange(n) for _ in range(2500)] + list(range(n))
+    r = [rng.randrange(n) for _ in range(2500)] + list(range(n))
+    _load(gpu_ctx, _genes_table(seqs))
+    off, res = _arena(seqs)
+    want = nw_c.batch(res, off, q, r, mode=0)
+    for mode in ("auto", "classic"):
+        gpu_ctx.set_dp_mode(mode)
+        gpu_ctx.reset_counters()
+        try:
+            got = gpu_ctx.alignment_identities(q, r)
+        finally:
+            gpu_ctx.set_dp_mode("auto")
+        lex = gpu_ctx.stats()["lex_alignments"]
+        # the hook runs every task twice (identity and ppos tables)
+        assert (lex > len(q)) if mode == "auto" else (lex == 0)
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (mode, [(len(seqs[q[k]]), len(seqs[r[k]]), got[k].tolist(), want[k].tolist())
+                                      for k in bad[:5]])
+
+
+def test_non_standard_residues_and_case(gpu_ctx, dp_mode):
     seqs = ["mktwACDE", "MKTWacde", "MKUXO*BZ", "MKOXU*ZB", "JJJJ", "jJjJ", "M-K.T", "M-K.T"]
     _load(gpu_ctx, _genes_table(seqs))
     q, r = [0, 2, 4, 6, 1, 3], [1, 3, 5, 7, 2, 0]
