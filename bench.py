@@ -36,12 +36,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALIGN_METRICS = ("aai", "peq")
-# SASS instructions per DP cell: 286 per 16-cell row step of nw_kernel<16,16,...>
-# (cuobjdump -sass); issue-slot roofline below
-DP_INSTR_PER_CELL = 17.9
-# of which on the ALU pipe (SEL, ISETP, VIADD, VIADDMNMX, VIMNMX3): 191 per 16 cells; ncu shows this
-# pipe 90 % busy and the FMA pipe 24 %, so the ALU pipe (16 lanes/clk/SMSP) is the binding unit
-DP_ALU_INSTR_PER_CELL = 11.94
+# SASS instructions per DP cell in the row loop (cuobjdump -sass), counted
+# over the unrolled K-cell row step of representative configs:
+#   classic nw_kernel<32,20> / <16,16>: 18.5 per cell, 10.7 of them on the ALU pipe
+#   LEX     nw_lex_kernel<16,16> / <16,24>: 11.0 per cell, 6.6 on the ALU pipe
+# ncu (profiles/r1b_ncu_dp_launches.txt) shows the ALU pipe (16 lanes/clk/SMSP) 88-95 % busy in both
+# kernels and the FMA pipe 14-27 %, so the ALU pipe is the binding unit of each
+DP_INSTR_PER_CELL = {"classic": 18.5, "lex": 11.0}
+DP_ALU_INSTR_PER_CELL = {"classic": 10.7, "lex": 6.6}
 SM_COUNT = 148
 
 
@@ -281,6 +283,7 @@ def run_native(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     counters = ctx.counters()
+    lex_cells = ctx.stats()["lex_cells"] if need_seqs else 0
     timings = ctx.timings()
     local_sum = out_local[:_native.tri_len(n, r0, r1)].to(torch.int64).sum().reshape(1)
     if world > 1:
@@ -358,24 +361,35 @@ def run_native(args):
     clk = clocks.summary()
     if need_seqs:
         cells = counters["dp_cells"]
+        cls_cells = cells - lex_cells
         align_ms = timings["align"]
         launches = max(counters["align_launches"], 1)
         gcups = cells / (align_ms * 1e-3) / 1e9 if align_ms > 0 else 0.0
         sm_mhz = clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
-        peak = SM_COUNT * 64 * sm_mhz * 1e6 / DP_ALU_INSTR_PER_CELL / 1e9
-        issue_peak = SM_COUNT * 128 * sm_mhz * 1e6 / DP_INSTR_PER_CELL / 1e9
-        roofline = {"bound": "int-alu-pipe", "kernel": "nw_kernel<G,K> (global-alignment DP, 23 configs)",
-                    "achieved": gcups, "peak": peak, "unit": "GCUPS", "frac": gcups / peak,
+        # pipe-bound time of this mix of cells: each kernel's cells x its ALU-pipe (resp. all)
+        # instructions per cell / the pipe's (resp. the issue ports') lanes per second
+        alu_lanes = SM_COUNT * 64 * sm_mhz * 1e6
+        issue_lanes = SM_COUNT * 128 * sm_mhz * 1e6
+        alu_work = lex_cells * DP_ALU_INSTR_PER_CELL["lex"] + cls_cells * DP_ALU_INSTR_PER_CELL["classic"]
+        issue_work = lex_cells * DP_INSTR_PER_CELL["lex"] + cls_cells * DP_INSTR_PER_CELL["classic"]
+        peak = cells / (alu_work / alu_lanes) / 1e9 if alu_work else 0.0
+        issue_peak = cells / (issue_work / issue_lanes) / 1e9 if issue_work else 0.0
+        roofline = {"bound": "int-alu-pipe",
+                    "kernel": "nw_lex_kernel<G,K> + nw_kernel<G,K> (global-alignment DP, one launch per config)",
+                    "achieved": gcups, "peak": peak, "unit": "GCUPS", "frac": gcups / peak if peak else None,
                     "traffic": 4.0e6, "cells_per_step": cells / max(args.steps, 1),
+                    "lex_cell_fraction": lex_cells / cells if cells else None,
                     "kernel_ms_per_step": align_ms / max(args.steps, 1),
                     "launches_per_step": launches / max(args.steps, 1),
                     "share_of_step": align_ms / total_ms if total_ms else None,
                     "issue_slot_peak": issue_peak,
                     "peak_basis": (f"ALU pipe: {SM_COUNT} SMs x 64 lanes/clk x {sm_mhz:.0f} MHz (median SM clock sampled "
-                                   f"under load) / {DP_ALU_INSTR_PER_CELL} ALU-pipe SASS instr per cell (of "
-                                   f"{DP_INSTR_PER_CELL} total); neither HBM nor tensor bound (SURVEY 8(d)); ncu: "
-                                   "sm__pipe_alu_cycles_active 90 %, DRAM traffic ~4.5 MB per launch ('of derived "
-                                   "pipe peak'); achieved counts only real cells (padding, pipeline fill excluded)")}
+                                   f"under load) / ALU-pipe SASS instr per cell, weighted by the cells each kernel ran: "
+                                   f"LEX {DP_ALU_INSTR_PER_CELL['lex']} (of {DP_INSTR_PER_CELL['lex']} total), classic "
+                                   f"{DP_ALU_INSTR_PER_CELL['classic']} (of {DP_INSTR_PER_CELL['classic']}); neither HBM nor "
+                                   "tensor bound (SURVEY 8(d)); ncu: sm__pipe_alu_cycles_active 88-95 %, DRAM traffic "
+                                   "~4 MB per launch ('of derived pipe peak'); achieved counts only real cells "
+                                   "(padding, pipeline fill excluded)")}
     else:
         contract_ms = timings["contract"]
         launches = max(counters["contract_launches"], 1)

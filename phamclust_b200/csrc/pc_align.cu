@@ -18,14 +18,18 @@
 // state, no trace table (the oracle checks this formulation against the
 // explicit traceback).
 //
-// Instruction diet (the kernel is integer-issue bound, ncu r1: 87 % issue
-// active; see DESIGN.md "K4"):
-//   * state is kept as X = H - open, so the open branch of both gap states is a
-//     plain register:  F = VIADDMNMX(Fup, -ext, Xup), opened iff X + ext > Fup;
+// Instruction diet (the kernel is bound by the integer ALU pipe; see DESIGN.md "K4"):
+//   * every state is kept DRIFTED by (i + j) * ext:  H^ = H + (i + j) ext, same for
+//     E and F.  An extension then leaves a gap state unchanged and an opening adds
+//     the constant C = ext - open, so each gap state is ONE instruction with no
+//     helper state:  F^ = VIADDMNMX(H^up, C, F^up), and "opened" is simply
+//     F^ != F^up (ties extend).  The diagonal adds score + 2 ext (in the table);
+//     comparisons inside a cell are unchanged because all its candidates carry
+//     the same drift; every boundary cell but (0, 0) is the constant ext - open;
 //   * counters are stored RELATIVE to (i + j): gap steps then add nothing and a
 //     diagonal step adds (hit << 16) - 1, which comes out of the table; the
 //     true counter is recovered once at the end as d + (m + n);
-//   * the substitution table is int2 {score + open, (hit << 16) - 1}: one
+//   * the substitution table is int2 {score + 2 ext, (hit << 16) - 1}: one
 //     LDS.64 yields both addends.  In the usual case (<= 24 residue codes) it
 //     is replicated once per lane ([24*24][32] int2 = 144 KB) so lane L only
 //     ever touches bank pair L: no bank conflicts (r1 lost 2/3 of the LSU
@@ -34,11 +38,10 @@
 
 #define NW_TAB_CODES 24       // codes of the replicated fast-path table
 
-// ncu (r1, profiles/): the DP is bound by the ALU pipe (SEL / ISETP / VIADD /
-// VIMNMX, 16 lanes/clk/SMSP, 90 % busy) while the FMA pipe idles at 24 %.  An add
+// ncu (r1, profiles/): the DP is bound by the ALU pipe (SEL / ISETP / LOP3 /
+// VIMNMX, 16 lanes/clk/SMSP, 90 % busy) while the FMA pipe idles.  An add
 // written as a*one+b with `one` a run-time 1 cannot be folded by ptxas and
-// issues as IMAD on the FMA pipe.  (Steering the selects the same way, as
-// predicated IMADs, was measured 6 % SLOWER: real IMADs are not cheap either.)
+// issues as IMAD on the FMA pipe (the LEX kernel's diagonal add; PC_NW_LEX_NO_FMA turns it off).
 __device__ __forceinline__ int fma_add(int a, int one, int b)
 {
     int d;
@@ -51,23 +54,21 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 {
     extern __shared__ __align__(16) int2 s_tab[];
     const int lane = threadIdx.x & 31;
-    // the reference never changes _align's defaults (metrics.py:160); compile-time
-    // constants let `X + ext > F` fold to `X >= F` and drop a register per column
+    // the reference never changes _align's defaults (metrics.py:160): compile-time constants
     constexpr int open = PC_GAP_OPEN_DEFAULT, ext = PC_GAP_EXTEND_DEFAULT;
-#ifdef PC_NW_XL_FMA
-    const int one = a.gap_extend;      // == 1 at run time, opaque to ptxas
-#endif
+    constexpr int C = -open + ext;     // opening a gap, in drifted units
+    constexpr int EDGE = -open + ext;  // H^ of every boundary cell but (0, 0)
     if (REPL) {
-        // s_tab[(q*24 + r)*32 + lane] = {score(q,r) + open, (hit << 16) - 1}
+        // s_tab[(q*24 + r)*32 + lane] = {score(q,r) + 2 ext, (hit << 16) - 1}
         for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
             const int e = x >> 5;
             const int2 v = a.subtab[(e / NW_TAB_CODES) * 32 + (e % NW_TAB_CODES)];
-            s_tab[x] = make_int2(v.x + open, v.y - 2);
+            s_tab[x] = make_int2(v.x + 2 * ext, v.y - 2);
         }
     } else {
         for (int x = threadIdx.x; x < 32 * 32; x += THREADS) {
             const int2 v = a.subtab[x];
-            s_tab[x] = make_int2(v.x + open, v.y - 2);
+            s_tab[x] = make_int2(v.x + 2 * ext, v.y - 2);
         }
     }
     __syncthreads();
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
         int res_x = 0, res_c = 0;   // valid on the owner lane after the last chunk
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int col0 = chunk * CAP + sl * K;   // 0-based first column of this lane
-            // per column: X = H - open, Y = X + ext, F, and the relative counters
-            int Xp[K], Fp[K], cHp[K], cFp[K], rc[K];
+            // per column: H^ and F^ of the previous row and their relative counters
+            int Hp[K], Fp[K], cHp[K], cFp[K], rc[K];
             // ref residues: K multiple of 4 and genes 16B aligned -> word loads
 #pragma unroll
             for (int w = 0; w < K / 4; ++w) {
@@ -128,18 +129,20 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
             }
 #pragma unroll
             for (int x = 0; x < K; ++x) {
-                const int j = col0 + x + 1;          // 1-based column
-                Xp[x] = -open - (j - 1) * ext - open;   // H[0][j] - open
+                Hp[x] = EDGE;                        // H^[0][j], j >= 1
                 Fp[x] = PC_NEG_INF;                  // F[0][j]
                 cHp[x] = 0;                          // cH[0][j] = (0, j)  -> relative 0
                 cFp[x] = 0;
             }
-            int diagX = ((col0 == 0) ? 0 : -open - (col0 - 1) * ext) - open;   // H[0][col0] - open
+            int diagH = (col0 == 0) ? 0 : EDGE;      // H^[0][col0]
             int diagC = 0;
-            int outX = 0, outE = PC_NEG_INF, outcH = 0, outcE = 0;
-
+            int outH = 0, outE = PC_NEG_INF, outcH = 0, outcE = 0;
+            // boundary column of a later chunk: fetched one row ahead so that the L2 round
+            // trip hides behind the K cells of the current row
+            int4 pre = make_int4(0, 0, 0, 0);
+            if (MULTI && chunk > 0 && sl == 0 && m >= 1) pre = __ldcg(spill + 1);
             for (int s = 1; s <= steps; ++s) {
-                int inX = __shfl_up_sync(FULL, outX, 1, G);
+                int inH = __shfl_up_sync(FULL, outH, 1, G);
                 int inE = __shfl_up_sync(FULL, outE, 1, G);
                 int incH = __shfl_up_sync(FULL, outcH, 1, G);
                 int incE = __shfl_up_sync(FULL, outcE, 1, G);
@@ -147,39 +150,40 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                 const bool active = (i >= 1) && (i <= m);
                 if (sl == 0) {
                     if (!MULTI || chunk == 0) {
-                        inX = -open - (i - 1) * ext - open;   // H[i][0] - open
+                        inH = EDGE;                  // H^[i][0], i >= 1
                         inE = PC_NEG_INF;
                         incH = 0;                    // cH[i][0] = (0, i) -> relative 0
                         incE = 0;
                     } else if (active) {
-                        const int4 v = __ldcg(spill + i);
-                        inX = v.x; inE = v.y; incH = v.z; incE = v.w;
+                        inH = pre.x; inE = pre.y; incH = pre.z; incE = pre.w;
+                        if (i < m) pre = __ldcg(spill + i + 1);
                     }
                 }
                 if (active) {
                     int qc = (int)(__ldg(q + (i - 1)) & 31u);
                     if (REPL && qc >= NW_TAB_CODES) qc = 0;
                     const int2 *trow = tab_lane + qc * QSTRIDE;
-                    int xl = inX, el = inE, cl = incH, ce = incE;
-                    int xd = diagX, cd = diagC;
-                    diagX = inX;
+                    int hl = inH, el = inE, cl = incH, ce = incE;
+                    int hd = diagH, cd = diagC;
+                    diagH = inH;
                     diagC = incH;
 #pragma unroll
                     for (int x = 0; x < K; ++x) {
-                        const int2 sc = trow[rc[x]];         // {score + open, (hit<<16) - 1}
-                        // F: from above.  open branch = X[i-1][j]; strict > means ties extend
+                        const int2 sc = trow[rc[x]];         // {score + 2 ext, (hit<<16) - 1}
+                        // F^ from above, E^ from the left: max(H^ + C, state), the state itself
+                        // when the gap extends
+                        const int f = __viaddmax_s32(Hp[x], C, Fp[x]);
+                        const int e = __viaddmax_s32(hl, C, el);
 #if PC_GAP_TIE_EXTENDS
-                        const bool pf = Xp[x] + ext > Fp[x];   // H-open > F-ext (folds to X >= F)
-                        const bool pe = xl + ext > el;
+                        const bool pf = f != Fp[x];          // opened iff H^ + C > F^ (strictly)
+                        const bool pe = e != el;
 #else
-                        const bool pf = Xp[x] + ext >= Fp[x];
-                        const bool pe = xl + ext >= el;
+                        const bool pf = Hp[x] + C >= Fp[x];
+                        const bool pe = hl + C >= el;
 #endif
-                        const int f = __viaddmax_s32(Fp[x], -ext, Xp[x]);
-                        const int e = __viaddmax_s32(el, -ext, xl);
                         const int cf = pf ? cHp[x] : cFp[x];
                         const int cee = pe ? cl : ce;
-                        const int hdg = xd + sc.x;           // H[i-1][j-1] + score
+                        const int hdg = hd + sc.x;           // H^[i-1][j-1] + score + 2 ext
                         const int cdg = cd + sc.y;
                         const int h = __vimax3_s32(hdg, f, e);
 #if PC_H_PRIORITY_DIAG_DEL_INS
@@ -187,19 +191,15 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 #else
                         const int ch = (h == hdg) ? cdg : (h == e) ? cee : cf;
 #endif
-                        xd = Xp[x];
+                        hd = Hp[x];
                         cd = cHp[x];
-#ifdef PC_NW_XL_FMA
-                        xl = fma_add(h, one, -open);
-#else
-                        xl = h - open;
-#endif
-                        Xp[x] = xl; Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
+                        hl = h;
+                        Hp[x] = h; Fp[x] = f; cHp[x] = ch; cFp[x] = cf;
                         el = e; cl = ch; ce = cee;
                     }
-                    outX = xl; outE = el; outcH = cl; outcE = ce;
+                    outH = hl; outE = el; outcH = cl; outcE = ce;
                     if (MULTI && sl == G - 1 && chunk + 1 < nchunks)
-                        __stcg(spill + i, make_int4(outX, outE, outcH, outcE));
+                        __stcg(spill + i, make_int4(outH, outE, outcH, outcE));
                 }
             }
             if (MULTI) __syncwarp();
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                     const int xs = last % K;
 #pragma unroll
                     for (int x = 0; x < K; ++x)
-                        if (x == xs) { res_x = Xp[x]; res_c = cHp[x]; }
+                        if (x == xs) { res_x = Hp[x]; res_c = cHp[x]; }
                 }
             }
         }
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
                 counter = m;
             } else {
                 owner = (sl == ((n - 1) % CAP) / K);
-                score = res_x + open;
+                score = res_x - (m + n) * ext;       // undo the drift
                 counter = res_c + (m + n);          // undo the (i + j) normalisation
             }
             if (owner) {
@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 
 
 // ---------------------------------------------------------------------------
-// LEX kernel: the same recurrences with the counters riding INSIDE the score
-// word, for alignments whose scores and counters fit 32 bits together
-// (pc_nw_lex_ok: min(m, n) < 2^B and a proven score range < 2^S).
+// LEX kernel: the same (drifted) recurrences with the counters riding INSIDE
+// the score word, for alignments whose scores and counters fit 32 bits
+// together (pc_nw_lex_ok: min(m, n) < 2^B and a proven score range < 2^S).
 //
 //   word = score << (2B+2)  |  prio << 2B  |  diag steps << B  |  matched
 //
@@ -247,15 +247,14 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 // beats an opening of equal score, and F beats E inside H's max), the diagonal
 // candidate gets 3 from the table.  The three candidates of a max always
 // differ in (score, prio), so the payload never takes part in a decision: it
-// is simply carried by the winner -- no ISETP/SEL per cell, 9 ALU-pipe
-// instructions instead of 12, two shuffles per row step instead of four.
+// is simply carried by the winner -- no ISETP/SEL per cell, 7 ALU-pipe
+// instructions instead of 11, two shuffles per row step instead of four.
 // The payload counts diagonal steps d and matches; columns = m + n - d.
-//   E = (viaddmax(E, -ext, Xleft)) | PRIO_E      F likewise from above
-//   H = vimax3(Xdiag + T[q][r], F, E)            T = (s + open, prio 3, d+1, hit)
-//   X = (H & ~PRIO) - open
-// Scores are biased per alignment so that the proven range
-// [-3 open - (m + n), min(rowmax-sum(q), rowmax-sum(r))] sits inside S bits;
-// cells of padding columns may wrap, nothing flows from them to real cells.
+//   F = VIADDMNMX(Hup, C, Fup) | PRIO_F         E likewise from the left
+//   H = VIMNMX3(Hdiag + T[q][r], F, E) & ~PRIO  T = (s + 2 ext, prio 3, d+1, hit)
+// Scores are biased so that the proven range of the drifted values,
+// [-2 open - ext, min(rowmax-sum(q), rowmax-sum(r)) + (m + n) ext], sits inside
+// S bits; cells of padding columns may wrap, nothing flows from them to real cells.
 // ---------------------------------------------------------------------------
 template <int G, int K, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
@@ -270,18 +269,22 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
     constexpr int PRIO_F = (PC_H_PRIORITY_DIAG_DEL_INS ? 2 : 1) << (2 * B);
     constexpr int PRIO_D = 3 << (2 * B);
     constexpr int PMASK = 3 << (2 * B);
-    constexpr int OPENU = open * U, EXTU = ext * U;
-    constexpr int NEG = (-(1 << (S - 1)) + 2) * U;   // below every real word, survives one -ext
+    constexpr int BIAS = -(1 << (S - 1)) + PC_NW_LEX_FLOOR;   // H^[0][0]
+    constexpr int CU = (ext - open) * U;             // opening a gap, drifted
+    constexpr int ORIGIN = BIAS * U;                 // H^[0][0], no diagonal steps yet
+    constexpr int EDGE = (BIAS + ext - open) * U;    // every other boundary cell
+    constexpr int NEG = (-(1 << (S - 1)) + 2) * U;   // below every real word (nothing is subtracted from it)
     static_assert(PC_GAP_TIE_EXTENDS, "the LEX priorities encode 'ties extend'");
-#ifdef PC_NW_LEX_FMA
+#ifndef PC_NW_LEX_NO_FMA
+    // the diagonal add issues as IMAD on the otherwise idle FMA pipe (measured +3.5 %)
     const int one = a.gap_extend;                    // == 1 at run time, opaque to ptxas
 #endif
 
-    // s_lex[(q*24 + r)*32 + lane] = (score + open, prio 3, one diagonal step, hit)
+    // s_lex[(q*24 + r)*32 + lane] = (score + 2 ext, prio 3, one diagonal step, hit)
     for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
         const int e = x >> 5;
         const int2 v = a.subtab[(e / NW_TAB_CODES) * 32 + (e % NW_TAB_CODES)];
-        s_lex[x] = (v.x + open) * U + PRIO_D + (1 << B) + (v.y >> 16);
+        s_lex[x] = (v.x + 2 * ext) * U + PRIO_D + (1 << B) + (v.y >> 16);
     }
     __syncthreads();
 
@@ -313,13 +316,11 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
             r = a.codes + a.gene_off[rg];
         }
         if (valid && sl == 0 && a.cell_counter)
-            atomicAdd(a.cell_counter, (unsigned long long)m * (unsigned long long)n);
+            atomicAdd(a.cell_counter + 1, (unsigned long long)m * (unsigned long long)n);
         const int steps = __reduce_max_sync(FULL, m) + G - 1;
-        // H[0][0] = bias puts the lowest reachable word just above NEG (pc_nw_lex_ok)
-        const int bias = -(1 << (S - 1)) + PC_NW_LEX_FLOOR + (m + n);
 
         const int col0 = sl * K;
-        int Xp[K], Fp[K], rc[K];
+        int Hp[K], Fp[K], rc[K];
 #pragma unroll
         for (int w = 0; w < K / 4; ++w) {
             const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(r + col0) + w);
@@ -332,50 +333,45 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
         }
 #pragma unroll
         for (int x = 0; x < K; ++x) {
-            const int j = col0 + x + 1;                  // 1-based column
-            Xp[x] = (bias - open - (j - 1) * ext - open) * U;   // H[0][j] - open, no diagonal steps yet
+            Hp[x] = EDGE;                                // H^[0][j], j >= 1
             Fp[x] = NEG;
         }
-        int diagX = (bias + ((col0 == 0) ? 0 : -open - (col0 - 1) * ext) - open) * U;
-        int outX = 0, outE = NEG;
+        int diagH = (col0 == 0) ? ORIGIN : EDGE;         // H^[0][col0]
+        int outH = 0, outE = NEG;
 
         for (int s = 1; s <= steps; ++s) {
-            int inX = __shfl_up_sync(FULL, outX, 1, G);
+            int inH = __shfl_up_sync(FULL, outH, 1, G);
             int inE = __shfl_up_sync(FULL, outE, 1, G);
             const int i = s - sl;
             const bool active = (i >= 1) && (i <= m);
             if (sl == 0) {
-                inX = (bias - open - (i - 1) * ext - open) * U;  // H[i][0] - open
+                inH = EDGE;                              // H^[i][0], i >= 1
                 inE = NEG;
             }
             if (active) {
                 int qc = (int)(__ldg(q + (i - 1)) & 31u);
                 if (qc >= NW_TAB_CODES) qc = 0;
                 const int *trow = tab_lane + qc * QSTRIDE;
-                int xl = inX, el = inE;
-                int xd = diagX;
-                diagX = inX;
+                int hl = inH, el = inE;
+                int hd = diagH;
+                diagH = inH;
 #pragma unroll
                 for (int x = 0; x < K; ++x) {
                     const int tw = trow[rc[x]];
-                    const int f = __viaddmax_s32(Fp[x], -EXTU, Xp[x]) | PRIO_F;
-                    const int e = __viaddmax_s32(el, -EXTU, xl) | PRIO_E;
-#ifdef PC_NW_LEX_FMA
-                    const int hd = fma_add(xd, one, tw);
+                    const int f = __viaddmax_s32(Hp[x], CU, Fp[x]) | PRIO_F;
+                    const int e = __viaddmax_s32(hl, CU, el) | PRIO_E;
+#ifndef PC_NW_LEX_NO_FMA
+                    const int hdg = fma_add(hd, one, tw);
 #else
-                    const int hd = xd + tw;
+                    const int hdg = hd + tw;
 #endif
-                    const int h = __vimax3_s32(hd, f, e);
-                    xd = Xp[x];
-#ifdef PC_NW_LEX_FMA
-                    xl = fma_add(h & ~PMASK, one, -OPENU);
-#else
-                    xl = (h & ~PMASK) - OPENU;
-#endif
-                    Xp[x] = xl; Fp[x] = f;
+                    const int h = __vimax3_s32(hdg, f, e) & ~PMASK;
+                    hd = Hp[x];
+                    hl = h;
+                    Hp[x] = h; Fp[x] = f;
                     el = e;
                 }
-                outX = xl; outE = el;
+                outH = hl; outE = el;
             }
         }
         if (valid) {
@@ -393,8 +389,8 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
                 int word = 0;
 #pragma unroll
                 for (int x = 0; x < K; ++x)
-                    if (x == xs) word = Xp[x];
-                score = (word >> SH) + open - bias;
+                    if (x == xs) word = Hp[x];
+                score = (word >> SH) - BIAS - (m + n) * ext;     // undo bias and drift
                 matched = word & CMASK;
                 columns = m + n - ((word >> B) & CMASK);
             }

@@ -736,12 +736,13 @@ static bool lex_allowed(const pc_ctx *ctx)
     return PC_NW_LEX_ENABLED && ctx->dp_mode == PC_DP_AUTO && ctx->n_codes <= 24 && ctx->d_gene_hi.p;
 }
 
-// counters layout: [0..PC_NW_NCFG) work counters, [PC_NW_NCFG] cumulative cells
+// counters layout: [0..PC_NW_NCFG) work counters, [PC_NW_NCFG] cumulative cells of the classic
+// DP kernel, [PC_NW_NCFG + 1] of the LEX kernel
 static int ensure_counters(pc_ctx *ctx)
 {
     if (!ctx->d_counters.p) {
-        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_NCFG + 1)));
-        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_NCFG + 1), ctx->stream));
+        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_NCFG + 2)));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_NCFG + 2), ctx->stream));
     }
     return PC_OK;
 }
@@ -1145,9 +1146,11 @@ extern "C" int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
     PC_ENTER(ctx);
     unsigned long long cells = 0;
     if (ctx->d_counters.p) {
+        unsigned long long both[2] = {0, 0};
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG,
-                                sizeof cells, cudaMemcpyDeviceToHost));
+        PC_CUDA(ctx, cudaMemcpy(both, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG,
+                                sizeof both, cudaMemcpyDeviceToHost));
+        cells = both[0] + both[1];
     }
     if (launches) *launches = ctx->launches;
     if (dp_cells) *dp_cells = (int64_t)cells;
@@ -1167,6 +1170,16 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
     case PC_STAT_OPERAND_COLUMNS: *out = ctx->P_eff; break;
     case PC_STAT_GENES: *out = ctx->n_genes; break;
     case PC_STAT_LEX_ALIGNMENTS: *out = ctx->lex_alignments; break;
+    case PC_STAT_LEX_CELLS: {
+        unsigned long long cells = 0;
+        if (ctx->d_counters.p) {
+            PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG + 1,
+                                    sizeof cells, cudaMemcpyDeviceToHost));
+        }
+        *out = (int64_t)cells;
+        break;
+    }
     default: return pc_fail(ctx, PC_EINVAL, "pc_stat: unknown statistic %d", which);
     }
     return PC_OK;
@@ -1183,7 +1196,7 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
     ctx->lex_alignments = 0;
     if (ctx->d_counters.p) {
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG, 0,
-                                     sizeof(unsigned long long), ctx->stream));
+                                     2 * sizeof(unsigned long long), ctx->stream));
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return PC_OK;

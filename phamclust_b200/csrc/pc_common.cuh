@@ -232,13 +232,13 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #define PC_NW_LEX0 32               // first LEX config
 #define PC_NW_COST_PER_CELL 18      // SASS instructions per cell (see pc_align.cu)
 #define PC_NW_COST_PER_STEP 15      // per row-step overhead (shuffles, boundary, loop)
-#define PC_NW_LEX_COST_PER_CELL 12  // ALU-pipe bound: 9 half-rate instructions vs 12
+#define PC_NW_LEX_COST_PER_CELL 11  // in units where the classic kernel costs 18 (ALU-pipe bound)
 #define PC_NW_LEX_COST_PER_STEP 10
 
 // LEX word: score << SHIFT | prio << 2*BITS | diagonal steps << BITS | matched
 #define PC_NW_LEX_BITS 9
 #define PC_NW_LEX_SHIFT (2 * PC_NW_LEX_BITS + 2)
-#define PC_NW_LEX_FLOOR 40          // H[0][0] sits FLOOR + m + n above the most negative score
+#define PC_NW_LEX_FLOOR 40          // H^[0][0] sits FLOOR above the most negative score
 #define PC_NW_LEX_ENABLED PC_GAP_TIE_EXTENDS
 
 #ifdef __CUDACC__
@@ -254,10 +254,11 @@ PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
 }
 
 // May the (m-row query, n-column ref) alignment run on the LEX kernel?  Both
-// counters are bounded by min(m, n); every real H/E/F/X value lies in
-// [-3 open - (m + n), hi] with hi = min over the two sequences of the summed
-// per-residue best substitution score (rowmax >= 0 for every residue), and the
-// kernel biases scores by 2^(S-1) - FLOOR - (m + n).
+// counters are bounded by min(m, n).  The kernel works on values drifted by
+// (i + j) ext: every real H^/E^/F^ and diagonal candidate then lies in
+// [-2 open - ext - 4, hi + (m + n) ext] with hi = min over the two sequences of
+// the summed per-residue best substitution score (rowmax >= 0 for every
+// residue), and H^[0][0] is placed FLOOR above the most negative score.
 PC_HD inline bool pc_nw_lex_ok(int m, int n, int hi_q, int hi_r)
 {
 #if PC_NW_LEX_ENABLED
@@ -271,27 +272,33 @@ PC_HD inline bool pc_nw_lex_ok(int m, int n, int hi_q, int hi_r)
 }
 
 // cheapest config for an m-row query against n ref columns: issue slots per
-// alignment ~ chunks x (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp
+// alignment ~ chunks x (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp.
+// Per G the cost of a single-pass config grows with K, so only the smallest K
+// that covers n competes; the LEX grid (when admitted) is cheaper cell for cell
+// and always covers what the classic single-pass grid covers.
 PC_HD inline int pc_nw_choose_cfg(int m, int n, bool lex)
 {
     int best = PC_NW_LEX0 - 1;
     long long best_cost = -1;
-    for (int c = 0; c < PC_NW_NCFG; ++c) {
-        int G, K;
-        pc_nw_cfg(c, G, K);
-        long long chunks = 1;
-        long long per_cell = PC_NW_COST_PER_CELL, per_step = PC_NW_COST_PER_STEP;
-        if (c >= PC_NW_LEX0) {
-            if (!lex || G * K < n) continue;
-            per_cell = PC_NW_LEX_COST_PER_CELL;
-            per_step = PC_NW_LEX_COST_PER_STEP;
-        } else if (c < PC_NW_MULTI0) {
-            if (G * K < n) continue;
-        } else {
-            chunks = (n + G * K - 1) / (G * K);
-            if (chunks < 2) continue;             // single-pass configs cover it without the spill
+    const long long per_cell = lex ? PC_NW_LEX_COST_PER_CELL : PC_NW_COST_PER_CELL;
+    const long long per_step = lex ? PC_NW_LEX_COST_PER_STEP : PC_NW_COST_PER_STEP;
+    for (int g = 0; g < 4; ++g) {
+        const int G = 4 << g;
+        int K = ((n + G - 1) / G + 3) & ~3;
+        if (K < 8) K = 8;
+        if (K > 32) continue;
+        const long long cost = (long long)(m + G - 1) * (K * per_cell + per_step) * G;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = (lex ? PC_NW_LEX0 : 0) + g * 7 + (K - 8) / 4;
         }
-        const long long cost = chunks * (long long)(m + G - 1) * (K * per_cell + per_step) * G;
+    }
+    if (best_cost >= 0) return best;      // single-pass configs cover it without the spill
+    for (int c = PC_NW_MULTI0; c < PC_NW_LEX0; ++c) {
+        const int G = 32, K = 20 + 4 * (c - PC_NW_MULTI0);
+        const long long chunks = (n + G * K - 1) / (G * K);
+        const long long cost = chunks * (long long)(m + G - 1) *
+                               (K * (long long)PC_NW_COST_PER_CELL + PC_NW_COST_PER_STEP) * G;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
