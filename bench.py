@@ -119,6 +119,10 @@ def build_workload(args):
             synthetic.attach_m_translations(table)
         name = (f"configs[2]: metric={args.metric} on synthetic.sparse_table("
                 f"n_genomes={args.genomes}, n_phams={args.phams}, seed=1)")
+    elif args.workload == "c4":
+        table = synthetic.phage_table(args.genomes, seed=2)
+        name = (f"configs[3]: metric={args.metric}, pham-sharded alignment, on synthetic.phage_table("
+                f"n_genomes={args.genomes}, seed=2) [SURVEY 8(d) C4: clusters of 50 genomes x 150-pham pools]")
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     return table, name
@@ -477,7 +481,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--metric", default=None)
     ap.add_argument("--genomes", type=int, default=None)
     ap.add_argument("--phams", type=int, default=60000)
@@ -486,9 +490,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.metric is None:
-        args.metric = "peq" if args.workload == "c2" else "jc"
+        args.metric = "jc" if args.workload == "c3" else "peq"
     if args.genomes is None:
-        args.genomes = 2000 if args.workload == "c2" else 10000
+        args.genomes = {"c2": 2000, "c3": 10000, "c4": 50000}[args.workload]
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)

@@ -206,7 +206,9 @@ enum {
     PC_STAT_OPERAND_COLUMNS = 2,    /* phams held by >= 2 genomes (contraction K)                */
     PC_STAT_GENES = 3,
     PC_STAT_LEX_ALIGNMENTS = 4,     /* DP tasks run by the LEX kernel since pc_reset_counters    */
-    PC_STAT_LEX_CELLS = 5           /* DP cells of those tasks (pc_counters' dp_cells has both)  */
+    PC_STAT_LEX_CELLS = 5,          /* DP cells of those tasks (pc_counters' dp_cells has both)  */
+    PC_STAT_DP_CONFIGS_USED = 6,    /* distinct DP kernel configs launched since the reset        */
+    PC_STAT_DP_CONFIGS = 7          /* DP kernel configs the chooser can pick for the loaded data */
 };
 int pc_stat(pc_ctx *ctx, int which, int64_t *out);
 

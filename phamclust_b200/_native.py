@@ -224,7 +224,7 @@ class Context:
     def stats(self):
         out = {}
         for which, key in enumerate(("logical_alignments", "unique_genes", "operand_columns", "genes",
-                                     "lex_alignments", "lex_cells")):
+                                     "lex_alignments", "lex_cells", "dp_configs_used", "dp_configs")):
             v = ctypes.c_int64()
             self._check(self._lib.pc_stat(self._h, which, ctypes.byref(v)))
             out[key] = v.value

@@ -49,6 +49,37 @@ __device__ __forceinline__ int fma_add(int a, int one, int b)
     return d;
 }
 
+
+// ref residue codes of this lane's K columns as table offsets (code << SHIFT); genes are
+// 16 B aligned and K is even, so lane sl's first column (sl * K) is 2 B aligned at least
+template <int K, int SHIFT, bool CLAMP>
+__device__ __forceinline__ void load_ref_codes(const uint8_t *p, int (&rc)[K])
+{
+    if constexpr (K % 4 == 0) {
+#pragma unroll
+        for (int w = 0; w < K / 4; ++w) {
+            const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(p) + w);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int code = (int)((word >> (8 * b)) & 31u);
+                if (CLAMP && code >= NW_TAB_CODES) code = 0;   // padding past the gene only
+                rc[4 * w + b] = code << SHIFT;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < K / 2; ++w) {
+            const uint32_t word = __ldg(reinterpret_cast<const uint16_t *>(p) + w);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                int code = (int)((word >> (8 * b)) & 31u);
+                if (CLAMP && code >= NW_TAB_CODES) code = 0;
+                rc[2 * w + b] = code << SHIFT;
+            }
+        }
+    }
+}
+
 template <int G, int K, bool MULTI, bool REPL, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 {
@@ -116,17 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
             const int col0 = chunk * CAP + sl * K;   // 0-based first column of this lane
             // per column: H^ and F^ of the previous row and their relative counters
             int Hp[K], Fp[K], cHp[K], cFp[K], rc[K];
-            // ref residues: K multiple of 4 and genes 16B aligned -> word loads
-#pragma unroll
-            for (int w = 0; w < K / 4; ++w) {
-                const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(r + col0) + w);
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    int code = (int)((word >> (8 * b)) & 31u);
-                    if (REPL && code >= NW_TAB_CODES) code = 0;   // padding past the gene only
-                    rc[4 * w + b] = code << RSHIFT;
-                }
-            }
+            load_ref_codes<K, RSHIFT, REPL>(r + col0, rc);
 #pragma unroll
             for (int x = 0; x < K; ++x) {
                 Hp[x] = EDGE;                        // H^[0][j], j >= 1
@@ -321,16 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
 
         const int col0 = sl * K;
         int Hp[K], Fp[K], rc[K];
-#pragma unroll
-        for (int w = 0; w < K / 4; ++w) {
-            const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(r + col0) + w);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int code = (int)((word >> (8 * b)) & 31u);
-                if (code >= NW_TAB_CODES) code = 0;      // padding past the gene only
-                rc[4 * w + b] = code << 5;
-            }
-        }
+        load_ref_codes<K, 5, true>(r + col0, rc);
 #pragma unroll
         for (int x = 0; x < K; ++x) {
             Hp[x] = EDGE;                                // H^[0][j], j >= 1
@@ -405,9 +417,9 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
 template <int G, int K>
 static int launch_lex(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
 {
-    // 3 words of state per column: more warps fit than in the classic kernel
-    // (registers per thread by ptxas: 57 / 71 / 86 / 101 / 117 / 133 / 148 for K = 8 .. 32)
-    constexpr int THREADS = K <= 12 ? 768 : K <= 24 ? 512 : 384;
+    // 3 words of state per column: more warps fit than in the classic kernel, and K goes to 48
+    // (registers per thread by ptxas: 57 / 71 / 86 / 101 / 117 / 133 / 148 for K = 8, 12 .. 32)
+    constexpr int THREADS = K <= 12 ? 768 : K <= 24 ? 512 : K <= 36 ? 384 : 256;
     const size_t smem = (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int);
     auto kern = nw_lex_kernel<G, K, THREADS>;
     PC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -426,18 +438,20 @@ static int launch_lex(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
     return PC_OK;
 }
 
+// the G x K grid the chooser can pick (pc_nw_choose_cfg): K >= 16 for G >= 8
+#define PC_K_CASE(K_, CALL) case K_: if constexpr (G == 4 || K_ >= 16) { return CALL; } break;
+
 template <int G>
 static int launch_lex_k(pc_ctx *ctx, const NwArgs &args, int K, cudaStream_t stream)
 {
+#define PC_LEX_CASE(K_) PC_K_CASE(K_, (launch_lex<G, K_>(ctx, args, stream)))
     switch (K) {
-    case 8: return launch_lex<G, 8>(ctx, args, stream);
-    case 12: return launch_lex<G, 12>(ctx, args, stream);
-    case 16: return launch_lex<G, 16>(ctx, args, stream);
-    case 20: return launch_lex<G, 20>(ctx, args, stream);
-    case 24: return launch_lex<G, 24>(ctx, args, stream);
-    case 28: return launch_lex<G, 28>(ctx, args, stream);
-    case 32: return launch_lex<G, 32>(ctx, args, stream);
+    PC_LEX_CASE(8) PC_LEX_CASE(10) PC_LEX_CASE(12) PC_LEX_CASE(14) PC_LEX_CASE(16) PC_LEX_CASE(18)
+    PC_LEX_CASE(20) PC_LEX_CASE(22) PC_LEX_CASE(24) PC_LEX_CASE(26) PC_LEX_CASE(28) PC_LEX_CASE(30)
+    PC_LEX_CASE(32) PC_LEX_CASE(34) PC_LEX_CASE(36) PC_LEX_CASE(38) PC_LEX_CASE(40) PC_LEX_CASE(42)
+    PC_LEX_CASE(44) PC_LEX_CASE(46) PC_LEX_CASE(48)
     }
+#undef PC_LEX_CASE
     return pc_fail(ctx, PC_EINVAL, "no LEX DP kernel for G=%d K=%d", G, K);
 }
 
@@ -466,8 +480,11 @@ static int launch_cfg(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
 template <int G, int K, bool MULTI, int THREADS>
 static int launch_one(pc_ctx *ctx, const NwArgs &args, bool repl, cudaStream_t stream)
 {
-    return repl ? launch_cfg<G, K, MULTI, true, THREADS>(ctx, args, stream)
-                : launch_cfg<G, K, MULTI, false, THREADS>(ctx, args, stream);
+    if (repl) return launch_cfg<G, K, MULTI, true, THREADS>(ctx, args, stream);
+    // the 32-code table (inputs with residue symbols beyond the 24 matrix letters) only
+    // comes with K in multiples of 4 (pc_nw_choose_cfg's coarse grid)
+    if constexpr (K % 4 == 0) return launch_cfg<G, K, MULTI, false, THREADS>(ctx, args, stream);
+    return pc_fail(ctx, PC_EINVAL, "no 32-code DP kernel for G=%d K=%d", G, K);
 }
 
 // upper bound on the warps a launch of the multi-chunk config keeps resident
@@ -489,15 +506,13 @@ static int launch_gk(pc_ctx *ctx, const NwArgs &args, bool repl, cudaStream_t st
 template <int G>
 static int launch_k(pc_ctx *ctx, const NwArgs &args, bool repl, int K, cudaStream_t stream)
 {
+#define PC_CLS_CASE(K_) PC_K_CASE(K_, (launch_gk<G, K_, false>(ctx, args, repl, stream)))
     switch (K) {
-    case 8: return launch_gk<G, 8, false>(ctx, args, repl, stream);
-    case 12: return launch_gk<G, 12, false>(ctx, args, repl, stream);
-    case 16: return launch_gk<G, 16, false>(ctx, args, repl, stream);
-    case 20: return launch_gk<G, 20, false>(ctx, args, repl, stream);
-    case 24: return launch_gk<G, 24, false>(ctx, args, repl, stream);
-    case 28: return launch_gk<G, 28, false>(ctx, args, repl, stream);
-    case 32: return launch_gk<G, 32, false>(ctx, args, repl, stream);
+    PC_CLS_CASE(8) PC_CLS_CASE(10) PC_CLS_CASE(12) PC_CLS_CASE(14) PC_CLS_CASE(16) PC_CLS_CASE(18)
+    PC_CLS_CASE(20) PC_CLS_CASE(22) PC_CLS_CASE(24) PC_CLS_CASE(26) PC_CLS_CASE(28) PC_CLS_CASE(30)
+    PC_CLS_CASE(32)
     }
+#undef PC_CLS_CASE
     return pc_fail(ctx, PC_EINVAL, "no DP kernel for G=%d K=%d", G, K);
 }
 
@@ -505,6 +520,7 @@ int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream)
 {
     if (args.n_tasks <= 0) return PC_OK;
     if (cfg < 0 || cfg >= PC_NW_NCFG) return pc_fail(ctx, PC_EINVAL, "bad DP config %d", cfg);
+    ctx->cfg_used[cfg] = 1;
     const bool repl = ctx->n_codes <= NW_TAB_CODES;
     int G, K;
     pc_nw_cfg(cfg, G, K);

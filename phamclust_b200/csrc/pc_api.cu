@@ -193,7 +193,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_pham_col, &ctx->d_copies, &ctx->d_len_sum,
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
-                      &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_codes,
+                      &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_i8_occ, &ctx->d_codes,
                       &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_canon, &ctx->d_gene_hi, &ctx->d_subtab[0],
                       &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
                       &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
@@ -286,6 +286,8 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     std::vector<int64_t> entry_first_gene(nnz + 1);
     std::vector<int64_t> seen(n_phams, -1);
     std::vector<int64_t> pham_count(n_phams + 1, 0);
+    std::vector<int32_t> first_seen;               // phams in order of their first genome
+    first_seen.reserve(n_phams);
     uint32_t max_copies = 0, max_len = 0;
     int64_t gene_cursor = 0;
     for (int64_t g = 0; g < n_genomes; ++g) {
@@ -298,6 +300,7 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
                 return pc_fail(ctx, PC_EINVAL, "pham id %d out of range at entry %lld", p, (long long)k);
             if (seen[p] == g)
                 return pc_fail(ctx, PC_EINVAL, "pham %d listed twice for genome %lld", p, (long long)g);
+            if (seen[p] < 0) first_seen.push_back(p);
             seen[p] = g;
             if (copies[k] == 0)
                 return pc_fail(ctx, PC_EINVAL, "entry %lld has 0 copies", (long long)k);
@@ -340,10 +343,14 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     ctx->planes_kind = -1; ctx->i8_kind = -1;
     ctx->plan.part = ctx->plan.n_parts = -1;
     // operand columns: a pham held by a single genome can never be shared, so it
-    // gets no column (exact; orphams are common in phage tables)
+    // gets no column (exact; orphams are common in phage tables).  Columns are
+    // handed out in order of the first genome holding the pham (the result does
+    // not depend on the column order): the phams of a run of related genomes land
+    // in neighbouring K blocks whatever their ids, which is what the block-sparse
+    // K schedule of the int8 engine feeds on.
     std::vector<int32_t> pham_col(std::max<int64_t>(n_phams, 1), -1);
     int64_t p_eff = 0;
-    for (int64_t p = 0; p < n_phams; ++p)
+    for (const int32_t p : first_seen)
         if (ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p] >= 2) pham_col[p] = (int32_t)p_eff++;
     ctx->P_eff = p_eff;
     const int64_t words = (p_eff + 31) / 32;
@@ -516,8 +523,8 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
         if ((rc = pc_stage_end(ctx))) break;
         dbg_mark("seqs: uploads queued");
         // + tail padding: lanes read whole K-column words past the last gene
-        if ((rc = devbuf_reserve(ctx, ctx->d_codes, (size_t)cursor + 1024))) break;
-        if (cudaMemsetAsync(ctx->d_codes.p, 0, (size_t)cursor + 1024, ctx->stream) != cudaSuccess) {
+        if ((rc = devbuf_reserve(ctx, ctx->d_codes, (size_t)cursor + 2048))) break;
+        if (cudaMemsetAsync(ctx->d_codes.p, 0, (size_t)cursor + 2048, ctx->stream) != cudaSuccess) {
             rc = pc_fail(ctx, PC_ECUDA, "memset of the code arena failed");
             break;
         }
@@ -785,6 +792,7 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     u.mem_copies = pl.mem_copies.as<int32_t>();
     u.gene_len = ctx->d_gene_len.as<int32_t>();
     u.gene_hi = lex_allowed(ctx) ? ctx->d_gene_hi.as<int32_t>() : nullptr;
+    u.coarse_k = ctx->n_codes > 24;
     u.n_genomes = ctx->N;
     {
         int64_t blocks = (pl.n_units + 255) / 256;
@@ -1042,7 +1050,7 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
             return pc_fail(ctx, PC_EINVAL, "task %lld names a gene outside [0,%lld)", (long long)t, (long long)ctx->n_genes);
         const int lq = ctx->h_gene_len[query_gene[t]], lr = ctx->h_gene_len[ref_gene[t]];
         const bool lex = use_lex && pc_nw_lex_ok(lq, lr, ctx->h_gene_hi[query_gene[t]], ctx->h_gene_hi[ref_gene[t]]);
-        bucket[t] = pc_nw_choose_cfg(lq, lr, lex);
+        bucket[t] = pc_nw_choose_cfg(lq, lr, lex, ctx->n_codes > 24);
         bucket_count[bucket[t]]++;
         if (bucket[t] >= PC_NW_MULTI0 && bucket[t] < PC_NW_LEX0)
             max_q_multi = std::max(max_q_multi, ctx->h_gene_len[query_gene[t]]);
@@ -1180,6 +1188,28 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
         *out = (int64_t)cells;
         break;
     }
+    case PC_STAT_DP_CONFIGS_USED: {
+        int64_t used = 0;
+        for (char c : ctx->cfg_used) used += c;
+        *out = used;
+        break;
+    }
+    case PC_STAT_DP_CONFIGS: {
+        // every config pc_nw_choose_cfg returns for some (query rows, ref columns) with the
+        // loaded alphabet, by enumeration; the classic kernel only gets what the LEX kernel
+        // cannot take for ANY residues (score bound of an all-W sequence: 11 per residue)
+        const bool coarse = ctx->n_codes > 24, lex = lex_allowed(ctx);
+        std::vector<char> reach(PC_NW_NCFG, 0);
+        for (int n = 1; n <= 4200; ++n)
+            for (int m = 1; m <= 4096; m *= 4) {
+                if (lex && pc_nw_lex_ok(m, n, 0, 0)) reach[pc_nw_choose_cfg(m, n, true, coarse)] = 1;
+                if (!lex || !pc_nw_lex_ok(m, n, 11 * m, 11 * n)) reach[pc_nw_choose_cfg(m, n, false, coarse)] = 1;
+            }
+        int64_t count = 0;
+        for (char c : reach) count += c;
+        *out = count;
+        break;
+    }
     default: return pc_fail(ctx, PC_EINVAL, "pc_stat: unknown statistic %d", which);
     }
     return PC_OK;
@@ -1194,6 +1224,7 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
     ctx->alignments = 0;
     ctx->logical_alignments = 0;
     ctx->lex_alignments = 0;
+    std::fill(ctx->cfg_used.begin(), ctx->cfg_used.end(), 0);
     if (ctx->d_counters.p) {
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG, 0,
                                      2 * sizeof(unsigned long long), ctx->stream));

@@ -92,6 +92,7 @@ struct UnitArgs {
     const int32_t *mem_copies;
     const int32_t *gene_len;
     const int32_t *gene_hi;      // per-gene score bound; NULL = never use the LEX DP kernel
+    int coarse_k;                // 1: the 32-code table is in use (K in multiples of 4 only)
     int64_t n_genomes;
     // device-side bucketing of the units by DP kernel config
     int64_t units_per_block;     // contiguous units owned by one classify/scatter block
@@ -160,6 +161,7 @@ struct pc_ctx {
     DevBuf d_numer;                                // int32 scratch triangle slice
     // int8 operand for the tcgen05 engine
     DevBuf d_i8;                                   // [N_pad][K_pad]
+    DevBuf d_i8_occ;                               // [N_pad / 128][occ_words] K-block occupancy bits
     int i8_kind = -1; int64_t i8_K = 0, i8_rows = 0;
 
     // ---- sequences ----
@@ -190,6 +192,7 @@ struct pc_ctx {
     double stage_ms[PC_T_COUNT] = {0};
     int64_t launches = 0, contract_launches = 0, align_launches = 0;
     int64_t dp_cells = 0, alignments = 0, logical_alignments = 0, lex_alignments = 0;
+    std::vector<char> cfg_used = std::vector<char>(512, 0);   // [config]: launched since the reset
 };
 
 // stage timing helpers (events on ctx->stream)
@@ -221,19 +224,27 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
 int pc_i8_supported(const pc_ctx *ctx, int metric);
 int pc_build_canonical_genes(pc_ctx *ctx);
 
-// DP kernel configs: a subgroup of G lanes per alignment, K ref columns per lane
-// (G*K columns per pass).  0..27: G in {4,8,16,32} x K in {8,12,...,32};
-// 28..31: multi-chunk (G = 32, K in {20,24,28,32}: the ref is cut into
-// ceil(n / 32K) column chunks, any length); 32..59: the same single-pass G x K
-// grid on the LEX kernel (counters inside the score word, pc_align.cu) for the
-// alignments pc_nw_lex_ok admits.
-#define PC_NW_NCFG 60
-#define PC_NW_MULTI0 28             // first multi-chunk config
-#define PC_NW_LEX0 32               // first LEX config
-#define PC_NW_COST_PER_CELL 18      // SASS instructions per cell (see pc_align.cu)
-#define PC_NW_COST_PER_STEP 15      // per row-step overhead (shuffles, boundary, loop)
-#define PC_NW_LEX_COST_PER_CELL 11  // in units where the classic kernel costs 18 (ALU-pipe bound)
-#define PC_NW_LEX_COST_PER_STEP 10
+// DP kernel configs: a subgroup of G lanes per alignment (G in {4,8,16,32}), K ref
+// columns per lane in registers (G*K columns per pass), K even.
+//   classic single-pass  c = g*13 + (K-8)/2,          K in 8..32   (5 registers per column)
+//   multi-chunk          c = 52 + (K-20)/4,  G = 32,  K in {20,24,28,32}: the ref is cut into
+//                        ceil(n / 32K) column chunks, any length
+//   LEX single-pass      c = 56 + g*21 + (K-8)/2,     K in 8..48   (3 registers per column;
+//                        counters inside the score word, for the alignments pc_nw_lex_ok admits)
+// The chooser only ever picks K >= 16 for G >= 8 (a smaller G covers the same columns with less
+// pipeline fill), and multiples of 4 up to 32 when the 32-code table is in use; only those
+// combinations are instantiated (pc_align.cu).
+#define PC_NW_NK 13                 // classic K values per G
+#define PC_NW_LEX_NK 21             // LEX K values per G
+#define PC_NW_MULTI0 (4 * PC_NW_NK) // first multi-chunk config
+#define PC_NW_LEX0 (PC_NW_MULTI0 + 4)
+#define PC_NW_NCFG (PC_NW_LEX0 + 4 * PC_NW_LEX_NK)
+#define PC_NW_KMAX 32
+#define PC_NW_LEX_KMAX 48
+#define PC_NW_COST_PER_CELL 18      // relative cost model (the kernels are ALU-pipe bound)
+#define PC_NW_COST_PER_STEP 18      // per row-step overhead (shuffles, boundary, loop)
+#define PC_NW_LEX_COST_PER_CELL 11
+#define PC_NW_LEX_COST_PER_STEP 15
 
 // LEX word: score << SHIFT | prio << 2*BITS | diagonal steps << BITS | matched
 #define PC_NW_LEX_BITS 9
@@ -248,9 +259,17 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #endif
 PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
 {
-    if (c >= PC_NW_LEX0) c -= PC_NW_LEX0;
-    if (c < PC_NW_MULTI0) { G = 4 << (c / 7); K = 8 + 4 * (c % 7); }
-    else { G = 32; K = 20 + 4 * (c - PC_NW_MULTI0); }
+    if (c >= PC_NW_LEX0) {
+        c -= PC_NW_LEX0;
+        G = 4 << (c / PC_NW_LEX_NK);
+        K = 8 + 2 * (c % PC_NW_LEX_NK);
+    } else if (c >= PC_NW_MULTI0) {
+        G = 32;
+        K = 20 + 4 * (c - PC_NW_MULTI0);
+    } else {
+        G = 4 << (c / PC_NW_NK);
+        K = 8 + 2 * (c % PC_NW_NK);
+    }
 }
 
 // May the (m-row query, n-column ref) alignment run on the LEX kernel?  Both
@@ -271,26 +290,30 @@ PC_HD inline bool pc_nw_lex_ok(int m, int n, int hi_q, int hi_r)
 #endif
 }
 
-// cheapest config for an m-row query against n ref columns: issue slots per
+// cheapest config for an m-row query against n ref columns: pipe slots per
 // alignment ~ chunks x (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp.
 // Per G the cost of a single-pass config grows with K, so only the smallest K
 // that covers n competes; the LEX grid (when admitted) is cheaper cell for cell
-// and always covers what the classic single-pass grid covers.
-PC_HD inline int pc_nw_choose_cfg(int m, int n, bool lex)
+// and covers everything the classic single-pass grid covers.  coarse: K in
+// multiples of 4 (the kernels of the 32-code table).
+PC_HD inline int pc_nw_choose_cfg(int m, int n, bool lex, bool coarse)
 {
     int best = PC_NW_LEX0 - 1;
     long long best_cost = -1;
     const long long per_cell = lex ? PC_NW_LEX_COST_PER_CELL : PC_NW_COST_PER_CELL;
     const long long per_step = lex ? PC_NW_LEX_COST_PER_STEP : PC_NW_COST_PER_STEP;
+    const int kmax = lex ? PC_NW_LEX_KMAX : PC_NW_KMAX;
     for (int g = 0; g < 4; ++g) {
         const int G = 4 << g;
-        int K = ((n + G - 1) / G + 3) & ~3;
-        if (K < 8) K = 8;
-        if (K > 32) continue;
+        int K = (n + G - 1) / G;
+        K = coarse ? (K + 3) & ~3 : (K + 1) & ~1;
+        const int kmin = g == 0 ? 8 : 16;
+        if (K < kmin) K = kmin;
+        if (K > kmax) continue;
         const long long cost = (long long)(m + G - 1) * (K * per_cell + per_step) * G;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
-            best = (lex ? PC_NW_LEX0 : 0) + g * 7 + (K - 8) / 4;
+            best = lex ? PC_NW_LEX0 + g * PC_NW_LEX_NK + (K - 8) / 2 : g * PC_NW_NK + (K - 8) / 2;
         }
     }
     if (best_cost >= 0) return best;      // single-pass configs cover it without the spill

@@ -24,6 +24,14 @@
 // touch TMEM lane quadrant warp%4, two warps share a quadrant and split the columns).  4-stage 48 KB smem ring (128B-swizzled 128-byte K
 // slabs), mbarrier full/empty pairs, tcgen05.commit releases the slots.
 // Tensor-pipe bound: 2*K*128*256 int8 ops per tile.
+//
+// Block sparsity: pack_i8_kernel also records which (128-genome group, 128-column
+// K block) pairs hold any presence bit.  A CTA ANDs the occupancy of its row
+// groups with that of its column groups and only streams the K blocks both sides
+// occupy; a tile whose genomes share no K block at all (e.g. genomes of
+// different phage clusters, whose phams sit in disjoint column ranges) never
+// touches the tensor core: its shared counts are 0 by construction and the
+// epilogue values are written directly.  Dense tables (C3/C5) keep every block.
 #include <cuda.h>
 
 #include "pc_common.cuh"
@@ -38,16 +46,23 @@
 #define I8_A_BYTES (I8_BM * I8_BK)
 #define I8_B_BYTES (I8_BN * I8_BK)
 #define I8_MAX_STAGES 4
+// occupancy words per genome group: bit b covers K blocks [b << occ_shift, (b + 1) << occ_shift);
+// occ_shift is the smallest shift that fits the segment's K blocks into this many words
+#define I8_MAX_OCC_WORDS 1024
 template <int MT> struct I8Cfg {
     static constexpr int STAGE_BYTES = MT * I8_A_BYTES + I8_B_BYTES;     // 48 KB / 64 KB
     static constexpr int STAGES = MT == 1 ? 4 : 3;                        // 192 KB ring either way
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * I8_BN * 4;
+    static constexpr int MASK_OFF = STAGES * STAGE_BYTES + 256 /*barriers*/ + 2 * I8_BN * 4 /*denominators*/;
+    static constexpr int SMEM_BYTES = MASK_OFF + I8_MAX_OCC_WORDS * 4 + 1024 /*align*/;
 };
 
 struct I8Args {
     int64_t p_pad;        // bytes per segment (multiple of 128)
     int n_limbs;          // 0: gcs/jc (single segment); else weight limbs before the B segment
     int tile_row0;        // first 128-row tile of the launch
+    const uint32_t *occ;  // [rows_pad / 128][occ_words]: bit b set <=> the group holds a pham of K blocks b << occ_shift ..
+    int occ_words;
+    int occ_shift;
     EpilogueArgs ep;
 };
 
@@ -152,28 +167,51 @@ __device__ __forceinline__ constexpr uint32_t i8_idesc()
            ((uint32_t)(I8_BM >> 4) << 24);
 }
 
-// step `it` of the K schedule -> (segment read by the row tile, segment read by
-// the column tile, accumulator, k-block)
-__device__ __forceinline__ void i8_schedule(const I8Args &a, int64_t kb_per_seg, int64_t it,
-                                            int64_t &a_col, int64_t &b_col, int &acc, bool &first)
+// K schedule: n_limbs == 0 -> one pass over the K blocks of the single segment;
+// else per weight limb two passes (row tile reads the limb while the column tile
+// reads B, then swapped), limb t accumulating into accumulator t.  Within a pass
+// only the K blocks of the CTA's occupancy mask are visited, in ascending order
+// (producer and MMA issuer walk the same mask, so they agree on the sequence).
+struct I8Step {
+    int64_t a_col, b_col;
+    int acc;
+    bool first;
+};
+
+template <typename F>
+__device__ __forceinline__ void i8_for_each_step(const I8Args &a, const uint32_t *mask, F &&body)
 {
-    if (a.n_limbs == 0) {
-        a_col = b_col = it * I8_BK;
-        acc = 0;
-        first = (it == 0);
-        return;
+    const int64_t kb_per_seg = a.p_pad / I8_BK;
+    const int n_pass = a.n_limbs == 0 ? 1 : 2 * a.n_limbs;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int limb = pass >> 1;
+        const bool swapped = (pass & 1) != 0;
+        bool first = !swapped;                       // first step of this accumulator
+        for (int w = 0; w < a.occ_words; ++w) {
+            uint32_t bits = mask[w];
+            while (bits) {
+                const int64_t b = (int64_t)w * 32 + (__ffs((int)bits) - 1);
+                bits &= bits - 1;
+                const int64_t kb_end = min((b + 1) << a.occ_shift, kb_per_seg);
+                for (int64_t kb = b << a.occ_shift; kb < kb_end; ++kb) {
+                    I8Step st;
+                    if (a.n_limbs == 0) {
+                        st.a_col = st.b_col = kb * I8_BK;
+                        st.acc = 0;
+                    } else {
+                        const int64_t wcol = (int64_t)limb * a.p_pad + kb * I8_BK;
+                        const int64_t bcol = (int64_t)a.n_limbs * a.p_pad + kb * I8_BK;
+                        st.a_col = swapped ? bcol : wcol;
+                        st.b_col = swapped ? wcol : bcol;
+                        st.acc = limb;
+                    }
+                    st.first = first;
+                    first = false;
+                    body(st);
+                }
+            }
+        }
     }
-    const int64_t per_limb = 2 * kb_per_seg;
-    const int limb = (int)(it / per_limb);
-    const int64_t r = it % per_limb;
-    const int64_t kb = r % kb_per_seg;
-    const bool swapped = r >= kb_per_seg;
-    const int64_t wcol = (int64_t)limb * a.p_pad + kb * I8_BK;
-    const int64_t bcol = (int64_t)a.n_limbs * a.p_pad + kb * I8_BK;
-    a_col = swapped ? bcol : wcol;
-    b_col = swapped ? wcol : bcol;
-    acc = limb;
-    first = (r == 0);
 }
 
 template <int MT>
@@ -195,13 +233,26 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint64_t *tmem_full_bar = empty_bar + I8_STAGES;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
     int32_t *s_den = reinterpret_cast<int32_t *>(smem + I8_STAGES * I8_STAGE_BYTES + 256);
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + I8Cfg<MT>::MASK_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_acc = (a.n_limbs == 0 ? 1 : a.n_limbs) * MT;       // host guarantees <= 2
     const uint32_t tmem_cols = n_acc * I8_BN <= 256 ? 256 : 512;
-    const int64_t kb_per_seg = a.p_pad / I8_BK;
-    const int64_t n_steps = a.n_limbs == 0 ? kb_per_seg : 2 * (int64_t)a.n_limbs * kb_per_seg;
+
+    // K blocks this tile has to visit: occupied by one of its row groups AND one of its column groups
+    int any_block = 0;
+    for (int w = threadIdx.x; w < a.occ_words; w += I8_THREADS) {
+        uint32_t rows = 0;
+#pragma unroll
+        for (int u = 0; u < MT; ++u) rows |= a.occ[(int64_t)(bi * MT + u) * a.occ_words + w];
+        uint32_t cols = 0;
+#pragma unroll
+        for (int u = 0; u < I8_BN / I8_BM; ++u)
+            cols |= a.occ[(int64_t)(bj * (I8_BN / I8_BM) + u) * a.occ_words + w];
+        s_mask[w] = rows & cols;
+        any_block |= (rows & cols) != 0;
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -223,37 +274,37 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    // no common K block: every shared count of the tile is 0, the tensor core is never started
+    const bool empty_tile = __syncthreads_or(any_block) == 0;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int64_t it = 0; it < n_steps; ++it) {
-                const int s = (int)(it % I8_STAGES);
-                const uint32_t ph = (uint32_t)((it / I8_STAGES) & 1);
-                int64_t a_col, b_col; int acc; bool first;
-                i8_schedule(a, kb_per_seg, it, a_col, b_col, acc, first);
+            int s = 0;
+            uint32_t ph = 0;
+            i8_for_each_step(a, s_mask, [&](const I8Step &st) {
                 mbar_wait(empty_bar + s, ph ^ 1);
                 mbar_expect_tx(full_bar + s, I8_STAGE_BYTES);
                 uint8_t *sa = tiles + (size_t)s * I8_STAGE_BYTES;
 #pragma unroll
                 for (int u = 0; u < MT; ++u)
-                    tma_load_2d(sa + u * I8_A_BYTES, &map_a, full_bar + s, (int32_t)a_col,
+                    tma_load_2d(sa + u * I8_A_BYTES, &map_a, full_bar + s, (int32_t)st.a_col,
                                 (bi * MT + u) * I8_BM);
-                tma_load_2d(sa + MT * I8_A_BYTES, &map_b, full_bar + s, (int32_t)b_col, bj * I8_BN);
-            }
+                tma_load_2d(sa + MT * I8_A_BYTES, &map_b, full_bar + s, (int32_t)st.b_col, bj * I8_BN);
+                if (++s == I8_STAGES) { s = 0; ph ^= 1; }
+            });
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = i8_idesc();
-            for (int64_t it = 0; it < n_steps; ++it) {
-                const int s = (int)(it % I8_STAGES);
-                const uint32_t ph = (uint32_t)((it / I8_STAGES) & 1);
-                int64_t a_col, b_col; int acc; bool first;
-                i8_schedule(a, kb_per_seg, it, a_col, b_col, acc, first);
+            int s = 0;
+            uint32_t ph = 0;
+            i8_for_each_step(a, s_mask, [&](const I8Step &st) {
+                const int acc = st.acc;
+                const bool first = st.first;
                 mbar_wait(full_bar + s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(tiles + (size_t)s * I8_STAGE_BYTES);
@@ -270,8 +321,9 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                 }
                 umma_commit(empty_bar + s);          // frees the smem slot when the MMAs retire
-            }
-            umma_commit(tmem_full_bar);              // accumulators complete
+                if (++s == I8_STAGES) { s = 0; ph ^= 1; }
+            });
+            if (!empty_tile) umma_commit(tmem_full_bar);   // accumulators complete
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
@@ -286,8 +338,10 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (!ep.raw)
             for (int x = et; x < I8_BN; x += 32 * I8_EPI_WARPS) s_den[x] = (col0 + x < n) ? ep.den[col0 + x] : 0;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");      // epilogue warps only
-        mbar_wait(tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!empty_tile) {
+            mbar_wait(tmem_full_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
 
         const int64_t out_base = pc_tri_index(n, ep.row_begin, ep.row_begin);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -302,8 +356,13 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int c = c_begin; c < c_end; ++c) {
                 if (col0 + c * 32 + 31 < warp_row0) continue;          // warp-uniform
                 uint32_t v[32];
-                tmem_ld32(lane_addr + (uint32_t)((MT == 1 ? 0 : u) * I8_BN + c * 32), v);
-                if (MT == 1 && n_acc == 2) {
+                if (empty_tile) {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) v[x] = 0;
+                } else {
+                    tmem_ld32(lane_addr + (uint32_t)((MT == 1 ? 0 : u) * I8_BN + c * 32), v);
+                }
+                if (!empty_tile && MT == 1 && n_acc == 2) {
                     uint32_t hi[32];
                     tmem_ld32(lane_addr + (uint32_t)(I8_BN + c * 32), hi);
 #pragma unroll
@@ -342,7 +401,8 @@ __global__ void pack_i8_kernel(const int32_t *__restrict__ entry_genome,
                                const int32_t *__restrict__ pham_id,
                                const int32_t *__restrict__ pham_col,
                                const uint32_t *__restrict__ weight, int n_limbs, int64_t p_pad,
-                               int64_t row_bytes, int64_t nnz, uint8_t *__restrict__ dst)
+                               int64_t row_bytes, int64_t nnz, uint8_t *__restrict__ dst,
+                               uint32_t *__restrict__ occ, int occ_words, int occ_shift)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
@@ -352,6 +412,11 @@ __global__ void pack_i8_kernel(const int32_t *__restrict__ entry_genome,
         const uint32_t w = weight ? weight[e] : 0;
         for (int t = 0; t < n_limbs; ++t) row[(int64_t)t * p_pad + p] = (uint8_t)((w >> (8 * t)) & 0xffu);
         row[(int64_t)n_limbs * p_pad + p] = 1;
+        // occupancy of (128-genome group, K block); most entries find their bit already set
+        const int b = (p / I8_BK) >> occ_shift;
+        uint32_t *word = occ + (int64_t)(entry_genome[e] / I8_BM) * occ_words + (b >> 5);
+        const uint32_t bit = 1u << (b & 31);
+        if (!(*reinterpret_cast<volatile uint32_t *>(word) & bit)) atomicOr(word, bit);
     }
 }
 
@@ -403,11 +468,19 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
     const int64_t p_pad = std::max<int64_t>(I8_BK, (ctx->P_eff + I8_BK - 1) / I8_BK * I8_BK);
     const int64_t row_bytes = p_pad * (n_limbs + 1);
     const int64_t rows_pad = (ctx->N + I8_BN - 1) / I8_BN * I8_BN;
+    const int64_t kb_per_seg = p_pad / I8_BK;
+    auto occ_words_at = [&](int shift) { return (((kb_per_seg - 1) >> shift) + 32) / 32; };
+    int occ_shift = 0;
+    while (occ_words_at(occ_shift) > I8_MAX_OCC_WORDS) ++occ_shift;
+    const int occ_words = (int)occ_words_at(occ_shift);
+    const size_t occ_bytes = (size_t)(rows_pad / I8_BM) * occ_words * sizeof(uint32_t);
     if (ctx->i8_kind != kind || ctx->i8_K != row_bytes) {
         const size_t bytes = (size_t)rows_pad * row_bytes;
         PC_TRY(devbuf_reserve(ctx, ctx->d_i8, bytes));
+        PC_TRY(devbuf_reserve(ctx, ctx->d_i8_occ, occ_bytes));
         PC_TRY(pc_stage_begin(ctx, PC_T_PACK));
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8.p, 0, bytes, ctx->stream));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8_occ.p, 0, occ_bytes, ctx->stream));
         if (ctx->nnz) {
             const uint32_t *w = kind == 0 ? nullptr
                               : kind == 1 ? ctx->d_copies.as<uint32_t>() : ctx->d_len_sum.as<uint32_t>();
@@ -416,7 +489,8 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
             pack_i8_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
                 ctx->d_entry_genome.as<int32_t>(), ctx->d_pham_id.as<int32_t>(), ctx->d_pham_col.as<int32_t>(), w,
                 n_limbs, p_pad,
-                row_bytes, ctx->nnz, ctx->d_i8.as<uint8_t>());
+                row_bytes, ctx->nnz, ctx->d_i8.as<uint8_t>(), ctx->d_i8_occ.as<uint32_t>(), occ_words,
+                occ_shift);
             PC_CUDA(ctx, cudaGetLastError());
             ctx->launches++;
         }
@@ -430,6 +504,9 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
     I8Args args;
     args.p_pad = p_pad;
     args.n_limbs = n_limbs;
+    args.occ = ctx->d_i8_occ.as<uint32_t>();
+    args.occ_words = occ_words;
+    args.occ_shift = occ_shift;
     args.ep = ep;
     // two row tiles per CTA whenever one accumulator per row tile is enough
     const int mt = n_limbs <= 1 ? 2 : 1;

@@ -194,6 +194,7 @@ __device__ __forceinline__ uint64_t ht_find(const unsigned long long *keys, uint
 // (block, config)
 __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const UnitArgs u)
 {
+    static_assert(PC_NW_NCFG <= UNIT_THREADS, "one thread per config zeroes and writes the block counts");
     __shared__ unsigned int s_cnt[PC_NW_NCFG];
     if (threadIdx.x < PC_NW_NCFG) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const Unit
                 if (inserted) {
                     const int lq = u.gene_len[cq], lr = u.gene_len[cr];
                     const bool lex = u.gene_hi && pc_nw_lex_ok(lq, lr, u.gene_hi[cq], u.gene_hi[cr]);
-                    const int cfg = pc_nw_choose_cfg(lq, lr, lex);
+                    const int cfg = pc_nw_choose_cfg(lq, lr, lex, u.coarse_k != 0);
                     const unsigned int rank = atomicAdd(&s_cnt[cfg], 1u);
                     u.ht_vals[h] = ((unsigned long long)cfg << 56) | ((unsigned long long)blockIdx.x << 32) | rank;
                 }
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const Unit
 }
 
 // pass B: per config, exclusive scan over blocks; config bases in launch order
-static_assert(PC_NW_NCFG <= 64, "scan_blocks_kernel runs one thread per config in a 64-thread block");
+static_assert(PC_NW_NCFG <= 256, "scan_blocks_kernel runs one thread per config in a 256-thread block");
 __global__ void scan_blocks_kernel(const UnitArgs u)
 {
     const int c = threadIdx.x;
@@ -307,7 +308,7 @@ int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u)
     PC_CUDA(ctx, cudaMemsetAsync(u.ht_keys, 0xff, sizeof(unsigned long long) * (u.ht_mask + 1), ctx->stream));
     classify_units_kernel<<<u.n_blocks, UNIT_THREADS, 0, ctx->stream>>>(u);
     PC_CUDA(ctx, cudaGetLastError());
-    scan_blocks_kernel<<<1, 64, 0, ctx->stream>>>(u);
+    scan_blocks_kernel<<<1, 256, 0, ctx->stream>>>(u);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     return PC_OK;

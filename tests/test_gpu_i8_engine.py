@@ -53,3 +53,35 @@ def test_i8_engine_at_benchmark_size(gpu_ctx):
         assert np.array_equal(gpu_ctx.matrix("jc"), want)
     finally:
         gpu_ctx.set_engine("auto")
+
+
+@pytest.mark.parametrize("shuffle_ids", [False, True])
+def test_i8_block_sparse_schedule_on_clustered_tables(gpu_ctx, shuffle_ids):
+    """Genomes of different phage clusters share no K block: most 256 x 256 tiles
+    of this table skip the tensor core entirely (shared count 0 by construction),
+    the diagonal ones visit a handful of K blocks.  Every value must still equal
+    the popc engine's and the oracle's; with shuffled pham ids the library's own
+    column order (first genome holding the pham) has to rebuild the blocks."""
+    n = 1100                                         # 22 clusters, ragged last tiles
+    table = synthetic.phage_table(n, seed=11, with_sequences=False)
+    if shuffle_ids:
+        perm = np.random.default_rng(3).permutation(table.meta["n_phams"]).astype(np.int32)
+        table.pham_id = perm[table.pham_id]
+    gpu_ctx.load_table(table)
+    iu = np.triu_indices(n)
+    try:
+        for key in CHEAP:
+            gpu_ctx.set_engine("popc")
+            want_num = gpu_ctx.numerators(key)
+            want = gpu_ctx.matrix(key, as_distance=True)
+            oracle_num = po.table_numerators(table, key)[iu].copy()
+            oracle_num[iu[0] == iu[1]] = 0
+            assert np.array_equal(want_num, oracle_num), key
+            gpu_ctx.set_engine("i8mma")
+            assert np.array_equal(gpu_ctx.numerators(key), want_num), key
+            assert np.array_equal(gpu_ctx.matrix(key, as_distance=True), want), key
+            parts = [gpu_ctx.matrix_rows(key, False, r0, r1) for r0, r1 in ((0, 300), (300, 513), (513, n))]
+            gpu_ctx.set_engine("popc")
+            assert np.array_equal(np.concatenate(parts), gpu_ctx.matrix(key, as_distance=False)), key
+    finally:
+        gpu_ctx.set_engine("auto")

@@ -180,6 +180,41 @@ def test_random_alignments_bit_exact_all_kernel_configs(gpu_ctx, dp_mode):
                            for k in bad[:5]]
 
 
+def test_every_reachable_dp_config_is_launched_and_bit_exact(gpu_ctx, dp_mode):
+    """One ref length just under every G x K capacity (K even: 8..32 classic, 8..48
+    LEX), against short queries (LEX-admissible: min length < 512 and the score word
+    fits), a same-length mutant and a 4090-residue query (never LEX-admissible: the
+    classic kernel at every K); then ref lengths beyond the single-pass grid for the
+    multi-chunk configs.  The library must report that every config its chooser
+    can return was launched, and every alignment must equal the traceback oracle."""
+    rng = random.Random(4848)
+    short = [testdata.random_protein(rng, m, m, testdata.AA) for m in (1, 37, 300, 4090)]
+    seqs = list(short)
+    q, r = [], []
+    lengths = sorted({g * k - d for g in (4, 8, 16, 32) for k in range(8, 50, 2) for d in (0, 1)}
+                     | {1537, 1700, 2049, 2300, 2561, 2700, 3000})
+    for n in lengths:
+        ref = testdata.random_protein(rng, n, n, testdata.AA if n % 3 else "AG")
+        twin = testdata.mutate(rng, ref, 0.3, testdata.AA)
+        base = len(seqs)
+        seqs += [ref, twin]
+        for k in range(len(short)):
+            q.append(k); r.append(base)
+        q.append(base + 1); r.append(base)
+        q.append(base); r.append(base + 1)
+    _load(gpu_ctx, _genes_table(seqs))
+    gpu_ctx.reset_counters()
+    got = gpu_ctx.alignment_identities(q, r)
+    stats = gpu_ctx.stats()
+    assert stats["dp_configs_used"] == stats["dp_configs"], stats
+    assert stats["dp_configs"] >= (90 if dp_mode == "auto" else 40), stats
+    off, res = _arena(seqs)
+    want = nw_c.batch(res, off, q, r, mode=0)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, [(len(seqs[q[k]]), len(seqs[r[k]]), got[k].tolist(), want[k].tolist())
+                           for k in bad[:5]]
+
+
 def test_lex_kernel_at_the_edges_of_its_word(gpu_ctx):
     """The LEX DP kernel packs score | priority | diagonal steps | matches into 32
     bits (9-bit counters, 12-bit biased score).  Lengths around 511, score bounds
