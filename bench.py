@@ -123,6 +123,10 @@ def build_workload(args):
         table = synthetic.phage_table(args.genomes, seed=2)
         name = (f"configs[3]: metric={args.metric}, pham-sharded alignment, on synthetic.phage_table("
                 f"n_genomes={args.genomes}, seed=2) [SURVEY 8(d) C4: clusters of 50 genomes x 150-pham pools]")
+    elif args.workload == "c5":
+        table = synthetic.sparse_table(args.genomes, args.phams, seed=3)
+        name = (f"configs[4]: metric={args.metric}, full upper triangle in row blocks + NCCL gather, on "
+                f"synthetic.sparse_table(n_genomes={args.genomes}, n_phams={args.phams}, seed=3) [SURVEY 8(d) C5]")
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     return table, name
@@ -481,7 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--metric", default=None)
     ap.add_argument("--genomes", type=int, default=None)
     ap.add_argument("--phams", type=int, default=60000)
@@ -490,9 +494,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.metric is None:
-        args.metric = "jc" if args.workload == "c3" else "peq"
+        args.metric = {"c2": "peq", "c3": "jc", "c4": "peq", "c5": "gcs"}[args.workload]
     if args.genomes is None:
-        args.genomes = {"c2": 2000, "c3": 10000, "c4": 50000}[args.workload]
+        args.genomes = {"c2": 2000, "c3": 10000, "c4": 50000, "c5": 100000}[args.workload]
+    if args.workload == "c5" and args.phams == 60000:
+        args.phams = 200000
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)

@@ -419,7 +419,9 @@ static int launch_lex(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
 {
     // 3 words of state per column: more warps fit than in the classic kernel, and K goes to 48
     // (registers per thread by ptxas: 57 / 71 / 86 / 101 / 117 / 133 / 148 for K = 8, 12 .. 32)
-    constexpr int THREADS = K <= 12 ? 768 : K <= 24 ? 512 : K <= 36 ? 384 : 256;
+    // warps per SM sub-partition (16384 registers each): 8 / 7 / 6 / 5 / 4 / 3 / 2
+    constexpr int THREADS = K <= 10 ? 1024 : K <= 12 ? 896 : K <= 14 ? 768 : K <= 18 ? 640 : K <= 24 ? 512
+                          : K <= 38 ? 384 : 256;
     const size_t smem = (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int);
     auto kern = nw_lex_kernel<G, K, THREADS>;
     PC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -498,8 +500,9 @@ int pc_nw_multichunk_warps(pc_ctx *ctx)
 template <int G, int K, bool MULTI>
 static int launch_gk(pc_ctx *ctx, const NwArgs &args, bool repl, cudaStream_t stream)
 {
-    // (registers are split per SM sub-partition: 4/3/2 warps each -> 128/168/255 per thread)
-    constexpr int THREADS = K <= 12 ? 512 : K <= 20 ? 384 : 256;
+    // (registers are split per SM sub-partition: 6/5/4/3/2 warps each -> 80/96/128/168/255 per thread)
+    constexpr int THREADS = MULTI ? (K <= 20 ? 384 : 256)
+                          : K <= 8 ? 768 : K <= 10 ? 640 : K <= 14 ? 512 : K <= 20 ? 384 : 256;
     return launch_one<G, K, MULTI, THREADS>(ctx, args, repl, stream);
 }
 
