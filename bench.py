@@ -291,7 +291,8 @@ def run_native(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     counters = ctx.counters()
-    lex_cells = ctx.stats()["lex_cells"] if need_seqs else 0
+    stats = ctx.stats()
+    lex_cells = stats["lex_cells"] if need_seqs else 0
     timings = ctx.timings()
     local_sum = out_local[:_native.tri_len(n, r0, r1)].to(torch.int64).sum().reshape(1)
     if world > 1:
@@ -316,6 +317,8 @@ def run_native(args):
         ctx.set_stream(0, external=False)
         e2e_secs = []
         for it in range(args.warmup + args.steps):
+            if it == args.warmup:
+                ctx.reset_counters()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             ctx.load_table(host_table)
@@ -329,40 +332,56 @@ def run_native(args):
         e2e = {"value": pairs / float(np.mean(e2e_secs)), "unit": "pairs/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(host_out.nbytes),
                "ms_per_step": 1e3 * float(np.mean(e2e_secs)),
+               "stage_ms_per_step": {k: v / max(args.steps, 1) for k, v in ctx.timings().items()},
                "api": "pc_load_table + pc_load_sequences + pc_matrix (host buffers)"}
         assert int(host_out.astype(np.int64).sum()) == checksum, "e2e and resident results differ"
     else:
-        # N > 1: the same C-ABI sequence on every rank from HOST buffers (load table /
-        # sequences, this rank's share of the work, NCCL exchange), result copied to
-        # rank 0's pinned host buffer
+        # N > 1: the same C-ABI sequence on every rank from pinned HOST buffers (load table /
+        # sequences, this rank's share of the work, NCCL all-reduce of the pair accumulators),
+        # then every rank copies its row block from its own GPU straight into ONE triangle in
+        # page-locked POSIX shared memory (distributed.SharedTriangle): the consumer is the host,
+        # so no device-side all-gather and no single-link D2H of the whole triangle
+        import copy
         arrays = [table.genome_ptr, table.pham_id, table.copies, table.len_sum] + \
             ([table.seq_off, table.residues] if need_seqs else [])
-        host_full = torch.empty(world * width, dtype=torch.int32).pin_memory() if rank == 0 else None
+        pinned = [pinned_copy(torch, a) for a in arrays]
+        host_table = copy.copy(table)
+        host_table.genome_ptr, host_table.pham_id, host_table.copies, host_table.len_sum = \
+            [p.numpy() for p in pinned[:4]]
+        if need_seqs:
+            host_table.seq_off, host_table.residues = pinned[4].numpy(), pinned[5].numpy()
+        shared = distributed.SharedTriangle(n)
+        my_rows = shared.rows(r0, r1)
         secs = []
         for it in range(min(args.warmup, 2) + args.steps):
+            if it == min(args.warmup, 2):
+                ctx.reset_counters()
             barrier()
             t0 = time.perf_counter()
-            ctx.load_table(table)
+            ctx.load_table(host_table)
             if need_seqs:
-                ctx.load_sequences(table)
-            step()
-            if rank == 0:
-                host_full.copy_(gathered, non_blocking=True)
+                ctx.load_sequences(host_table)
+                acc.zero_()
+                ctx.align_accumulate(acc.data_ptr(), part=rank, n_parts=world)
+                dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            if r1 > r0:
+                ctx.matrix_rows(metric, True, r0, r1, acc_ptr=acc.data_ptr() if need_seqs else None, out=my_rows)
             barrier()
             if it >= min(args.warmup, 2):
                 secs.append(time.perf_counter() - t0)
         worst = torch.tensor([float(np.mean(secs))], dtype=torch.float64, device=dev)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         if rank == 0:
-            host = host_full.numpy().reshape(world, width)
-            total = sum(int(host[r, :_native.tri_len(n, bounds[r], bounds[r + 1])].astype(np.int64).sum())
-                        for r in range(world))
-            assert total == checksum, "e2e and resident results differ"
+            assert int(shared.array.sum(dtype=np.int64)) == checksum, "e2e and resident results differ"
         e2e = {"value": pairs / float(worst.item()), "unit": "pairs/s",
                "h2d_bytes_per_step": int(sum(a.nbytes for a in arrays)) * world,
-               "d2h_bytes_per_step": int(world * width * 4), "ms_per_step": 1e3 * float(worst.item()),
-               "api": "per rank: pc_load_table + pc_load_sequences + pc_align_accumulate/pc_matrix_rows "
-                      "(host buffers) + NCCL all-reduce/all-gather; result to rank 0's host buffer"}
+               "d2h_bytes_per_step": int(tri * 4), "ms_per_step": 1e3 * float(worst.item()),
+               "stage_ms_per_step_rank0": {k: v / max(args.steps, 1) for k, v in ctx.timings().items()},
+               "api": "per rank: pc_load_table + pc_load_sequences + pc_align_accumulate (pinned host buffers) + "
+                      "NCCL all-reduce + pc_matrix_rows into the node's shared page-locked host triangle "
+                      "(distributed.SharedTriangle), every GPU over its own PCIe link"}
+        barrier()
+        shared.close()
 
     # ---- roofline of the dominant kernel --------------------------------------------
     peaks, peak_kind = measured_peaks()
@@ -411,10 +430,16 @@ def run_native(args):
             # shared and get no operand column (exact)
             k_eff = int((np.bincount(table.pham_id, minlength=table.n_phams) >= 2).sum())
             ops = 2.0 * k_eff * limbs * _native.tri_len(n, r0, r1)   # this rank's row block
-            tops = ops / (per_launch_ms * 1e-3) / 1e12
+            # block-sparse K schedule: only the (tile, K block) pairs both operands occupy are
+            # multiplied; the algorithmic ops of the launch shrink by the same fraction (1.0 on
+            # dense tables such as C3)
+            visited = (stats["i8_tile_steps"] / stats["i8_tile_steps_dense"]) if stats["i8_tile_steps_dense"] else 1.0
+            dense_tops = ops / (per_launch_ms * 1e-3) / 1e12
+            tops = dense_tops * visited
             peak = 2.0 * peaks["bf16_tflops"]
             roofline = {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05 kind::i8 + fused epilogue)",
                         "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak,
+                        "k_blocks_visited_frac": visited, "dense_equivalent_tops": dense_tops,
                         # dram__bytes_read+write of one launch, ncu --set full (profiles/): only
                         # captured for the C3 jc launch on one GPU
                         "traffic": 3.35e9 if (args.workload == "c3" and metric == "jc" and world == 1

@@ -177,6 +177,7 @@ class Context:
             return None
         if out is None:
             out = np.empty(count, dtype=np.int32)
+        assert out.dtype == np.int32 and out.size == count and out.flags.c_contiguous
         self._check(self._lib.pc_matrix_rows(
             self._h, _metric_id(metric), int(bool(as_distance)), int(bool(ppos)), row_begin,
             row_end, ctypes.c_void_p(acc_ptr or 0), out.ctypes.data, 0))
@@ -224,7 +225,8 @@ class Context:
     def stats(self):
         out = {}
         for which, key in enumerate(("logical_alignments", "unique_genes", "operand_columns", "genes",
-                                     "lex_alignments", "lex_cells", "dp_configs_used", "dp_configs")):
+                                     "lex_alignments", "lex_cells", "dp_configs_used", "dp_configs", "i8_tile_steps",
+                                     "i8_tile_steps_dense")):
             v = ctypes.c_int64()
             self._check(self._lib.pc_stat(self._h, which, ctypes.byref(v)))
             out[key] = v.value

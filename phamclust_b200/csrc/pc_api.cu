@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <numeric>
 #include <chrono>
+#include <climits>
+#include <thread>
 
 #include "pc_common.cuh"
 
@@ -193,7 +195,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_pham_col, &ctx->d_copies, &ctx->d_len_sum,
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
-                      &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_i8_occ, &ctx->d_codes,
+                      &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_i8_occ, &ctx->d_i8_steps, &ctx->d_codes,
                       &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_canon, &ctx->d_gene_hi, &ctx->d_subtab[0],
                       &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
                       &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
@@ -260,6 +262,32 @@ static int upload(pc_ctx *ctx, DevBuf &b, const T *src, size_t count)
     return PC_OK;
 }
 
+// host threads for the O(nnz) passes over the caller's table (PC_HOST_THREADS overrides)
+static int host_threads(int64_t work)
+{
+    if (const char *env = getenv("PC_HOST_THREADS")) {
+        const int t = atoi(env);
+        if (t >= 1) return std::min(t, 64);
+    }
+    if (work < 100000) return 1;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(8u, hw / 2));
+}
+
+template <typename F>
+static void run_threads(int T, F &&body)
+{
+    if (T <= 1) {
+        body(0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(T - 1);
+    for (int t = 1; t < T; ++t) pool.emplace_back([&body, t] { body(t); });
+    body(0);
+    for (auto &th : pool) th.join();
+}
+
 // ---------------------------------------------------------------------------
 // pc_load_table
 // ---------------------------------------------------------------------------
@@ -280,61 +308,140 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     if (nnz < 0 || (nnz > 0 && (!pham_id || !copies || !len_sum)))
         return pc_fail(ctx, PC_EINVAL, "pc_load_table: missing entry arrays");
 
-    // validate + derive per-genome denominators
-    std::vector<int32_t> den_phams(n_genomes), den_genes(n_genomes), den_len(n_genomes);
-    std::vector<int32_t> entry_genome(nnz);
-    std::vector<int64_t> entry_first_gene(nnz + 1);
-    std::vector<int64_t> seen(n_phams, -1);
-    std::vector<int64_t> pham_count(n_phams + 1, 0);
-    std::vector<int32_t> first_seen;               // phams in order of their first genome
-    first_seen.reserve(n_phams);
+    for (int64_t g = 0; g < n_genomes; ++g)
+        if (genome_ptr[g + 1] < genome_ptr[g] || genome_ptr[g + 1] > nnz)
+            return pc_fail(ctx, PC_EINVAL, "genome_ptr is not monotone at %lld", (long long)g);
+
+    // the entry arrays go to the device as they are, while the host validates them
+    PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+    PC_TRY(upload(ctx, ctx->d_pham_id, pham_id, nnz));
+    PC_TRY(upload(ctx, ctx->d_copies, copies, nnz));
+    PC_TRY(upload(ctx, ctx->d_len_sum, len_sum, nnz));
+    PC_TRY(pc_stage_end(ctx));
+
+    // validate + derive per-genome denominators, CSC counts and the first entry of every
+    // pham, on a few host threads over contiguous genome ranges of equal entry counts
+    // (every buffer lives in the ctx: a reload of a table of the same size touches no fresh page)
+    ctx->have_table = false;
+    for (auto &d : ctx->h_den) d.resize(n_genomes);
+    std::vector<int32_t> &den_phams = ctx->h_den[0], &den_genes = ctx->h_den[1], &den_len = ctx->h_den[2];
+    std::vector<int32_t> &entry_genome = ctx->h_entry_genome;
+    std::vector<int64_t> &entry_first_gene = ctx->h_entry_first_gene;
+    std::vector<int64_t> &pham_count = ctx->h_pham_ptr;
+    std::vector<int64_t> &first_entry = ctx->h_first_entry;
+    entry_genome.resize(nnz);
+    entry_first_gene.resize(nnz + 1);
+    pham_count.assign(n_phams + 1, 0);
+    first_entry.assign(n_phams, INT64_MAX);
+    ctx->h_genome_ptr.assign(genome_ptr, genome_ptr + n_genomes + 1);
+    ctx->h_pham_id.resize(nnz);
+    ctx->h_copies.resize(nnz);
+    ctx->h_len_sum.resize(nnz);
+    const int T = host_threads(nnz);
+    std::vector<int64_t> cut(T + 1, n_genomes);       // thread t owns genomes [cut[t], cut[t+1])
+    cut[0] = 0;
+    for (int t = 1; t < T; ++t)
+        cut[t] = std::lower_bound(genome_ptr, genome_ptr + n_genomes, nnz * t / T) - genome_ptr;
+    struct Part {
+        int64_t genes = 0, err_at = INT64_MAX;
+        uint32_t max_copies = 0, max_len = 0;
+        std::string err;
+        std::vector<int32_t> first_seen;          // phams whose first entry lies in this range, in order
+    };
+    std::vector<Part> part(T);
+    // duplicate check: stamp[p] = epoch + genome that last listed the pham; a new epoch per load
+    // instead of clearing the per-thread arrays
+    if ((int64_t)ctx->stamp_epoch + 2 * (n_genomes + 1) >= INT32_MAX) {
+        ctx->stamp_epoch = 0;
+        for (auto &v : ctx->h_stamp) std::fill(v.begin(), v.end(), 0);
+    }
+    const int32_t epoch = ctx->stamp_epoch + 1;
+    ctx->stamp_epoch += (int32_t)n_genomes + 1;
+    if ((int)ctx->h_stamp.size() < T) ctx->h_stamp.resize(T);
+    run_threads(T, [&](int t) {
+        Part &me = part[t];
+        std::vector<int32_t> &stamp = ctx->h_stamp[t];
+        if ((int64_t)stamp.size() < n_phams) stamp.resize(n_phams, 0);
+        auto fail = [&](int64_t at, const char *fmt, auto... args) {
+            char buf[160];
+            snprintf(buf, sizeof buf, fmt, args...);
+            me.err_at = at;                        // the lowest entry index wins across threads
+            me.err = buf;
+        };
+        for (int64_t g = cut[t]; g < cut[t + 1]; ++g) {
+            const int64_t b = genome_ptr[g], e = genome_ptr[g + 1];
+            int64_t genes = 0, len = 0;
+            for (int64_t k = b; k < e; ++k) {
+                const int32_t p = pham_id[k];
+                if (p < 0 || p >= n_phams)
+                    return fail(k, "pham id %d out of range at entry %lld", p, (long long)k);
+                if (stamp[p] == epoch + (int32_t)g)
+                    return fail(k, "pham %d listed twice for genome %lld", p, (long long)g);
+                stamp[p] = epoch + (int32_t)g;
+                if (copies[k] == 0) return fail(k, "entry %lld has 0 copies", (long long)k);
+                entry_genome[k] = (int32_t)g;
+                genes += copies[k];
+                len += len_sum[k];
+                me.max_copies = std::max(me.max_copies, copies[k]);
+                me.max_len = std::max(me.max_len, len_sum[k]);
+                __atomic_fetch_add(&pham_count[p + 1], (int64_t)1, __ATOMIC_RELAXED);
+                int64_t cur = __atomic_load_n(&first_entry[p], __ATOMIC_RELAXED);
+                while (k < cur && !__atomic_compare_exchange_n(&first_entry[p], &cur, k, true, __ATOMIC_RELAXED,
+                                                               __ATOMIC_RELAXED)) {
+                }
+            }
+            if (genes > (1 << 30) || len > (1 << 30))
+                return fail(b, "genome %lld too large for int32 numerators", (long long)g);
+            den_phams[g] = (int32_t)(e - b);
+            den_genes[g] = (int32_t)genes;
+            den_len[g] = (int32_t)len;
+            me.genes += genes;
+        }
+        const int64_t b = genome_ptr[cut[t]], e = genome_ptr[cut[t + 1]];
+        if (e > b) {
+            memcpy(ctx->h_pham_id.data() + b, pham_id + b, (size_t)(e - b) * sizeof(int32_t));
+            memcpy(ctx->h_copies.data() + b, copies + b, (size_t)(e - b) * sizeof(uint32_t));
+            memcpy(ctx->h_len_sum.data() + b, len_sum + b, (size_t)(e - b) * sizeof(uint32_t));
+        }
+    });
     uint32_t max_copies = 0, max_len = 0;
     int64_t gene_cursor = 0;
-    for (int64_t g = 0; g < n_genomes; ++g) {
-        const int64_t b = genome_ptr[g], e = genome_ptr[g + 1];
-        if (e < b || e > nnz) return pc_fail(ctx, PC_EINVAL, "genome_ptr is not monotone at %lld", (long long)g);
-        int64_t genes = 0, len = 0;
-        for (int64_t k = b; k < e; ++k) {
-            const int32_t p = pham_id[k];
-            if (p < 0 || p >= n_phams)
-                return pc_fail(ctx, PC_EINVAL, "pham id %d out of range at entry %lld", p, (long long)k);
-            if (seen[p] == g)
-                return pc_fail(ctx, PC_EINVAL, "pham %d listed twice for genome %lld", p, (long long)g);
-            if (seen[p] < 0) first_seen.push_back(p);
-            seen[p] = g;
-            if (copies[k] == 0)
-                return pc_fail(ctx, PC_EINVAL, "entry %lld has 0 copies", (long long)k);
-            entry_genome[k] = (int32_t)g;
-            entry_first_gene[k] = gene_cursor;
-            gene_cursor += copies[k];
-            genes += copies[k];
-            len += len_sum[k];
-            max_copies = std::max(max_copies, copies[k]);
-            max_len = std::max(max_len, len_sum[k]);
-            pham_count[p + 1]++;
+    {
+        const Part *bad = nullptr;
+        for (const Part &q : part) {
+            if (q.err_at != INT64_MAX && (!bad || q.err_at < bad->err_at)) bad = &q;
+            max_copies = std::max(max_copies, q.max_copies);
+            max_len = std::max(max_len, q.max_len);
+            gene_cursor += q.genes;
         }
-        if (genes > (1 << 30) || len > (1 << 30))
-            return pc_fail(ctx, PC_EINVAL, "genome %lld too large for int32 numerators", (long long)g);
-        den_phams[g] = (int32_t)(e - b);
-        den_genes[g] = (int32_t)genes;
-        den_len[g] = (int32_t)len;
+        if (bad) {
+            cudaStreamSynchronize(ctx->stream);        // the uploads read the caller's buffers
+            return pc_fail(ctx, PC_EINVAL, "%s", bad->err.c_str());
+        }
     }
-    entry_first_gene[nnz] = gene_cursor;
-    if (gene_cursor >= (1ll << 31))
+    if (gene_cursor >= (1ll << 31)) {
+        cudaStreamSynchronize(ctx->stream);
         return pc_fail(ctx, PC_EINVAL, "too many genes (%lld)", (long long)gene_cursor);
+    }
+    // second pass: first gene of every entry, and the phams in order of their first entry
+    std::vector<int64_t> gene_base(T + 1, 0);
+    for (int t = 0; t < T; ++t) gene_base[t + 1] = gene_base[t] + part[t].genes;
+    run_threads(T, [&](int t) {
+        int64_t cursor = gene_base[t];
+        Part &me = part[t];
+        for (int64_t k = genome_ptr[cut[t]]; k < genome_ptr[cut[t + 1]]; ++k) {
+            entry_first_gene[k] = cursor;
+            cursor += copies[k];
+            if (first_entry[pham_id[k]] == k) me.first_seen.push_back(pham_id[k]);
+        }
+    });
+    entry_first_gene[nnz] = gene_cursor;
 
     // per-pham member counts -> CSC pointers; the member lists themselves are only
     // needed by the alignment planner and are built there on demand
     for (int64_t p = 0; p < n_phams; ++p) pham_count[p + 1] += pham_count[p];
 
     ctx->N = n_genomes; ctx->P = n_phams; ctx->nnz = nnz;
-    ctx->h_genome_ptr.assign(genome_ptr, genome_ptr + n_genomes + 1);
-    ctx->h_pham_id.assign(pham_id, pham_id + nnz);
-    ctx->h_copies.assign(copies, copies + nnz);
-    ctx->h_len_sum.assign(len_sum, len_sum + nnz);
-    ctx->h_entry_genome.swap(entry_genome);
-    ctx->h_entry_first_gene.swap(entry_first_gene);
-    ctx->h_pham_ptr.swap(pham_count);
     ctx->h_pham_members.clear();
     ctx->bits_ready = false;
     ctx->max_copies = max_copies; ctx->max_len_sum = max_len;
@@ -348,25 +455,24 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     // not depend on the column order): the phams of a run of related genomes land
     // in neighbouring K blocks whatever their ids, which is what the block-sparse
     // K schedule of the int8 engine feeds on.
-    std::vector<int32_t> pham_col(std::max<int64_t>(n_phams, 1), -1);
+    std::vector<int32_t> &pham_col = ctx->h_pham_col;
+    pham_col.assign(std::max<int64_t>(n_phams, 1), -1);
     int64_t p_eff = 0;
-    for (const int32_t p : first_seen)
-        if (ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p] >= 2) pham_col[p] = (int32_t)p_eff++;
+    for (const auto &q : part)
+        for (const int32_t p : q.first_seen)
+            if (ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p] >= 2) pham_col[p] = (int32_t)p_eff++;
     ctx->P_eff = p_eff;
     const int64_t words = (p_eff + 31) / 32;
     ctx->W = std::max<int64_t>(32, (words + 31) / 32 * 32);
 
     PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
     PC_TRY(upload(ctx, ctx->d_entry_genome, ctx->h_entry_genome.data(), nnz));
-    PC_TRY(upload(ctx, ctx->d_pham_id, ctx->h_pham_id.data(), nnz));
     PC_TRY(upload(ctx, ctx->d_pham_col, pham_col.data(), pham_col.size()));
-    PC_TRY(upload(ctx, ctx->d_copies, ctx->h_copies.data(), nnz));
-    PC_TRY(upload(ctx, ctx->d_len_sum, ctx->h_len_sum.data(), nnz));
     PC_TRY(upload(ctx, ctx->d_den_phams, den_phams.data(), n_genomes));
     PC_TRY(upload(ctx, ctx->d_den_genes, den_genes.data(), n_genomes));
     PC_TRY(upload(ctx, ctx->d_den_len, den_len.data(), n_genomes));
     PC_TRY(pc_stage_end(ctx));
-    // den_* are stack-owned vectors: the copies above must finish before return
+    // the copies read the caller's buffers and scratch the next load rewrites: finish them
     PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_table = true;
     return PC_OK;
@@ -1188,6 +1294,16 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
         *out = (int64_t)cells;
         break;
     }
+    case PC_STAT_I8_TILE_STEPS: {
+        unsigned long long steps = 0;
+        if (ctx->d_i8_steps.p) {
+            PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            PC_CUDA(ctx, cudaMemcpy(&steps, ctx->d_i8_steps.p, sizeof steps, cudaMemcpyDeviceToHost));
+        }
+        *out = (int64_t)steps;
+        break;
+    }
+    case PC_STAT_I8_TILE_STEPS_DENSE: *out = ctx->i8_dense_steps; break;
     case PC_STAT_DP_CONFIGS_USED: {
         int64_t used = 0;
         for (char c : ctx->cfg_used) used += c;
@@ -1225,6 +1341,9 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
     ctx->logical_alignments = 0;
     ctx->lex_alignments = 0;
     std::fill(ctx->cfg_used.begin(), ctx->cfg_used.end(), 0);
+    ctx->i8_dense_steps = 0;
+    if (ctx->d_i8_steps.p)
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8_steps.p, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->d_counters.p) {
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG, 0,
                                      2 * sizeof(unsigned long long), ctx->stream));

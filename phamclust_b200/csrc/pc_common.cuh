@@ -144,6 +144,11 @@ struct pc_ctx {
     std::vector<int32_t> h_entry_genome;
     std::vector<int64_t> h_entry_first_gene;
     std::vector<int64_t> h_pham_ptr;      // CSC
+    // pc_load_table scratch, kept between calls (no fresh pages per load)
+    std::vector<int64_t> h_first_entry;
+    std::vector<int32_t> h_den[3], h_pham_col;
+    std::vector<std::vector<int32_t>> h_stamp;   // per host thread: epoch + genome that last listed the pham
+    int32_t stamp_epoch = 0;
     std::vector<int64_t> h_pham_members;  // entry ids grouped by pham, genome ascending
     uint32_t max_copies = 0, max_len_sum = 0;
     int64_t n_genes_total = 0;
@@ -162,6 +167,8 @@ struct pc_ctx {
     // int8 operand for the tcgen05 engine
     DevBuf d_i8;                                   // [N_pad][K_pad]
     DevBuf d_i8_occ;                               // [N_pad / 128][occ_words] K-block occupancy bits
+    int64_t i8_dense_steps = 0;                    // ... and what the dense K schedule would have issued
+    DevBuf d_i8_steps;                             // u64: 128 x 256 x 128 MMA groups issued since the reset
     int i8_kind = -1; int64_t i8_K = 0, i8_rows = 0;
 
     // ---- sequences ----

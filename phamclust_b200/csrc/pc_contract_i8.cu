@@ -63,6 +63,7 @@ struct I8Args {
     const uint32_t *occ;  // [rows_pad / 128][occ_words]: bit b set <=> the group holds a pham of K blocks b << occ_shift ..
     int occ_words;
     int occ_shift;
+    unsigned long long *tile_steps;   // += MT per K block visited (one 128 x 256 x 128 MMA group each)
     EpilogueArgs ep;
 };
 
@@ -221,7 +222,9 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 {
     constexpr int I8_STAGES = I8Cfg<MT>::STAGES;
     constexpr int I8_STAGE_BYTES = I8Cfg<MT>::STAGE_BYTES;
-    const int bi = blockIdx.y + a.tile_row0;      // (128*MT)-row tile
+    // last row tiles first: with the columns in first-genome order the late genomes occupy the
+    // most K blocks, so their tiles are the long ones and must not form the tail of the launch
+    const int bi = (int)(gridDim.y - 1 - blockIdx.y) + a.tile_row0;      // (128*MT)-row tile
     const int bj = blockIdx.x;                    // 256-column tile
     if ((int64_t)bj * I8_BN + (I8_BN - 1) < (int64_t)bi * I8_BM * MT) return;   // strictly lower triangle
 
@@ -300,7 +303,7 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = i8_idesc();
-            int s = 0;
+            int s = 0, n_steps = 0;
             uint32_t ph = 0;
             i8_for_each_step(a, s_mask, [&](const I8Step &st) {
                 const int acc = st.acc;
@@ -321,9 +324,11 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                 }
                 umma_commit(empty_bar + s);          // frees the smem slot when the MMAs retire
+                ++n_steps;
                 if (++s == I8_STAGES) { s = 0; ph ^= 1; }
             });
             if (!empty_tile) umma_commit(tmem_full_bar);   // accumulators complete
+            if (n_steps) atomicAdd(a.tile_steps, (unsigned long long)n_steps * MT);
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
@@ -507,6 +512,11 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
     args.occ = ctx->d_i8_occ.as<uint32_t>();
     args.occ_words = occ_words;
     args.occ_shift = occ_shift;
+    if (!ctx->d_i8_steps.p) {
+        PC_TRY(devbuf_reserve(ctx, ctx->d_i8_steps, sizeof(unsigned long long)));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8_steps.p, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    args.tile_steps = ctx->d_i8_steps.as<unsigned long long>();
     args.ep = ep;
     // two row tiles per CTA whenever one accumulator per row tile is enough
     const int mt = n_limbs <= 1 ? 2 : 1;
@@ -514,6 +524,12 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
     args.tile_row0 = (int)(ep.row_begin / rows_per_tile);
     const int tile_row1 = (int)((ep.row_end + rows_per_tile - 1) / rows_per_tile);
     dim3 grid((unsigned)((ctx->N + I8_BN - 1) / I8_BN), (unsigned)(tile_row1 - args.tile_row0));
+    // MMA groups the dense schedule would issue for this launch (statistics only)
+    for (unsigned by = 0; by < grid.y; ++by) {
+        const int64_t first_col_tile = ((int64_t)(by + args.tile_row0) * rows_per_tile) / I8_BN;
+        if (first_col_tile < (int64_t)grid.x)
+            ctx->i8_dense_steps += ((int64_t)grid.x - first_col_tile) * kb_per_seg * (n_limbs == 0 ? 1 : 2 * n_limbs) * mt;
+    }
     PC_TRY(pc_stage_begin(ctx, PC_T_CONTRACT));
     if (mt == 2) {
         PC_CUDA(ctx, cudaFuncSetAttribute(i8_contract_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -14,6 +14,13 @@ How the path shards:
   ``(matched << 32) | length``.  ONE integer all-reduce (exact, order
   independent) merges them, then the row-block epilogue + all-gather as above.
 
+When the consumer of the matrix is the HOST (the reference hands it to host
+clustering), the all-gather is the wrong exchange: ``sharded_matrix_to_host``
+lets every rank copy its finished row block straight from its GPU into ONE
+triangle in POSIX shared memory (``SharedTriangle``, page-locked by every rank),
+over that GPU's own PCIe link and in parallel with the others -- no device-side
+assembly, no single-link D2H of the whole triangle.
+
 The compute callables are injectable so the host logic (partitioning,
 all-reduce, assembly) is covered on CPU with world_size-2 gloo.
 """
@@ -104,6 +111,94 @@ def sharded_matrix(table, metric, as_distance=True, ppos=False, backend_ops=None
     return assemble(n, bounds, [host[r] for r in range(world)])
 
 
+class SharedTriangle:
+    """The packed int32 triangle of an n-genome matrix in POSIX shared memory:
+    created by rank 0, attached by every rank of the node; with a GPU present each
+    rank page-locks the rows it will write (``pin_rows=(r0, r1)``, rounded out to
+    whole pages; ``None`` = its ``row_partition`` block) so that its D2H is a
+    full-speed DMA.  ``array`` is the numpy view; ``close()`` unmaps, rank 0 also
+    unlinks."""
+
+    def __init__(self, n, pin_rows=None):
+        from multiprocessing import shared_memory
+        dist = _dist()
+        self.rank = dist.get_rank()
+        self.n = n
+        count = n * (n + 1) // 2
+        nbytes = max(count, 1) * 4
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self._shm.name
+        dist.broadcast_object_list(name, src=0)
+        if self.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:        # the creator unlinks; keep this process's resource tracker out of it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.array = np.ndarray((count,), dtype=np.int32, buffer=self._shm.buf)
+        self._registered = None
+        if pin_rows is None:
+            bounds = row_partition(n, dist.get_world_size())
+            pin_rows = (bounds[self.rank], bounds[self.rank + 1])
+        self._pin(tri_offset(n, pin_rows[0]) * 4, tri_offset(n, pin_rows[1]) * 4, nbytes)
+
+    def _pin(self, lo, hi, nbytes):
+        import sys
+        if hi <= lo or "torch" not in sys.modules:
+            return
+        import torch
+        if not torch.cuda.is_available():
+            return
+        page = 4096                          # the mapping itself starts on a page boundary
+        lo = lo // page * page
+        hi = min((hi + page - 1) // page * page, (nbytes + page - 1) // page * page)
+        addr = self.array.ctypes.data + lo
+        rc = torch.cuda.cudart().cudaHostRegister(addr, hi - lo, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister of the shared triangle failed ({rc})")
+        self._registered = addr
+
+    def rows(self, r0, r1):
+        """View of the rows [r0, r1) of the triangle."""
+        return self.array[tri_offset(self.n, r0):tri_offset(self.n, r1)]
+
+    def close(self):
+        if self._registered is not None:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self._registered)
+            self._registered = None
+        self.array = None
+        self._shm.close()
+        if self.rank == 0:
+            self._shm.unlink()
+
+
+def sharded_matrix_to_host(table, metric, shared, as_distance=True, ppos=False, backend_ops=None):
+    """Every rank computes its row block and copies it from its own GPU straight
+    into ``shared`` (a SharedTriangle); returns after a barrier, when the whole
+    triangle is in host memory (``shared.array``, valid on every rank of the node).
+
+    ``backend_ops`` (tests): object with ``accumulate(part, n_parts) -> int64
+    tensor`` and ``rows_to_host(r0, r1, acc, out)`` filling the int32 numpy view
+    ``out``; the default drives libphamclust_b200 on this rank's GPU.
+    """
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = len(table.genome_ptr) - 1
+    ops = backend_ops or _GpuOps(table, metric, as_distance, ppos)
+    bounds = row_partition(n, world)
+    acc = None
+    if metric in ("aai", "peq"):
+        acc = ops.accumulate(rank, world)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)       # exact integer sum
+    ops.rows_to_host(bounds[rank], bounds[rank + 1], acc, shared.rows(bounds[rank], bounds[rank + 1]))
+    dist.barrier()
+    return shared.array
+
+
 class _GpuOps:
     """The real thing: this rank's GPU through the C ABI, on torch's stream so
     that NCCL collectives order after the kernels."""
@@ -137,3 +232,11 @@ class _GpuOps:
                                  acc_ptr=acc.data_ptr() if acc is not None else None,
                                  out_device_ptr=out.data_ptr(), ppos=self.ppos)
         return out[:count]
+
+    def rows_to_host(self, r0, r1, acc, out):
+        """Row block computed on this GPU, D2H by the library into ``out`` (page-locked
+        shared memory: a full-speed DMA on this GPU's own link)."""
+        if r1 > r0:
+            self.ctx.matrix_rows(self.metric, self.as_distance, r0, r1,
+                                 acc_ptr=acc.data_ptr() if acc is not None else None, out=out,
+                                 ppos=self.ppos)

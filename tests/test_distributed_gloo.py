@@ -55,6 +55,9 @@ class OracleOps:
                 out.append(po.round6_micro(w))
         return torch.tensor(out, dtype=torch.int32)
 
+    def rows_to_host(self, r0, r1, acc, out):
+        out[:] = self.rows(r0, r1, acc).numpy()
+
 
 def _worker(rank, world, port, rows, metric, queue):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -65,6 +68,15 @@ def _worker(rank, world, port, rows, metric, queue):
         assert distributed.is_active()
         got = distributed.sharded_matrix(table, metric, as_distance=True,
                                          backend_ops=OracleOps(genomes, metric, True))
+        # the host-consumer exchange: every rank writes its row block into one shared triangle
+        shared = distributed.SharedTriangle(len(genomes))
+        try:
+            host = distributed.sharded_matrix_to_host(table, metric, shared, as_distance=True,
+                                                      backend_ops=OracleOps(genomes, metric, True))
+            assert host.tolist() == got.tolist()
+            dist.barrier()
+        finally:
+            shared.close()
         queue.put((rank, got.tolist()))
     finally:
         dist.destroy_process_group()

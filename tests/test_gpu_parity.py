@@ -531,3 +531,62 @@ def test_counters_report_kernel_launches(gpu_ctx):
     t = gpu_ctx.timings()
     assert c["launches"] >= 4 and c["align_launches"] >= 1 and c["contract_launches"] >= 1
     assert c["alignments"] > 0 and c["dp_cells"] > 0 and t["align"] > 0.0
+
+
+def test_host_gather_through_the_shared_triangle(gpu_ctx):
+    """distributed.sharded_matrix_to_host on a 1-rank group: the row block is computed on
+    the GPU and DMA'd by the library into page-locked POSIX shared memory."""
+    import socket
+    import torch.distributed as dist
+    from phamclust_b200 import distributed
+    table = synthetic.phage_table(120, seed=9)
+    _load(gpu_ctx, table)
+    want = {m: gpu_ctx.matrix(m, as_distance=True) for m in ("jc", "peq")}
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        shared = distributed.SharedTriangle(table.n_genomes)
+        try:
+            assert shared._registered is not None
+            for m in ("jc", "peq"):
+                got = distributed.sharded_matrix_to_host(table, m, shared, as_distance=True)
+                assert np.array_equal(got, want[m]), m
+        finally:
+            shared.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_threaded_table_load(gpu_ctx, monkeypatch):
+    """pc_load_table validates and derives the CSR/CSC bookkeeping on several host threads:
+    same operand columns and same matrix as the single-thread pass, and of two bad entries
+    the one with the lower index is reported whichever thread meets it."""
+    import copy
+    table = synthetic.sparse_table(3000, 20000, seed=5)
+    results = []
+    for threads in ("1", "7"):
+        monkeypatch.setenv("PC_HOST_THREADS", threads)
+        gpu_ctx.load_table(table)
+        results.append((gpu_ctx.stats()["operand_columns"], gpu_ctx.matrix("pocp"), gpu_ctx.numerators("af")))
+    assert results[0][0] == results[1][0]
+    assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][2], results[1][2])
+    bad = copy.copy(table)
+    bad.pham_id = table.pham_id.copy()
+    nnz = len(bad.pham_id)
+    lo, hi = nnz // 5, nnz - 7
+    bad.pham_id[lo] = table.meta["n_phams"] + 3                 # out of range, early
+    g_hi = int(np.searchsorted(table.genome_ptr, hi, side="right") - 1)
+    if hi == table.genome_ptr[g_hi]:
+        hi += 1
+    bad.pham_id[hi] = bad.pham_id[hi - 1]                       # listed twice, late
+    for threads in ("1", "7"):
+        monkeypatch.setenv("PC_HOST_THREADS", threads)
+        with pytest.raises(ValueError, match=f"out of range at entry {lo}"):
+            gpu_ctx.load_table(bad)
+        with pytest.raises(ValueError):                          # no table left half-loaded
+            gpu_ctx.matrix("gcs")
+    monkeypatch.delenv("PC_HOST_THREADS")
+    gpu_ctx.load_table(table)
+    assert np.array_equal(gpu_ctx.matrix("pocp"), results[0][1])
