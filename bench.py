@@ -442,7 +442,7 @@ def run_native(args):
                         "k_blocks_visited_frac": visited, "dense_equivalent_tops": dense_tops,
                         # dram__bytes_read+write of one launch, ncu --set full (profiles/): only
                         # captured for the C3 jc launch on one GPU
-                        "traffic": 3.35e9 if (args.workload == "c3" and metric == "jc" and world == 1
+                        "traffic": 3.58e9 if (args.workload == "c3" and metric == "jc" and world == 1
                                               and n == 10000) else None, "kernel_ms_per_step": contract_ms / max(args.steps, 1),
                         "share_of_step": contract_ms / total_ms if total_ms else None,
                         "algorithmic_ops_per_launch": ops, "k_columns": k_eff * limbs,

@@ -420,7 +420,7 @@ static int launch_lex(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
     // 3 words of state per column: more warps fit than in the classic kernel, and K goes to 48
     // (registers per thread by ptxas: 57 / 71 / 86 / 101 / 117 / 133 / 148 for K = 8, 12 .. 32)
     // warps per SM sub-partition (16384 registers each): 8 / 7 / 6 / 5 / 4 / 3 / 2
-    constexpr int THREADS = K <= 10 ? 1024 : K <= 12 ? 896 : K <= 14 ? 768 : K <= 18 ? 640 : K <= 24 ? 512
+    constexpr int THREADS = K <= 10 ? 1024 : K <= 12 ? 896 : K <= 14 ? 768 : K <= 18 ? 640 : K <= 28 ? 512
                           : K <= 38 ? 384 : 256;
     const size_t smem = (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int);
     auto kern = nw_lex_kernel<G, K, THREADS>;
