@@ -520,33 +520,98 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
                        (long long)n_genes, (long long)ctx->n_genes_total);
     if (!seq_off || seq_off[0] != 0) return pc_fail(ctx, PC_EINVAL, "seq_off[0] must be 0");
     const int64_t total = seq_off[n_genes];
+    if (total < 0) return pc_fail(ctx, PC_EINVAL, "seq_off is not monotone (negative total)");
     if (total > 0 && !residues) return pc_fail(ctx, PC_EINVAL, "residues is NULL");
 
     dbg_mark("seqs: enter");
-    std::vector<int32_t> gene_len(n_genes);
-    std::vector<int64_t> gene_off(n_genes + 1);
+    // the residues go first: the copy runs while the host validates the offsets
+    PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+    PC_TRY(upload(ctx, ctx->d_raw, residues, (size_t)total));
+    PC_TRY(upload(ctx, ctx->d_raw_off, seq_off, (size_t)n_genes + 1));
+    PC_TRY(pc_stage_end(ctx));
+
+    // gene lengths and their 16 B aligned offsets in the code arena, on a few host threads
+    std::vector<int32_t> &gene_len = ctx->h_gene_len;
+    std::vector<int64_t> &gene_off = ctx->h_gene_off;
+    ctx->have_seqs = false;
+    gene_len.resize(n_genes);
+    gene_off.resize(n_genes + 1);
+    const int T = host_threads(n_genes);
+    struct SeqPart {
+        int64_t padded = 0, err_at = INT64_MAX;
+        int32_t max_len = 0;
+        std::string err;
+    };
+    std::vector<SeqPart> part(T);
+    auto lo_of = [&](int t) { return n_genes * t / T; };
+    run_threads(T, [&](int t) {
+        SeqPart &me = part[t];
+        for (int64_t g = lo_of(t); g < lo_of(t + 1); ++g) {
+            const int64_t len = seq_off[g + 1] - seq_off[g];
+            char buf[200];
+            if (len < 0) {
+                snprintf(buf, sizeof buf, "seq_off is not monotone at gene %lld", (long long)g);
+                me.err_at = g; me.err = buf;
+                return;
+            }
+            if (len > 32767) {
+                snprintf(buf, sizeof buf,
+                         "gene %lld has %lld residues; the alignment counters hold at most 32767 "
+                         "(parasail's 16-bit scores are undefined there anyway)", (long long)g, (long long)len);
+                me.err_at = g; me.err = buf;
+                return;
+            }
+            gene_len[g] = (int32_t)len;
+            me.max_len = std::max(me.max_len, (int32_t)len);
+            me.padded += (len + 15) / 16 * 16;
+        }
+    });
     int64_t cursor = 0;
-    for (int64_t g = 0; g < n_genes; ++g) {
-        const int64_t len = seq_off[g + 1] - seq_off[g];
-        if (len < 0) return pc_fail(ctx, PC_EINVAL, "seq_off is not monotone at gene %lld", (long long)g);
-        if (len > 32767)
-            return pc_fail(ctx, PC_EINVAL,
-                           "gene %lld has %lld residues; the alignment counters hold at most 32767 "
-                           "(parasail's 16-bit scores are undefined there anyway)",
-                           (long long)g, (long long)len);
-        gene_len[g] = (int32_t)len;
-        gene_off[g] = cursor;
-        cursor += (len + 15) / 16 * 16;
-    }
-    gene_off[n_genes] = cursor;
-    // the table's len_sum must describe these genes (metrics.py:136-147 sums them)
-    for (int64_t e = 0; e < ctx->nnz; ++e) {
-        int64_t s = 0;
-        for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g)
-            s += gene_len[g];
-        if (s != (int64_t)ctx->h_len_sum[e])
-            return pc_fail(ctx, PC_EINVAL, "len_sum[%lld]=%u but its genes sum to %lld",
-                           (long long)e, ctx->h_len_sum[e], (long long)s);
+    {
+        const SeqPart *bad = nullptr;
+        std::vector<int64_t> base(T + 1, 0);
+        int32_t max_len = 0;
+        for (int t = 0; t < T; ++t) {
+            if (part[t].err_at != INT64_MAX && (!bad || part[t].err_at < bad->err_at)) bad = &part[t];
+            base[t + 1] = base[t] + part[t].padded;
+            max_len = std::max(max_len, part[t].max_len);
+        }
+        if (bad) {
+            cudaStreamSynchronize(ctx->stream);        // the uploads read the caller's buffers
+            return pc_fail(ctx, PC_EINVAL, "%s", bad->err.c_str());
+        }
+        cursor = base[T];
+        ctx->max_gene_len = max_len;
+        // second pass: arena offsets; and the table's len_sum must describe these genes
+        // (metrics.py:136-147 sums them)
+        std::vector<SeqPart> chk(T);
+        auto elo_of = [&](int t) { return ctx->nnz * t / T; };
+        run_threads(T, [&](int t) {
+            int64_t at = base[t];
+            for (int64_t g = lo_of(t); g < lo_of(t + 1); ++g) {
+                gene_off[g] = at;
+                at += ((int64_t)gene_len[g] + 15) / 16 * 16;
+            }
+            for (int64_t e = elo_of(t); e < elo_of(t + 1); ++e) {
+                int64_t sum = 0;
+                for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g)
+                    sum += gene_len[g];
+                if (sum != (int64_t)ctx->h_len_sum[e]) {
+                    char buf[160];
+                    snprintf(buf, sizeof buf, "len_sum[%lld]=%u but its genes sum to %lld", (long long)e,
+                             ctx->h_len_sum[e], (long long)sum);
+                    chk[t].err_at = e; chk[t].err = buf;
+                    return;
+                }
+            }
+        });
+        gene_off[n_genes] = cursor;
+        for (int t = 0; t < T; ++t)
+            if (chk[t].err_at != INT64_MAX && (!bad || chk[t].err_at < bad->err_at)) bad = &chk[t];
+        if (bad) {
+            cudaStreamSynchronize(ctx->stream);
+            return pc_fail(ctx, PC_EINVAL, "%s", bad->err.c_str());
+        }
     }
 
     dbg_mark("seqs: lengths validated");
@@ -556,9 +621,6 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     // device (a host scan of the arena cost 11 ms of a 16 ms call at 40 MB)
     unsigned int present[256];
     {
-        PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
-        PC_TRY(upload(ctx, ctx->d_raw, residues, (size_t)total));
-        PC_TRY(pc_stage_end(ctx));
         PC_TRY(devbuf_reserve(ctx, ctx->d_lut, 256 * sizeof(unsigned int)));
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_lut.p, 0, 256 * sizeof(unsigned int), ctx->stream));
         if (total > 0) {
@@ -608,22 +670,18 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     for (int c = 0; c < 256; ++c) lut[c] = (uint8_t)(ctx->code_of_byte[c] < 0 ? 23 : ctx->code_of_byte[c]);
 
     ctx->n_genes = n_genes;
-    ctx->h_gene_len.swap(gene_len);
 
     DevBuf &d_raw_off = ctx->d_raw_off, &d_lut = ctx->d_lut;
+    std::vector<int2> tabs[2];           // alive until the sync below
     int rc = PC_OK;
     do {
         if ((rc = pc_stage_begin(ctx, PC_T_H2D))) break;
-        if ((rc = upload(ctx, d_raw_off, seq_off, (size_t)n_genes + 1))) break;
         if ((rc = upload(ctx, ctx->d_gene_off, gene_off.data(), (size_t)n_genes + 1))) break;
         if ((rc = upload(ctx, ctx->d_gene_len, ctx->h_gene_len.data(), (size_t)n_genes))) break;
         if ((rc = upload(ctx, d_lut, lut, 256))) break;
         for (int ppos = 0; ppos < 2 && rc == PC_OK; ++ppos) {
-            std::vector<int2> tab;
-            build_subtab(ctx, ppos, tab);
-            rc = upload(ctx, ctx->d_subtab[ppos], tab.data(), tab.size());
-            if (rc == PC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-                rc = pc_fail(ctx, PC_ECUDA, "sync failed while uploading the substitution table");
+            build_subtab(ctx, ppos, tabs[ppos]);
+            rc = upload(ctx, ctx->d_subtab[ppos], tabs[ppos].data(), tabs[ppos].size());
         }
         if (rc) break;
         if ((rc = pc_stage_end(ctx))) break;
@@ -765,62 +823,113 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
     AlignPlan &pl = ctx->plan;
     if (pl.part == part && pl.n_parts == n_parts) return PC_OK;
     HostTimer host_timer(ctx, PC_T_HOST_PLAN);
+    const int T = host_threads(ctx->nnz);
+    const int64_t P = ctx->P;
+    auto entries_of = [&](int t) { return ctx->nnz * t / T; };
+    auto phams_of = [&](int t) { return P * t / T; };
     if (ctx->h_pham_members.size() != (size_t)ctx->nnz) {
-        // CSC by stable counting sort: members of a pham in ascending genome order
-        ctx->h_pham_members.assign(ctx->nnz, 0);
-        std::vector<int64_t> cursor(ctx->h_pham_ptr.begin(), ctx->h_pham_ptr.end() - 1);
-        for (int64_t k = 0; k < ctx->nnz; ++k)
-            ctx->h_pham_members[cursor[ctx->h_pham_id[k]]++] = k;
+        // CSC by a stable counting sort over T entry ranges: members of a pham in ascending
+        // genome order.  cnt[t][p] = entries of pham p in range t, then their rank offset.
+        ctx->h_pham_members.resize(ctx->nnz);
+        std::vector<std::vector<int32_t>> cnt(T);
+        run_threads(T, [&](int t) {
+            cnt[t].assign(P, 0);
+            for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) cnt[t][ctx->h_pham_id[k]]++;
+        });
+        run_threads(T, [&](int t) {
+            for (int64_t p = phams_of(t); p < phams_of(t + 1); ++p) {
+                int32_t run = 0;
+                for (int u = 0; u < T; ++u) {
+                    const int32_t c = cnt[u][p];
+                    cnt[u][p] = run;
+                    run += c;
+                }
+            }
+        });
+        run_threads(T, [&](int t) {
+            for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) {
+                const int32_t p = ctx->h_pham_id[k];
+                ctx->h_pham_members[ctx->h_pham_ptr[p] + cnt[t][p]++] = k;
+            }
+        });
     }
     struct PhamInfo { int64_t pham; double cost; };
     std::vector<PhamInfo> infos;
-    for (int64_t p = 0; p < ctx->P; ++p) {
-        const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
-        if (e - b < 2) continue;              // cannot be shared by two genomes
-        double tot = 0;
-        for (int64_t k = b; k < e; ++k) {
-            const int64_t ent = ctx->h_pham_members[k];
-            tot += ctx->h_len_sum[ent];
-        }
-        infos.push_back({p, tot * tot});      // ~ sum of len_a * len_b over its member pairs
+    {
+        std::vector<std::vector<PhamInfo>> local(T);
+        run_threads(T, [&](int t) {
+            for (int64_t p = phams_of(t); p < phams_of(t + 1); ++p) {
+                const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
+                if (e - b < 2) continue;              // cannot be shared by two genomes
+                double tot = 0;
+                for (int64_t k = b; k < e; ++k) tot += ctx->h_len_sum[ctx->h_pham_members[k]];
+                local[t].push_back({p, tot * tot});   // ~ sum of len_a * len_b over its member pairs
+            }
+        });
+        size_t n = 0;
+        for (auto &v : local) n += v.size();
+        infos.reserve(n);
+        for (auto &v : local) infos.insert(infos.end(), v.begin(), v.end());
     }
     // descending cost (LPT), dealt round-robin over the partitions
-    std::sort(infos.begin(), infos.end(), [](const PhamInfo &x, const PhamInfo &y) {
+    auto by_cost = [](const PhamInfo &x, const PhamInfo &y) {
         if (x.cost != y.cost) return x.cost > y.cost;
         return x.pham < y.pham;
-    });
-    std::vector<int64_t> ph_mem_off{0}, ph_unit_off{0};
-    std::vector<int32_t> mem_genome, mem_first_gene, mem_copies;
-    int64_t n_tasks = 0;
-    for (size_t pos = 0; pos < infos.size(); ++pos) {
-        // snake order (0..P-1, P-1..0, ...): plain round-robin would hand partition 0 the
-        // largest pham of every group of P
-        const size_t lap = pos / (size_t)n_parts, in_lap = pos % (size_t)n_parts;
-        if ((int)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap) != part) continue;
-        const int64_t p = infos[pos].pham;
-        const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
-        const int64_t m = e - b;
-        int64_t sum_c = 0, sum_c2 = 0;
-        for (int64_t k = b; k < e; ++k) {
-            const int64_t ent = ctx->h_pham_members[k];
-            const int64_t c = ctx->h_copies[ent];
-            mem_genome.push_back(ctx->h_entry_genome[ent]);
-            mem_first_gene.push_back((int32_t)ctx->h_entry_first_gene[ent]);
-            mem_copies.push_back((int32_t)c);
-            sum_c += c;
-            sum_c2 += c * c;
+    };
+    {
+        // chunk sort + pairwise merges (the order is total, so the result does not depend on T)
+        const int chunks = infos.size() < 20000 ? 1 : T;
+        auto cut = [&](int c) { return infos.size() * (size_t)c / (size_t)chunks; };
+        run_threads(chunks, [&](int c) { std::sort(infos.begin() + cut(c), infos.begin() + cut(c + 1), by_cost); });
+        for (int width = 1; width < chunks; width *= 2) {
+            const int pairs = (chunks + 2 * width - 1) / (2 * width);
+            run_threads(pairs, [&](int q) {
+                const int lo = q * 2 * width, mid = std::min(lo + width, chunks), hi = std::min(lo + 2 * width, chunks);
+                if (mid < hi)
+                    std::inplace_merge(infos.begin() + cut(lo), infos.begin() + cut(mid), infos.begin() + cut(hi), by_cost);
+            });
         }
-        n_tasks += (sum_c * sum_c - sum_c2) / 2;          // sum over member pairs of ca * cb
-        ph_mem_off.push_back(ph_mem_off.back() + m);
-        ph_unit_off.push_back(ph_unit_off.back() + m * (m - 1) / 2);
     }
+    // this partition's phams, in snake order (0..P-1, P-1..0, ...): plain round-robin would hand
+    // partition 0 the largest pham of every group of P
+    std::vector<int64_t> mine;
+    for (size_t pos = 0; pos < infos.size(); ++pos) {
+        const size_t lap = pos / (size_t)n_parts, in_lap = pos % (size_t)n_parts;
+        if ((int)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap) == part) mine.push_back(infos[pos].pham);
+    }
+    std::vector<int64_t> ph_mem_off(mine.size() + 1, 0), ph_unit_off(mine.size() + 1, 0);
+    for (size_t x = 0; x < mine.size(); ++x) {
+        const int64_t m = ctx->h_pham_ptr[mine[x] + 1] - ctx->h_pham_ptr[mine[x]];
+        ph_mem_off[x + 1] = ph_mem_off[x] + m;
+        ph_unit_off[x + 1] = ph_unit_off[x] + m * (m - 1) / 2;
+    }
+    std::vector<int32_t> mem_genome(ph_mem_off.back()), mem_first_gene(ph_mem_off.back()), mem_copies(ph_mem_off.back());
+    std::vector<int64_t> tasks_of(T, 0);
+    run_threads(T, [&](int t) {
+        int64_t tasks = 0;
+        for (size_t x = mine.size() * (size_t)t / (size_t)T; x < mine.size() * (size_t)(t + 1) / (size_t)T; ++x) {
+            const int64_t b = ctx->h_pham_ptr[mine[x]], e = ctx->h_pham_ptr[mine[x] + 1];
+            int64_t sum_c = 0, sum_c2 = 0, at = ph_mem_off[x];
+            for (int64_t k = b; k < e; ++k, ++at) {
+                const int64_t ent = ctx->h_pham_members[k];
+                const int64_t c = ctx->h_copies[ent];
+                mem_genome[at] = ctx->h_entry_genome[ent];
+                mem_first_gene[at] = (int32_t)ctx->h_entry_first_gene[ent];
+                mem_copies[at] = (int32_t)c;
+                sum_c += c;
+                sum_c2 += c * c;
+            }
+            tasks += (sum_c * sum_c - sum_c2) / 2;        // sum over member pairs of ca * cb
+        }
+        tasks_of[t] = tasks;
+    });
+    int64_t n_tasks = 0;
+    for (int64_t v : tasks_of) n_tasks += v;
     pl.n_ph = (int64_t)ph_mem_off.size() - 1;
     pl.n_units = ph_unit_off.back();
     pl.n_tasks = n_tasks;
     pl.n_mem = (int64_t)mem_genome.size();
-    int32_t max_len = 0;
-    for (int32_t v : ctx->h_gene_len) max_len = std::max(max_len, v);
-    pl.max_gene_len = max_len;
+    pl.max_gene_len = ctx->max_gene_len;
     PC_TRY(upload(ctx, pl.ph_mem_off, ph_mem_off.data(), ph_mem_off.size()));
     PC_TRY(upload(ctx, pl.ph_unit_off, ph_unit_off.data(), ph_unit_off.size()));
     PC_TRY(upload(ctx, pl.mem_genome, mem_genome.data(), mem_genome.size()));

@@ -174,6 +174,8 @@ struct pc_ctx {
     // ---- sequences ----
     int64_t n_genes = 0;
     std::vector<int32_t> h_gene_len;
+    std::vector<int64_t> h_gene_off;               // 16 B aligned offsets in the code arena
+    int32_t max_gene_len = 0;
     DevBuf d_codes, d_gene_off, d_gene_len, d_raw, d_raw_off, d_lut;
     DevBuf d_canon;                                // gene -> smallest gene with the same translation
     DevBuf d_gene_hi;                              // per-gene upper bound of any DP score (LEX eligibility)
