@@ -36,6 +36,11 @@ def lib():
         L.nw_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.nw_tie_range.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ip]
+        L.nw_tie_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -77,4 +82,27 @@ def batch(residues, seq_off, q_idx, r_idx, gap_open=11, gap_extend=1, mode=1):
                         out.ctypes.data)
     if rc:
         raise MemoryError("nw_batch failed")
+    return out
+
+
+def tie_range(s1, s2, gap_open=11, gap_extend=1):
+    """(id_min, id_max, sm_min, sm_max, ln_min, ln_max, score) over ALL co-optimal
+    alignments of the score model -- what any tie-break rule could produce."""
+    a, b = s1.encode("latin-1"), s2.encode("latin-1")
+    out = (ctypes.c_int * 7)()
+    if lib().nw_tie_range(a, len(a), b, len(b), gap_open, gap_extend, out):
+        raise MemoryError("nw_tie_range failed")
+    return tuple(out)
+
+
+def tie_batch(residues, seq_off, q_idx, r_idx, gap_open=11, gap_extend=1):
+    """tie_range over a residue arena; returns int32 [n_tasks, 7]."""
+    residues = np.ascontiguousarray(residues, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    q_idx = np.ascontiguousarray(q_idx, dtype=np.int32)
+    r_idx = np.ascontiguousarray(r_idx, dtype=np.int32)
+    out = np.empty((len(q_idx), 7), dtype=np.int32)
+    if lib().nw_tie_batch(residues.ctypes.data, seq_off.ctypes.data, q_idx.ctypes.data,
+                          r_idx.ctypes.data, len(q_idx), gap_open, gap_extend, out.ctypes.data):
+        raise MemoryError("nw_tie_batch failed")
     return out

@@ -374,3 +374,100 @@ int nw_batch(const char *residues, const int64_t *seq_off, const int32_t *q_idx,
     }
     return 0;
 }
+
+/*
+ * How much of (ident, similar, length) depends on the UNPINNED tie rules (U2-U4)?
+ * Over ALL co-optimal alignments of the affine-gap score model (U1: any chain of
+ * tying candidates through the H/E/F state graph, whatever a traceback would
+ * prefer) compute the min and max of each count.  min == max for ident and
+ * length means the pair's contribution to aai/peq is the same under ANY tie
+ * rule, i.e. pinned by the score model alone (tests/test_oracle_nw.py checks
+ * that the restated rules always land inside the range).
+ * out: id_min, id_max, sm_min, sm_max, ln_min, ln_max, score.
+ */
+typedef struct { int lo[3], hi[3]; } rng_t;      /* 0 = ident, 1 = similar, 2 = length */
+
+static inline void rng_join(rng_t *acc, const rng_t *x, int did, int dsm, int dln, int *have)
+{
+    const int d[3] = {did, dsm, dln};
+    for (int k = 0; k < 3; ++k) {
+        const int lo = x->lo[k] + d[k], hi = x->hi[k] + d[k];
+        if (!*have || lo < acc->lo[k]) acc->lo[k] = lo;
+        if (!*have || hi > acc->hi[k]) acc->hi[k] = hi;
+    }
+    *have = 1;
+}
+
+int nw_tie_range(const char *a, int m, const char *b, int n, int open, int ext, int *out)
+{
+    init_mapper();
+    const unsigned char *s1 = (const unsigned char *)a;
+    const unsigned char *s2 = (const unsigned char *)b;
+    int *H = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    int *F = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    rng_t *rH = (rng_t *)calloc((size_t)(n + 1), sizeof(rng_t));
+    rng_t *rF = (rng_t *)calloc((size_t)(n + 1), sizeof(rng_t));
+    if (!H || !F || !rH || !rF) return -1;
+    H[0] = 0; F[0] = NEG_INF;
+    for (int j = 1; j <= n; ++j) {
+        H[j] = -open - (j - 1) * ext; F[j] = NEG_INF;
+        rH[j].lo[2] = rH[j].hi[2] = j;
+    }
+    for (int i = 1; i <= m; ++i) {
+        const int8_t *row = BLOSUM62[MAPPER[s1[i - 1]]];
+        int NH = H[0]; rng_t rNH = rH[0];
+        int WH = -open - (i - 1) * ext;
+        rng_t rWH; memset(&rWH, 0, sizeof rWH); rWH.lo[2] = rWH.hi[2] = i;
+        int E = NEG_INF; rng_t rE; memset(&rE, 0, sizeof rE);
+        H[0] = WH; rH[0] = rWH;
+        for (int j = 1; j <= n; ++j) {
+            int NWH = NH; rng_t rNWH = rNH;
+            NH = H[j]; rNH = rH[j];
+            const int F_opn = NH - open, F_ext = F[j] - ext;
+            const int E_opn = WH - open, E_ext = E - ext;
+            const int f = imax(F_opn, F_ext), e = imax(E_opn, E_ext);
+            rng_t nf, ne, nh;
+            int have = 0;
+            if (F_opn == f) rng_join(&nf, &rNH, 0, 0, 1, &have);
+            if (F_ext == f) rng_join(&nf, &rF[j], 0, 0, 1, &have);
+            have = 0;
+            if (E_opn == e) rng_join(&ne, &rWH, 0, 0, 1, &have);
+            if (E_ext == e) rng_join(&ne, &rE, 0, 0, 1, &have);
+            const int sub = row[MAPPER[s2[j - 1]]];
+            const int H_dag = NWH + sub;
+            const int h = imax(imax(H_dag, f), e);
+            have = 0;
+            if (H_dag == h) {
+                const int hit = chars_match(s1[i - 1], s2[j - 1]);
+                rng_join(&nh, &rNWH, hit, (!hit && sub > 0) ? 1 : 0, 1, &have);
+            }
+            if (f == h) rng_join(&nh, &nf, 0, 0, 0, &have);
+            if (e == h) rng_join(&nh, &ne, 0, 0, 0, &have);
+            F[j] = f; rF[j] = nf;
+            E = e; rE = ne;
+            WH = h; rWH = nh;
+            H[j] = h; rH[j] = nh;
+        }
+    }
+    out[0] = rH[n].lo[0]; out[1] = rH[n].hi[0];
+    out[2] = rH[n].lo[1]; out[3] = rH[n].hi[1];
+    out[4] = rH[n].lo[2]; out[5] = rH[n].hi[2];
+    out[6] = H[n];
+    free(H); free(F); free(rH); free(rF);
+    return 0;
+}
+
+/* batch form of nw_tie_range over a residue arena; out is n_tasks x 7 ints */
+int nw_tie_batch(const char *residues, const int64_t *seq_off, const int32_t *q_idx,
+                 const int32_t *r_idx, int64_t n_tasks, int open, int ext, int32_t *out)
+{
+    for (int64_t t = 0; t < n_tasks; ++t) {
+        int q = q_idx[t], r = r_idx[t];
+        int o[7];
+        int rc = nw_tie_range(residues + seq_off[q], (int)(seq_off[q + 1] - seq_off[q]),
+                              residues + seq_off[r], (int)(seq_off[r + 1] - seq_off[r]), open, ext, o);
+        if (rc) return rc;
+        for (int k = 0; k < 7; ++k) out[7 * t + k] = o[k];
+    }
+    return 0;
+}

@@ -85,3 +85,61 @@ def test_parasail_stub_traceback_shape():
         assert tb.query == "MKTAA" and tb.ref == "MKT--" and tb.comp == "|||  "
     finally:
         sys.path.remove(str(stub))
+
+
+# ---- how much of the result the unpinned tie rules can move ------------------------
+def _all_alignments(a, b):
+    """Every global alignment of a and b as (query, ref) strings with '-' (no
+    column of two gaps): brute force, tiny inputs only."""
+    if not a and not b:
+        yield "", ""
+        return
+    if a and b:
+        for q, r in _all_alignments(a[1:], b[1:]):
+            yield a[0] + q, b[0] + r
+    if a:
+        for q, r in _all_alignments(a[1:], b):
+            yield a[0] + q, "-" + r
+    if b:
+        for q, r in _all_alignments(a, b[1:]):
+            yield "-" + q, b[0] + r
+
+
+def test_tie_range_equals_brute_force_over_all_cooptimal_alignments():
+    """nw_tie_range (min/max of ident, similar, length over EVERY co-optimal alignment of
+    the score model) against explicit enumeration; and the restated tie rules always pick
+    one of those alignments."""
+    rng = random.Random(6)
+    seen_ties = 0
+    for t in range(300):
+        alpha = ["AG", "AGS", "AS", "AGWC", "NDB", testdata.AA][t % 6]
+        a = testdata.random_protein(rng, 0 if t % 9 == 0 else 1, 7, alpha)
+        b = testdata.random_protein(rng, 0 if t % 13 == 0 else 1, 5, alpha)
+        best, stats = None, set()
+        for q, r in _all_alignments(a, b):
+            score = nw_py.rescore(q, r)
+            if best is None or score > best:
+                best, stats = score, set()
+            if score == best:
+                ident = sum(1 for x, y in zip(q, r) if x == y and x != "-")
+                similar = sum(1 for x, y in zip(q, r) if x != y and "-" not in (x, y)
+                              and nw_c.lib().nw_blosum62(nw_c.lib().nw_map_char(ord(x)),
+                                                         nw_c.lib().nw_map_char(ord(y))) > 0)
+                stats.add((ident, similar, len(q)))
+        got = nw_c.tie_range(a, b)
+        assert got[6] == best
+        assert (got[0], got[1]) == (min(s[0] for s in stats), max(s[0] for s in stats))
+        assert (got[2], got[3]) == (min(s[1] for s in stats), max(s[1] for s in stats))
+        assert (got[4], got[5]) == (min(s[2] for s in stats), max(s[2] for s in stats))
+        assert nw_c.forward_stats(a, b)[:3] in stats          # the restated rules are co-optimal
+        seen_ties += len(stats) > 1
+    assert seen_ties >= 3           # the sample does exercise tie-dependent cases
+
+
+def test_restated_rules_land_inside_the_tie_range_on_protein_sized_inputs():
+    for a, b in _pairs(600, 8, max_len=120):
+        lo_hi = nw_c.tie_range(a, b)
+        ident, similar, length, score = nw_c.forward_stats(a, b)
+        assert score == lo_hi[6]
+        assert lo_hi[0] <= ident <= lo_hi[1] and lo_hi[2] <= similar <= lo_hi[3]
+        assert lo_hi[4] <= length <= lo_hi[5]
