@@ -5,6 +5,7 @@ entry) and one residue arena with genes in CSR entry order.
 Only this module walks the Python dicts, once per matrix; the per-pair set
 construction of the reference (genome.py:135) has no equivalent here.
 """
+import itertools
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -57,28 +58,40 @@ class PackedTable:
 
 
 def pack_genomes(genomes, with_sequences=True):
-    """list[Genome] (anything with ``.name`` and ``.phams``) -> PackedTable."""
+    """list[Genome] (anything with ``.name`` and ``.phams``) -> PackedTable.
+
+    One Python-level step per (genome, pham) entry at most: ids come from a list
+    comprehension over the genome's dict, copies / gene lengths from ``map(len, ...)``
+    and the per-entry length sums from one ``np.add.reduceat`` (this pass is on the
+    critical path of ``matrix_de_novo`` and costs more than the GPU work when it is
+    written as a plain double loop)."""
     vocab = {}
+    intern_pham = vocab.setdefault
     names, ptr = [], [0]
-    pham_ids, copies, len_sums, seqs = [], [], [], []
+    pham_ids, gene_lists = [], []
     for genome in genomes:
         names.append(genome.name)
-        for pham, translations in genome.phams.items():
+        phams = genome.phams
+        for pham in phams:
             if not isinstance(pham, str):
                 raise TypeError(f"type(pham) should be 'str', not '{type(pham)}'")
-            pham_ids.append(vocab.setdefault(pham, len(vocab)))
-            copies.append(len(translations))
-            len_sums.append(sum(map(len, translations)))
-            if with_sequences:
-                seqs.extend(translations)
+        pham_ids += [intern_pham(pham, len(vocab)) for pham in phams]
+        gene_lists += phams.values()
         ptr.append(len(pham_ids))
+    nnz = len(pham_ids)
+    copies = np.fromiter(map(len, gene_lists), dtype=np.int64, count=nnz)
+    seqs = list(itertools.chain.from_iterable(gene_lists))
+    lens = np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs))
+    seq_off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=seq_off[1:])
+    first_gene = np.zeros(nnz + 1, dtype=np.int64)
+    np.cumsum(copies, out=first_gene[1:])
+    len_sums = seq_off[first_gene[1:]] - seq_off[first_gene[:-1]]      # exact, also for 0 copies
     table = PackedTable(names, list(vocab), np.asarray(ptr, dtype=np.int64),
                         np.asarray(pham_ids, dtype=np.int32),
-                        np.asarray(copies, dtype=np.uint32),
-                        np.asarray(len_sums, dtype=np.uint32))
+                        copies.astype(np.uint32), len_sums.astype(np.uint32))
     if with_sequences:
-        lens = np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs))
-        table.seq_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        table.seq_off = seq_off
         blob = "".join(seqs).encode("latin-1", errors="replace")
         if len(blob) != int(table.seq_off[-1]):
             raise ValueError("translations must be single-byte characters")
