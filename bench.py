@@ -14,9 +14,14 @@ bundled ``benchmark_data.tsv``.  That file is absent from the reference mount
 * ``value``  : pairs/s with the packed table + residues already resident in HBM
                (CUDA events on the stream the kernels run on, L2 flushed between
                steps, max over ranks).
-* ``e2e``    : the same metric through the C ABI with HOST buffers every step:
+* ``e2e``    : the same metric through the C ABI with (pinned) HOST buffers every step:
                pc_load_table + pc_load_sequences + pc_matrix, H2D and D2H inside
-               the timed region.
+               the timed region.  N > 1: every rank loads from host buffers, aligns
+               its phams, joins the NCCL all-reduce and copies its row block from
+               its own GPU into one page-locked shared-memory triangle
+               (distributed.SharedTriangle) -- the consumer is the host.
+* other workloads: ``--workload c3`` (10k x 60k, jc/pocp/af/gcs), ``c4`` (50k genomes,
+               peq/aai, the 8-GPU target of BASELINE.json), ``c5`` (100k x 200k, gcs).
 * ``roofline``: the dominant kernel (the alignment DP for peq/aai, the
                shared-count contraction for gcs/jc/pocp/af).
 * ``cpu_baseline``: the oracle port of the reference's CPU path on a bounded
