@@ -234,6 +234,14 @@ int pc_parse_squareform(const char *buf, int64_t len, int64_t n,
 /* Field scanner for the 2/3-column TSV of scripts/phamclust.py:21-47. */
 int64_t pc_scan_tsv(const char *buf, int64_t len, int64_t max_rows,
                     int64_t *fields);
+/*
+ * Dense square view of the packed triangle in traversal order: SymMatrix.to_ndarray
+ * (matrix.py:155-167), the array clustering.py:27 hands to scikit-learn.  kind 0:
+ * float64 micro / 1e6 (PC_EINVAL if an entry is unset / outside [0, 1e6]); kind 1:
+ * the int32 micro-units.  out holds n * n elements.
+ */
+int pc_dense_from_micro(int64_t n, const int32_t *micro, const int64_t *order,
+                        int kind, void *out);
 const char *pc_io_last_error(void);
 
 #ifdef __cplusplus

@@ -5,11 +5,13 @@
 // without this the hand-off of a 10k-genome matrix spends
 // minutes in per-value Python formatting.  The lower-triangle form is the
 // pipeline's on-disk cache (scripts/phamclust.py:254-268) and stays byte-identical.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/phamclust_b200.h"
@@ -182,3 +184,66 @@ extern "C" int64_t pc_scan_tsv(const char *buf, int64_t len, int64_t max_rows, i
     }
     return rows;
 }
+
+// Dense square view of the packed triangle in traversal order (SymMatrix.to_ndarray,
+// /root/reference/src/phamclust/matrix.py:155-167: what clustering.py:27 feeds to scikit-learn).
+// kind 0: float64 weights micro / 1e6 (the exact value round(w, 6) stores); every entry must
+// be a set weight in [0, 1e6] (PC_EINVAL otherwise: the caller falls back to the object
+// array the reference builds for unset entries).  kind 1: the int32 micro-units as they are.
+// order[k] = storage index of the k-th node in traversal order.
+extern "C" int pc_dense_from_micro(int64_t n, const int32_t *micro, const int64_t *order, int kind,
+                                   void *out)
+{
+    if (n < 0 || (n > 0 && (!micro || !order || !out)) || kind < 0 || kind > 1) {
+        g_io_error = "pc_dense_from_micro: bad arguments";
+        return PC_EINVAL;
+    }
+    for (int64_t k = 0; k < n; ++k)
+        if (order[k] < 0 || order[k] >= n) { g_io_error = "pc_dense_from_micro: bad traversal order"; return PC_EINVAL; }
+    // idx(a, b >= a) = base[a] + b
+    std::vector<int64_t> base((size_t)n);
+    for (int64_t a = 0; a < n; ++a) base[a] = a * n - (a * (a - 1)) / 2 - a;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = n < 512 ? 1 : (int)std::max(1u, std::min(8u, hw));
+    std::vector<int> bad((size_t)T, 0);
+    // 64 x 64 tiles; inside a tile the loop whose index runs along the packed rows of the
+    // triangle goes innermost (columns above the diagonal, rows below it), so both halves
+    // read the triangle contiguously when the traversal order is (piecewise) the storage order
+    constexpr int64_t TILE = 64;
+    const int64_t n_blocks = (n + TILE - 1) / TILE;
+    auto body = [&](int t) {
+        double *outd = static_cast<double *>(out);
+        int32_t *outi = static_cast<int32_t *>(out);
+        auto put = [&](int64_t k, int64_t l) {
+            const int64_t a = order[k], b = order[l];
+            const int32_t v = micro[b >= a ? base[a] + b : base[b] + a];
+            if (kind == 0) {
+                if ((uint32_t)v > 1000000u) bad[t] = 1;
+                outd[k * n + l] = (double)v / 1e6;
+            } else {
+                outi[k * n + l] = v;
+            }
+        };
+        for (int64_t kb = n_blocks * t / T; kb < n_blocks * (t + 1) / T; ++kb) {
+            const int64_t k0 = kb * TILE, k1 = std::min(n, k0 + TILE);
+            for (int64_t l0 = 0; l0 < n; l0 += TILE) {
+                const int64_t l1 = std::min(n, l0 + TILE);
+                if (order[l0] >= order[k0]) {
+                    for (int64_t k = k0; k < k1; ++k)
+                        for (int64_t l = l0; l < l1; ++l) put(k, l);
+                } else {
+                    for (int64_t l = l0; l < l1; ++l)
+                        for (int64_t k = k0; k < k1; ++k) put(k, l);
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(body, t);
+    body(0);
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < T; ++t)
+        if (bad[t]) { g_io_error = "pc_dense_from_micro: unset or out-of-range weight"; return PC_EINVAL; }
+    return PC_OK;
+}
+

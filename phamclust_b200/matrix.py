@@ -228,28 +228,38 @@ class SymMatrix:
         return self._locked
 
     # -- bulk views ---------------------------------------------------------------------
+    def _traversal_order(self):
+        """Storage index of every node in traversal order."""
+        if self._nodes == self._store:
+            return np.arange(len(self._store), dtype=np.int64)
+        return np.fromiter((self._index[x] for x in self._nodes), dtype=np.int64, count=len(self._nodes))
+
+    def _dense(self, order, kind):
+        """n x n view of the packed triangle with rows/columns in ``order`` through
+        libphamclust_b200's host-side pc_dense_from_micro (threaded gather; no
+        N(N+1)/2-sized index arrays): kind 0 = float64 weights, 1 = int32 micro-units.
+        Returns None when kind 0 meets an unset weight."""
+        n = len(self._store)
+        out = np.empty((n, n), dtype=np.float64 if kind == 0 else np.int32)
+        lib = _native.load_library()
+        micro = np.ascontiguousarray(self._micro, dtype=np.int32)
+        rc = lib.pc_dense_from_micro(n, micro.ctypes.data, order.ctypes.data, kind, out.ctypes.data)
+        return out if rc == 0 else None
+
     def _dense_micro(self):
         """Square int32 matrix in STORAGE order."""
-        n = len(self._store)
-        dense = np.empty((n, n), dtype=np.int32)
-        iu = np.triu_indices(n)
-        dense[iu] = self._micro
-        dense.T[iu] = self._micro
-        return dense
+        return self._dense(np.arange(len(self._store), dtype=np.int64), 1)
 
     def to_ndarray(self, condensed=False):
         """Square float64 matrix in TRAVERSAL order (or scipy's condensed form);
         what clustering.py:27 and _get_tree_order consume."""
-        dense = self._dense_micro()
-        if self._nodes != self._store:
-            perm = np.fromiter((self._index[x] for x in self._nodes), dtype=np.int64,
-                               count=len(self._nodes))
-            dense = dense[np.ix_(perm, perm)]
-        if (dense == _UNSET).any():
+        order = self._traversal_order()
+        full = self._dense(order, 0)
+        if full is None:                  # unset weights: the object array the reference builds
+            dense = self._dense(order, 1)
             full = dense.astype(object) / 1e6
             full[dense == _UNSET] = None
             return full
-        full = dense / 1e6
         if condensed:
             from scipy.spatial.distance import squareform
             return squareform(full, force="tovector")

@@ -330,3 +330,30 @@ def test_row_partition_balances_pairs():
             assert sum(sizes) == n * (n + 1) // 2
             if n >= 100:
                 assert max(sizes) - min(sizes) <= 2 * n
+
+
+def test_dense_views_come_from_the_native_gather():
+    """SymMatrix.to_ndarray / _dense_micro go through pc_dense_from_micro (threaded tiled
+    gather in libphamclust_b200, host only): storage order, permuted traversal order, sizes
+    that are not multiples of the tile, and the object-array fallback for unset weights."""
+    import numpy as np
+    from phamclust_b200.matrix import SymMatrix
+    rng = np.random.default_rng(12)
+    for n in (1, 2, 63, 64, 65, 700):
+        tri = rng.integers(0, 1000001, size=n * (n + 1) // 2, dtype=np.int32)
+        names = [f"n{k:04d}" for k in range(n)]
+        m = SymMatrix.from_micro(names, tri, is_distance=False)
+        iu = np.triu_indices(n)
+        want = np.empty((n, n), dtype=np.int32)
+        want[iu] = tri
+        want.T[iu] = tri
+        assert np.array_equal(m._dense_micro(), want)
+        assert np.array_equal(m.to_ndarray(), want / 1e6)
+        perm = rng.permutation(n)
+        m._nodes = [names[k] for k in perm]
+        got = m.to_ndarray()
+        assert got.dtype == np.float64 and np.array_equal(got, (want / 1e6)[np.ix_(perm, perm)])
+    holes = SymMatrix(["a", "b", "c"], is_distance=True)
+    holes.set_weight("a", "b", 0.25)
+    full = holes.to_ndarray()
+    assert full.dtype == object and full[0][1] == 0.25 and full[1][0] == 0.25 and full[2][2] is None
