@@ -271,10 +271,21 @@ class SymMatrix:
             yield source, [x if x is None else float(x) for x in full[k]]
 
     def __iter__(self):
-        """(source, target, weight) over the upper half in traversal order."""
-        for idx, source in enumerate(self._nodes):
-            for target in self._nodes[idx:]:
-                yield source, target, self.get_weight(source, target)
+        """(source, target, weight) over the upper half in traversal order
+        (matrix.py:349-357); one vectorised row of the packed triangle per source
+        instead of one dict-style lookup per edge."""
+        nodes = self._nodes[:]
+        order = self._traversal_order()
+        offsets = self._offsets
+        for idx, source in enumerate(nodes):
+            a, b = order[idx], order[idx:]
+            lo, hi = np.minimum(a, b), np.maximum(a, b)
+            vals = self._micro[offsets[lo] + (hi - lo)]
+            weights = (vals / 1e6).tolist()
+            if (vals == _UNSET).any():
+                weights = [None if v == _UNSET else w for v, w in zip(vals.tolist(), weights)]
+            for target, weight in zip(nodes[idx:], weights):
+                yield source, target, weight
 
     def __contains__(self, item):
         if not isinstance(item, str):
