@@ -17,7 +17,7 @@ SOURCES = ["pc_api.cu", "pc_contract_popc.cu", "pc_contract_i8.cu", "pc_align.cu
            "pc_io.cu", "pc_dedup.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",
-              "-lcuda"]
+              "-lcuda", "--threads", "8"]
 
 
 def _newest_source_mtime():
