@@ -235,6 +235,16 @@ int pc_parse_squareform(const char *buf, int64_t len, int64_t n,
 int64_t pc_scan_tsv(const char *buf, int64_t len, int64_t max_rows,
                     int64_t *fields);
 /*
+ * TSV -> packed table helpers: intern the name (col 0) or pham (col 1) column of the
+ * scanned rows in first-seen order (ids[r], first_row[id]; returns the number of
+ * distinct strings or -1), and concatenate byte ranges into the residue arena
+ * (start < 0 -> the single byte `fill`, the "M" of 2-column rows).
+ */
+int64_t pc_tsv_intern(const char *buf, int64_t rows, const int64_t *fields, int col,
+                      int32_t *ids, int64_t *first_row);
+int pc_gather_fields(const char *buf, int64_t n, const int64_t *start,
+                     const int64_t *len, uint8_t fill, uint8_t *out);
+/*
  * Dense square view of the packed triangle in traversal order: SymMatrix.to_ndarray
  * (matrix.py:155-167), the array clustering.py:27 hands to scikit-learn.  kind 0:
  * float64 micro / 1e6 (PC_EINVAL if an entry is unset / outside [0, 1e6]); kind 1:

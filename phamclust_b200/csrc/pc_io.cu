@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/phamclust_b200.h"
@@ -183,6 +185,53 @@ extern "C" int64_t pc_scan_tsv(const char *buf, int64_t len, int64_t max_rows, i
         pos = eol + 1;
     }
     return rows;
+}
+
+// Intern one column of the scanned TSV: ids[r] = index of the distinct byte string
+// buf[fields[6r + 2*col] .. fields[6r + 2*col + 1]) in FIRST-SEEN order (the order in which
+// load_genomes_from_tsv's dict meets genome names, scripts/phamclust.py:41-45);
+// first_row[id] = the row that introduced it.  col 0 = name, 1 = pham.  Returns the number
+// of distinct strings (first_row must hold `rows` entries at most), or -1.
+extern "C" int64_t pc_tsv_intern(const char *buf, int64_t rows, const int64_t *fields, int col,
+                                 int32_t *ids, int64_t *first_row)
+{
+    if (rows < 0 || (rows > 0 && (!buf || !fields || !ids || !first_row)) || col < 0 || col > 1) {
+        g_io_error = "pc_tsv_intern: bad arguments";
+        return -1;
+    }
+    std::unordered_map<std::string_view, int32_t> seen;
+    seen.reserve((size_t)std::min<int64_t>(rows, 1 << 20));
+    for (int64_t r = 0; r < rows; ++r) {
+        const int64_t b = fields[6 * r + 2 * col], e = fields[6 * r + 2 * col + 1];
+        const std::string_view key(buf + b, (size_t)(e - b));
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            const int32_t id = (int32_t)seen.size();
+            first_row[id] = r;
+            it = seen.emplace(key, id).first;
+        }
+        ids[r] = it->second;
+    }
+    return (int64_t)seen.size();
+}
+
+// Concatenate n byte ranges of buf into out (the residue arena): range k is
+// buf[start[k] .. start[k] + len[k]), or the single byte `fill` when start[k] < 0
+// (2-column rows carry the translation "M", scripts/phamclust.py:37-38).
+extern "C" int pc_gather_fields(const char *buf, int64_t n, const int64_t *start, const int64_t *len,
+                                uint8_t fill, uint8_t *out)
+{
+    if (n < 0 || (n > 0 && (!buf || !start || !len || !out))) {
+        g_io_error = "pc_gather_fields: bad arguments";
+        return PC_EINVAL;
+    }
+    int64_t at = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        if (start[k] < 0) { out[at++] = fill; continue; }
+        memcpy(out + at, buf + start[k], (size_t)len[k]);
+        at += len[k];
+    }
+    return PC_OK;
 }
 
 // Dense square view of the packed triangle in traversal order (SymMatrix.to_ndarray,

@@ -134,27 +134,27 @@ def table_from_tsv(filepath, with_sequences=True):
     rows = int(lib.pc_scan_tsv(data, len(data), max_rows, fields.ctypes.data))
     if rows < 0:
         raise ValueError(lib.pc_io_last_error().decode())
-    fields = fields[:rows]
-    genome_of, entry_of = {}, {}
-    names, vocab = [], {}
-    row_entry = np.empty(rows, dtype=np.int64)
-    entry_genome, entry_pham = [], []
-    for r, (n0, n1, p0, p1) in enumerate(fields[:, :4].tolist()):
-        name, pham = data[n0:n1], data[p0:p1]
-        g = genome_of.get(name)
-        if g is None:
-            g = genome_of[name] = len(names)
-            names.append(name.decode())
-        key = (g, pham)
-        e = entry_of.get(key)
-        if e is None:
-            e = entry_of[key] = len(entry_genome)
-            entry_genome.append(g)
-            entry_pham.append(pham)
-        row_entry[r] = e
-    entry_genome = np.asarray(entry_genome, dtype=np.int64)
-    # CSR order: by genome (first seen), then by first appearance of the pham in it
-    order = np.argsort(entry_genome, kind="stable")
+    fields = np.ascontiguousarray(fields[:rows])
+    # genome and pham names interned in first-seen order by the library (one hash lookup per
+    # row in C++, no per-row Python)
+    row_genome = np.empty(rows, dtype=np.int32)
+    row_name = np.empty(rows, dtype=np.int32)
+    first_genome_row = np.empty(max(rows, 1), dtype=np.int64)
+    first_name_row = np.empty(max(rows, 1), dtype=np.int64)
+    n_genomes = int(lib.pc_tsv_intern(data, rows, fields.ctypes.data, 0, row_genome.ctypes.data,
+                                      first_genome_row.ctypes.data))
+    n_names = int(lib.pc_tsv_intern(data, rows, fields.ctypes.data, 1, row_name.ctypes.data,
+                                    first_name_row.ctypes.data))
+    if n_genomes < 0 or n_names < 0:
+        raise ValueError(lib.pc_io_last_error().decode())
+    names = [data[b:e].decode() for b, e in fields[first_genome_row[:n_genomes], 0:2].tolist()]
+    # entries = distinct (genome, pham); CSR order = by genome (first seen), then by the first
+    # row of the pham inside that genome
+    key = row_genome.astype(np.int64) * max(n_names, 1) + row_name
+    uniq, first_row, row_entry = np.unique(key, return_index=True, return_inverse=True)
+    entry_genome = uniq // max(n_names, 1)
+    entry_name = uniq % max(n_names, 1)
+    order = np.lexsort((first_row, entry_genome))
     rank = np.empty(len(order), dtype=np.int64)
     rank[order] = np.arange(len(order))
     row_slot = rank[row_entry]
@@ -163,21 +163,25 @@ def table_from_tsv(filepath, with_sequences=True):
     t0, t1 = fields[:, 4], fields[:, 5]
     lens = np.where(t0 < 0, 1, t1 - t0)
     len_sum = np.bincount(row_slot, weights=lens, minlength=len(order)).astype(np.uint32)
-    ptr = np.zeros(len(names) + 1, dtype=np.int64)
-    np.cumsum(np.bincount(entry_genome, minlength=len(names)), out=ptr[1:])
-    # pham ids in the order pack_genomes would meet them (genome by genome)
-    pham_id = np.fromiter((vocab.setdefault(entry_pham[e], len(vocab)) for e in order.tolist()),
-                          dtype=np.int32, count=len(order))
-    table = PackedTable(names, [p.decode() for p in vocab], ptr, pham_id, copies, len_sum)
+    ptr = np.zeros(n_genomes + 1, dtype=np.int64)
+    np.cumsum(np.bincount(entry_genome, minlength=n_genomes), out=ptr[1:])
+    # pham ids in the order pack_genomes would meet them (genome by genome, CSR order)
+    csr_name = entry_name[order]
+    met, met_at = np.unique(csr_name, return_index=True)
+    vocab_rank = np.empty(max(n_names, 1), dtype=np.int64)
+    vocab_order = met[np.argsort(met_at, kind="stable")]      # interned name ids in vocabulary order
+    vocab_rank[vocab_order] = np.arange(len(vocab_order))
+    pham_id = vocab_rank[csr_name].astype(np.int32)
+    phams = [data[b:e].decode() for b, e in fields[first_name_row[vocab_order], 2:4].tolist()]
+    table = PackedTable(names, phams, ptr, pham_id, copies, len_sum)
     if with_sequences:
-        glen = lens[row_order]
+        glen = np.ascontiguousarray(lens[row_order], dtype=np.int64)
         table.seq_off = np.concatenate(([0], np.cumsum(glen))).astype(np.int64)
-        raw = np.frombuffer(data, dtype=np.uint8)
+        starts = np.ascontiguousarray(t0[row_order], dtype=np.int64)
         res = np.empty(int(table.seq_off[-1]), dtype=np.uint8)
-        starts = t0[row_order]
-        # gather every translation's bytes ("M" for 2-column rows)
-        idx = np.repeat(np.where(starts < 0, 0, starts) - table.seq_off[:-1], glen) + np.arange(len(res))
-        res[:] = raw[idx] if len(res) else res
-        res[np.repeat(starts < 0, glen)] = ord("M")
+        # every translation's bytes ("M" for 2-column rows), one memcpy per gene in the library
+        if lib.pc_gather_fields(data, len(starts), starts.ctypes.data, glen.ctypes.data, ord("M"),
+                                res.ctypes.data):
+            raise ValueError(lib.pc_io_last_error().decode())
         table.residues = res
     return table
