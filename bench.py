@@ -290,15 +290,24 @@ def run_native(args):
             step()
             stop.record()
         barrier()
-    step_ms = [s.elapsed_time(e) for s, e in events]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    counters = ctx.counters()
-    stats = ctx.stats()
-    lex_cells = stats["lex_cells"] if need_seqs else 0
-    timings = ctx.timings()
+        step_ms = [s.elapsed_time(e) for s, e in events]
+        total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        total_ms = float(total_ms.item())
+        counters = ctx.counters()
+        stats = ctx.stats()
+        lex_cells = stats["lex_cells"] if need_seqs else 0
+        timings = ctx.timings()
+        # nvidia-smi polls every 100 ms (and takes a while to start): a timed region shorter than
+        # ~0.7 s is followed by UNTIMED steps of the same load until the sampler has had time to
+        # see it.  The count derives from the max-over-ranks time, so every rank runs the same
+        # number of (collective) steps; counters and timings were read above.
+        clocks_extended = total_ms < 700.0
+        if clocks_extended:
+            for _ in range(min(200, int(np.ceil((700.0 - total_ms) / max(total_ms / args.steps, 1e-3))))):
+                step()
+            barrier()
     local_sum = out_local[:_native.tri_len(n, r0, r1)].to(torch.int64).sum().reshape(1)
     if world > 1:
         dist.all_reduce(local_sum, op=dist.ReduceOp.SUM)
@@ -391,6 +400,8 @@ def run_native(args):
     # ---- roofline of the dominant kernel --------------------------------------------
     peaks, peak_kind = measured_peaks()
     clk = clocks.summary()
+    if clocks_extended:
+        clk["window"] = "timed region + untimed repeats of the same step until 0.7 s had passed (nvidia-smi polls every 100 ms)"
     if need_seqs:
         cells = counters["dp_cells"]
         cls_cells = cells - lex_cells
