@@ -185,6 +185,39 @@ class SymMatrix:
         micro = self._micro[self._offsets[lo] + (hi - lo)]
         return SymMatrix(nodes, self.is_distance, _micro=np.ascontiguousarray(micro))
 
+    def threshold_components(self, max_micro):
+        """Connected components of the graph whose edges are the off-diagonal pairs with
+        weight <= max_micro micro-units, as one int label per node of ``self.nodes``
+        (traversal order); None if a weight is unset.  The packed triangle is scanned in
+        row blocks (no dense N x N): this is what lets clustering.hierarchical_clustering
+        hand scikit-learn one small block per component instead of the whole matrix."""
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        n = len(self._store)
+        if (self._micro == _UNSET).any():
+            return None
+        rows, cols = [], []
+        offsets = self._offsets
+        step = max(1, (1 << 24) // max(n, 1))              # ~16 M entries per block
+        for r0 in range(0, n, step):
+            r1 = min(n, r0 + step)
+            lo, hi = int(offsets[r0]), int(offsets[r1])
+            hit = np.flatnonzero(self._micro[lo:hi] <= max_micro) + lo
+            if hit.size == 0:
+                continue
+            i = np.searchsorted(offsets, hit, side="right") - 1
+            j = i + (hit - offsets[i])
+            off_diag = j != i
+            rows.append(i[off_diag])
+            cols.append(j[off_diag])
+        if rows:
+            rows, cols = np.concatenate(rows), np.concatenate(cols)
+        else:
+            rows = cols = np.zeros(0, dtype=np.int64)
+        graph = coo_matrix((np.ones(len(rows), dtype=np.int8), (rows, cols)), shape=(n, n))
+        _, storage_label = connected_components(graph, directed=False)
+        return storage_label[self._traversal_order()]
+
     def invert(self):
         """distance <-> similarity in place: round(1 - w, 6) == (1e6 - n)/1e6."""
         if self._locked:

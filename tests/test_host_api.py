@@ -357,3 +357,49 @@ def test_dense_views_come_from_the_native_gather():
     holes.set_weight("a", "b", 0.25)
     full = holes.to_ndarray()
     assert full.dtype == object and full[0][1] == 0.25 and full[1][0] == 0.25 and full[2][2] is None
+
+
+def test_component_wise_clustering_equals_the_dense_path():
+    """hierarchical_clustering on matrices too large for a dense N x N: connected components
+    of {d < eps} from the packed triangle, scikit-learn per component.  Same partitions in the
+    same order as the reference's dense path for all three linkages (continuous distances: no
+    exact ties), permuted traversal order included; single linkage also on a coarse grid."""
+    import numpy as np
+    from phamclust_b200 import clustering
+    from phamclust_b200.matrix import SymMatrix
+
+    def random_matrix(rng, n, k, grid):
+        g = rng.integers(0, k, size=n)
+        d = np.where(g[:, None] == g[None, :], rng.random((n, n)) * 0.5, 0.4 + rng.random((n, n)) * 0.6)
+        d = (d + d.T) / 2
+        if grid:
+            d = np.round(d * grid) / grid
+        np.fill_diagonal(d, 0.0)
+        micro = np.rint(d[np.triu_indices(n)] * 1e6).astype(np.int32)
+        return SymMatrix.from_micro([f"n{i:04d}" for i in range(n)], micro, True)
+
+    def run(matrix, linkage, eps, min_nodes):
+        saved = clustering.DECOMPOSE_MIN_NODES
+        clustering.DECOMPOSE_MIN_NODES = min_nodes
+        try:
+            return [frozenset(c.nodes) for c in clustering.hierarchical_clustering(matrix, linkage, eps=eps)]
+        finally:
+            clustering.DECOMPOSE_MIN_NODES = saved
+
+    rng = np.random.default_rng(5)
+    for trial in range(30):
+        n, k = int(rng.integers(5, 120)), int(rng.integers(1, 8))
+        m = random_matrix(rng, n, k, 0)
+        if trial % 3 == 0:
+            m.reorder([m.nodes[i] for i in rng.permutation(n)])
+        for linkage in ("single", "average", "complete"):
+            for eps in (0.25, 0.4, 0.75):
+                assert run(m, linkage, eps, 2) == run(m, linkage, eps, 10 ** 9), (trial, linkage, eps)
+        coarse = random_matrix(rng, n, k, 8)
+        assert run(coarse, "single", 0.4, 2) == run(coarse, "single", 0.4, 10 ** 9)
+    # the scan walks the triangle in row blocks: a matrix spanning several of them
+    big = random_matrix(rng, 4500, 90, 0)
+    assert run(big, "complete", 0.25, 4096) == run(big, "complete", 0.25, 10 ** 9)
+    # unset weights: no component labels, the dense path takes over (and fails like upstream)
+    holes = SymMatrix(["a", "b", "c"], is_distance=True)
+    assert holes.threshold_components(250001) is None
