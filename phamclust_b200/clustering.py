@@ -17,7 +17,6 @@ a coarse grid) the component-wise and the dense run may each return a different 
 single linkage is unique.  Matrices below ``DECOMPOSE_MIN_NODES`` nodes always take the
 reference's dense path.
 """
-import numpy as np
 from sklearn.cluster import AgglomerativeClustering
 
 # matrices with at least this many nodes take the component-wise path (tests lower it)
