@@ -134,8 +134,12 @@ class SharedTriangle:
         if self.rank != 0:
             self._shm = shared_memory.SharedMemory(name=name[0])
             try:        # the creator unlinks; keep this process's resource tracker out of it
+                import multiprocessing
                 from multiprocessing import resource_tracker
-                resource_tracker.unregister(self._shm._name, "shared_memory")
+                # (a multiprocessing child shares its parent's tracker with the creator:
+                # attaching registered nothing new there, so there is nothing to take back)
+                if multiprocessing.parent_process() is None:
+                    resource_tracker.unregister(self._shm._name, "shared_memory")
             except Exception:
                 pass
         self.array = np.ndarray((count,), dtype=np.int32, buffer=self._shm.buf)

@@ -112,6 +112,26 @@ def test_two_rank_sharding_equals_single_rank(metric):
     assert results[0] == single and results[1] == single
 
 
+def test_more_ranks_than_rows_leaves_empty_blocks():
+    """3 ranks, 2 genomes: one rank owns no row at all -- both exchanges must still agree."""
+    rows = testdata.genome_rows(seed=4, n_genomes=2, n_phams=6, lo=10, hi=30, paralog_p=0.3)
+    genomes = testdata.rows_to_genomes(rows, cls=Genome)
+    assert distributed.row_partition(2, 3) == [0, 1, 1, 2]
+    ops = OracleOps(genomes, "peq", True)
+    single = ops.rows(0, 2, ops.accumulate(0, 1)).tolist()
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 3, port, rows, "peq", queue)) for r in range(3)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=120) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0] == results[1] == results[2] == single
+
+
 def test_assemble_trims_padding():
     n, bounds = 5, [0, 2, 5]
     full = np.arange(15, dtype=np.int32)
