@@ -205,13 +205,14 @@ enum {
     PC_STAT_UNIQUE_GENES = 1,       /* distinct translations among the loaded genes              */
     PC_STAT_OPERAND_COLUMNS = 2,    /* phams held by >= 2 genomes (contraction K)                */
     PC_STAT_GENES = 3,
-    PC_STAT_LEX_ALIGNMENTS = 4,     /* DP tasks run by the LEX kernel since pc_reset_counters    */
-    PC_STAT_LEX_CELLS = 5,          /* DP cells of those tasks (pc_counters' dp_cells has both)  */
+    PC_STAT_LEX_ALIGNMENTS = 4,     /* DP tasks run by the LEX kernels since pc_reset_counters   */
+    PC_STAT_LEX_CELLS = 5,          /* DP cells of the plain LEX kernel (pc_counters' dp_cells has all) */
     PC_STAT_DP_CONFIGS_USED = 6,    /* distinct DP kernel configs launched since the reset        */
     PC_STAT_DP_CONFIGS = 7,         /* DP kernel configs the chooser can pick for the loaded data */
     PC_STAT_I8_TILE_STEPS = 8,      /* int8 engine: 128x256x128 MMA groups issued since the reset
                                        (the block-sparse K schedule skips the rest)              */
-    PC_STAT_I8_TILE_STEPS_DENSE = 9 /* ... and what a dense K schedule would have issued          */
+    PC_STAT_I8_TILE_STEPS_DENSE = 9,/* ... and what a dense K schedule would have issued          */
+    PC_STAT_LEXR_CELLS = 10         /* DP cells run by the rebased LEX kernel (10-bit counters)   */
 };
 int pc_stat(pc_ctx *ctx, int which, int64_t *out);
 

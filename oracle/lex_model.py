@@ -76,3 +76,105 @@ def lex_stats(q, r, ppos=False, check=None):
     matched = word & CMASK
     columns = m + n - ((word >> BITS) & CMASK)
     return matched, columns, score
+
+
+# ---------------------------------------------------------------------------------------------
+# LEXR: the same word with a NARROW score field that every lane keeps centred by rebasing.
+#
+# DP values are Lipschitz: neighbouring cells differ by at most LIP = max substitution score +
+# open + ext (drifted units), and E/F sit within open + LIP below their H.  A lane that owns K
+# adjacent columns therefore only ever combines values within LIP * (K/2 + rows since its last
+# rebase) + slack of the H of its centre column.  ``nw_lex_kernel<.., REBASE>`` subtracts that centre
+# score from all of the lane's state every REBASE row-steps and keeps the running sum (``base``)
+# in a separate register, so a 10-bit score field (window +-512) is enough for ANY score range
+# and the counters can take 10 bits each: alignments with min(m, n) < 1024.  This model follows
+# the kernel's schedule exactly (G lanes x K columns, lane l one row behind lane l-1, rebase at
+# the top of every REBASE-th step, values converted between lane frames when they are shuffled)
+# and reports the largest |score field| it met, so the window claim is checked, not assumed.
+# ---------------------------------------------------------------------------------------------
+LIP = 11 + OPEN + EXT                       # max BLOSUM62 entry (W/W) + open + ext
+
+
+def lexr_params(bits):
+    shift = 2 * bits + 2
+    return {"bits": bits, "shift": shift, "score_bits": 32 - shift, "U": 1 << shift,
+            "cmask": (1 << bits) - 1, "prio_e": 1 << (2 * bits), "prio_f": 2 << (2 * bits),
+            "prio_d": 3 << (2 * bits), "pmask": 3 << (2 * bits)}
+
+
+def lexr_window_ok(bits, K, rebase):
+    """The static guarantee the launcher relies on: LIP * (K/2 + rebase) + slack inside the field."""
+    half = 1 << (32 - (2 * bits + 2) - 1)
+    return LIP * (K // 2 + rebase) + OPEN + LIP + 8 < half
+
+
+def lexr_stats(q, r, G, K, rebase, bits=10, ppos=False):
+    """((matched, columns, score), max |score field| seen) through the rebased LEX word, with the
+    kernel's lane schedule.  Raises AssertionError if any intermediate sum wraps 32 bits."""
+    P = lexr_params(bits)
+    U, SH = P["U"], P["shift"]
+    m, n = len(q), len(r)
+    if n == 0:
+        return (0, m, (0 if m == 0 else -OPEN - (m - 1) * EXT)), 0
+    assert n <= G * K
+    qi = [nw_py.map_char(c) for c in q]
+    ri = [nw_py.map_char(c) for c in r] + [0] * (G * K - n)          # padding columns: code 0
+    rch = list(r.upper()) + ["A"] * (G * K - n)
+    CUr = (EXT - OPEN) * U
+    EDGE0 = (EXT - OPEN) * U
+    NEG0 = EDGE0 + CUr - 4 * U                   # below every opening from a boundary cell
+    lanes = []
+    for l in range(G):
+        lanes.append({"Hp": [EDGE0] * K, "Fp": [NEG0] * K, "diag": 0 if l == 0 else EDGE0,
+                      "outH": 0, "outE": NEG0, "base": 0})
+    worst = 0
+
+    def add(a, b):
+        s = a + b
+        assert wrap32(s) == s, "32-bit wrap in the rebased LEX word"
+        return s
+
+    for s in range(1, m + G):
+        if rebase and s % rebase == 0:
+            for L in lanes:
+                delta = L["Hp"][K // 2] >> SH
+                if delta:
+                    d = delta * U
+                    L["Hp"] = [add(v, -d) for v in L["Hp"]]
+                    L["Fp"] = [add(v, -d) for v in L["Fp"]]
+                    L["diag"] = add(L["diag"], -d)
+                    L["outH"] = add(L["outH"], -d)
+                    L["outE"] = add(L["outE"], -d)
+                    L["base"] += delta
+        shuffled = [(L["outH"], L["outE"], L["base"]) for L in lanes]
+        for l, L in enumerate(lanes):
+            i = s - l
+            inH, inE, inB = (EDGE0, NEG0, 0) if l == 0 else shuffled[l - 1]
+            conv = (inB - L["base"]) * U
+            inH, inE = add(inH, conv), add(inE, conv)
+            if not (1 <= i <= m):
+                continue
+            hl, el, hd = inH, inE, L["diag"]
+            L["diag"] = inH
+            for x in range(K):
+                j = l * K + x
+                sc = nw_py.BLOSUM62[qi[i - 1]][ri[j]]
+                same = q[i - 1].upper() == rch[j]
+                hit = 1 if (same or (ppos and sc > 0)) else 0
+                tw = (sc + 2 * EXT) * U + P["prio_d"] + (1 << bits) + hit
+                f = max(add(L["Hp"][x], CUr), L["Fp"][x]) | P["prio_f"]
+                e = max(add(hl, CUr), el) | P["prio_e"]
+                hdg = add(hd, tw)
+                h = max(hdg, f, e) & ~P["pmask"]
+                if j < n:
+                    worst = max(worst, abs(h >> SH), abs(f >> SH), abs(e >> SH))
+                hd = L["Hp"][x]
+                hl, el = h, e
+                L["Hp"][x], L["Fp"][x] = h, f
+            L["outH"], L["outE"] = hl, el
+    owner = lanes[(n - 1) // K]
+    word = owner["Hp"][(n - 1) % K]
+    score = (word >> SH) + owner["base"] - (m + n) * EXT
+    matched = word & P["cmask"]
+    columns = m + n - ((word >> bits) & P["cmask"])
+    return (matched, columns, score), worst

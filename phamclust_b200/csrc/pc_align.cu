@@ -277,29 +277,39 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 // [-2 open - ext, min(rowmax-sum(q), rowmax-sum(r)) + (m + n) ext], sits inside
 // S bits; cells of padding columns may wrap, nothing flows from them to real cells.
 // ---------------------------------------------------------------------------
-template <int G, int K, int THREADS>
+//
+// REBASE > 0 (the LEXR configs): B = 10-bit counters leave a 10-bit score field, far too narrow
+// for absolute scores -- but not for the values one lane ever holds at one time.  DP values are
+// Lipschitz (neighbouring cells differ by at most PC_NW_LEXR_LIP, E and F sit within open + LIP
+// below their H), so every REBASE row-steps each lane subtracts the score of its centre column
+// from all of its state and adds it to a separate register (`base`); words that cross to the
+// next lane are converted between the two lanes' frames.  All comparisons stay exact because
+// nothing ever leaves the signed window (PC_NW_LEXR_WINDOW_OK, checked at compile time); the
+// absolute score is the field plus `base`.  Cost: 2K + 3 IMADs on the FMA pipe per REBASE * K cells.
+template <int G, int K, int THREADS, int B, int REBASE>
 __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
 {
     extern __shared__ __align__(16) int s_lex[];
     const int lane = threadIdx.x & 31;
     constexpr int open = PC_GAP_OPEN_DEFAULT, ext = PC_GAP_EXTEND_DEFAULT;
-    constexpr int B = PC_NW_LEX_BITS, SH = PC_NW_LEX_SHIFT, S = 32 - SH;
+    constexpr int SH = 2 * B + 2, S = 32 - SH;
     constexpr int U = 1 << SH;                       // one score unit
     constexpr int CMASK = (1 << B) - 1;
     constexpr int PRIO_E = (PC_H_PRIORITY_DIAG_DEL_INS ? 1 : 2) << (2 * B);
     constexpr int PRIO_F = (PC_H_PRIORITY_DIAG_DEL_INS ? 2 : 1) << (2 * B);
     constexpr int PRIO_D = 3 << (2 * B);
     constexpr int PMASK = 3 << (2 * B);
-    constexpr int BIAS = -(1 << (S - 1)) + PC_NW_LEX_FLOOR;   // H^[0][0]
+    constexpr int BIAS = REBASE ? 0 : -(1 << (S - 1)) + PC_NW_LEX_FLOOR;   // H^[0][0]
     constexpr int CU = (ext - open) * U;             // opening a gap, drifted
     constexpr int ORIGIN = BIAS * U;                 // H^[0][0], no diagonal steps yet
     constexpr int EDGE = (BIAS + ext - open) * U;    // every other boundary cell
-    constexpr int NEG = (-(1 << (S - 1)) + 2) * U;   // below every real word (nothing is subtracted from it)
+    // below every real word; rebased: finite, just under any opening from a boundary cell
+    constexpr int NEG = REBASE ? EDGE + CU - 4 * U : (-(1 << (S - 1)) + 2) * U;
     static_assert(PC_GAP_TIE_EXTENDS, "the LEX priorities encode 'ties extend'");
-#ifndef PC_NW_LEX_NO_FMA
+    static_assert(REBASE == 0 || ((REBASE & (REBASE - 1)) == 0 && PC_NW_LEXR_WINDOW_OK(K, REBASE)),
+                  "rebased LEX: the lane's values must stay inside the score field");
     // the diagonal add issues as IMAD on the otherwise idle FMA pipe (measured +3.5 %)
     const int one = a.gap_extend;                    // == 1 at run time, opaque to ptxas
-#endif
 
     // s_lex[(q*24 + r)*32 + lane] = (score + 2 ext, prio 3, one diagonal step, hit)
     for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
             r = a.codes + a.gene_off[rg];
         }
         if (valid && sl == 0 && a.cell_counter)
-            atomicAdd(a.cell_counter + 1, (unsigned long long)m * (unsigned long long)n);
+            atomicAdd(a.cell_counter + (REBASE ? 2 : 1), (unsigned long long)m * (unsigned long long)n);
         const int steps = __reduce_max_sync(FULL, m) + G - 1;
 
         const int col0 = sl * K;
@@ -350,13 +360,35 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
         }
         int diagH = (col0 == 0) ? ORIGIN : EDGE;         // H^[0][col0]
         int outH = 0, outE = NEG;
+        int rb = 0, rbU = 0;                         // REBASE: score taken out of this lane's words
 
         for (int s = 1; s <= steps; ++s) {
+            if (REBASE && (s & (REBASE - 1)) == 0) {
+                // re-centre on the middle column (warp-uniform branch; every lane has its own frame)
+                const int d = Hp[K / 2] & ~(U - 1);      // its score field, in place
+                rb += Hp[K / 2] >> SH;
+                rbU += d;
+                const int nd = -d;
+#pragma unroll
+                for (int x = 0; x < K; ++x) {
+                    Hp[x] = fma_add(Hp[x], one, nd);
+                    Fp[x] = fma_add(Fp[x], one, nd);
+                }
+                diagH = fma_add(diagH, one, nd);
+                outH = fma_add(outH, one, nd);
+                outE = fma_add(outE, one, nd);
+            }
             int inH = __shfl_up_sync(FULL, outH, 1, G);
             int inE = __shfl_up_sync(FULL, outE, 1, G);
             const int i = s - sl;
             const bool active = (i >= 1) && (i <= m);
-            if (sl == 0) {
+            if (REBASE) {
+                int inB = __shfl_up_sync(FULL, rbU, 1, G);
+                if (sl == 0) { inH = EDGE; inE = NEG; inB = 0; }
+                const int conv = inB - rbU;            // sender's frame -> this lane's (mod 2^32)
+                inH += conv;
+                inE += conv;
+            } else if (sl == 0) {
                 inH = EDGE;                              // H^[i][0], i >= 1
                 inE = NEG;
             }
@@ -372,11 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
                     const int tw = trow[rc[x]];
                     const int f = __viaddmax_s32(Hp[x], CU, Fp[x]) | PRIO_F;
                     const int e = __viaddmax_s32(hl, CU, el) | PRIO_E;
-#ifndef PC_NW_LEX_NO_FMA
                     const int hdg = fma_add(hd, one, tw);
-#else
-                    const int hdg = hd + tw;
-#endif
                     const int h = __vimax3_s32(hdg, f, e) & ~PMASK;
                     hd = Hp[x];
                     hl = h;
@@ -402,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
 #pragma unroll
                 for (int x = 0; x < K; ++x)
                     if (x == xs) word = Hp[x];
-                score = (word >> SH) - BIAS - (m + n) * ext;     // undo bias and drift
+                score = (word >> SH) + rb - BIAS - (m + n) * ext;     // undo rebasing, bias and drift
                 matched = word & CMASK;
                 columns = m + n - ((word >> B) & CMASK);
             }
@@ -414,16 +442,17 @@ __global__ void __launch_bounds__(THREADS, 1) nw_lex_kernel(const NwArgs a)
     }
 }
 
-template <int G, int K>
+template <int G, int K, int B = PC_NW_LEX_BITS, int REBASE = 0>
 static int launch_lex(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
 {
     // 3 words of state per column: more warps fit than in the classic kernel, and K goes to 48
     // (registers per thread by ptxas: 57 / 71 / 86 / 101 / 117 / 133 / 148 for K = 8, 12 .. 32)
     // warps per SM sub-partition (16384 registers each): 8 / 7 / 6 / 5 / 4 / 3 / 2
-    constexpr int THREADS = K <= 10 ? 1024 : K <= 12 ? 896 : K <= 14 ? 768 : K <= 18 ? 640 : K <= 28 ? 512
-                          : K <= 38 ? 384 : 256;
+    // (the rebased variant carries two more registers: one block size earlier from K = 28)
+    constexpr int THREADS = K <= 10 ? 1024 : K <= 12 ? 896 : K <= 14 ? 768 : K <= 18 ? 640
+                          : K <= (REBASE ? 26 : 28) ? 512 : K <= 38 ? 384 : 256;
     const size_t smem = (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int);
-    auto kern = nw_lex_kernel<G, K, THREADS>;
+    auto kern = nw_lex_kernel<G, K, THREADS, B, REBASE>;
     PC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
     PC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem));
@@ -527,6 +556,16 @@ int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream)
     const bool repl = ctx->n_codes <= NW_TAB_CODES;
     int G, K;
     pc_nw_cfg(cfg, G, K);
+    if (cfg >= PC_NW_LEXR0) {
+        if (!repl) return pc_fail(ctx, PC_EINVAL, "LEX DP config %d needs the 24-code table", cfg);
+#define PC_LEXR_CASE(K_) case K_: return launch_lex<32, K_, PC_NW_LEXR_BITS, PC_NW_LEXR_REBASE(K_)>(ctx, args, stream);
+        switch (K) {
+        PC_LEXR_CASE(16) PC_LEXR_CASE(18) PC_LEXR_CASE(20) PC_LEXR_CASE(22) PC_LEXR_CASE(24)
+        PC_LEXR_CASE(26) PC_LEXR_CASE(28) PC_LEXR_CASE(30) PC_LEXR_CASE(32)
+        }
+#undef PC_LEXR_CASE
+        return pc_fail(ctx, PC_EINVAL, "no rebased LEX DP kernel for K=%d", K);
+    }
     if (cfg >= PC_NW_LEX0) {
         if (!repl) return pc_fail(ctx, PC_EINVAL, "LEX DP config %d needs the 24-code table", cfg);
         switch (G) {

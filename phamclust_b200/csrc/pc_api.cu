@@ -959,12 +959,12 @@ static bool lex_allowed(const pc_ctx *ctx)
 }
 
 // counters layout: [0..PC_NW_NCFG) work counters, [PC_NW_NCFG] cumulative cells of the classic
-// DP kernel, [PC_NW_NCFG + 1] of the LEX kernel
+// DP kernel, [PC_NW_NCFG + 1] of the LEX kernel, [PC_NW_NCFG + 2] of the rebased LEX kernel
 static int ensure_counters(pc_ctx *ctx)
 {
     if (!ctx->d_counters.p) {
-        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_NCFG + 2)));
-        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_NCFG + 2), ctx->stream));
+        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_NCFG + 3)));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_NCFG + 3), ctx->stream));
     }
     return PC_OK;
 }
@@ -1264,8 +1264,9 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
         if (query_gene[t] < 0 || query_gene[t] >= ctx->n_genes || ref_gene[t] < 0 || ref_gene[t] >= ctx->n_genes)
             return pc_fail(ctx, PC_EINVAL, "task %lld names a gene outside [0,%lld)", (long long)t, (long long)ctx->n_genes);
         const int lq = ctx->h_gene_len[query_gene[t]], lr = ctx->h_gene_len[ref_gene[t]];
-        const bool lex = use_lex && pc_nw_lex_ok(lq, lr, ctx->h_gene_hi[query_gene[t]], ctx->h_gene_hi[ref_gene[t]]);
-        bucket[t] = pc_nw_choose_cfg(lq, lr, lex, ctx->n_codes > 24);
+        const int mode = use_lex ? pc_nw_mode(lq, lr, ctx->h_gene_hi[query_gene[t]], ctx->h_gene_hi[ref_gene[t]], true)
+                                 : PC_NW_MODE_CLASSIC;
+        bucket[t] = pc_nw_choose_cfg(lq, lr, mode, ctx->n_codes > 24);
         bucket_count[bucket[t]]++;
         if (bucket[t] >= PC_NW_MULTI0 && bucket[t] < PC_NW_LEX0)
             max_q_multi = std::max(max_q_multi, ctx->h_gene_len[query_gene[t]]);
@@ -1369,11 +1370,11 @@ extern "C" int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
     PC_ENTER(ctx);
     unsigned long long cells = 0;
     if (ctx->d_counters.p) {
-        unsigned long long both[2] = {0, 0};
+        unsigned long long all[3] = {0, 0, 0};        // classic, LEX, rebased LEX
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PC_CUDA(ctx, cudaMemcpy(both, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG,
-                                sizeof both, cudaMemcpyDeviceToHost));
-        cells = both[0] + both[1];
+        PC_CUDA(ctx, cudaMemcpy(all, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG,
+                                sizeof all, cudaMemcpyDeviceToHost));
+        cells = all[0] + all[1] + all[2];
     }
     if (launches) *launches = ctx->launches;
     if (dp_cells) *dp_cells = (int64_t)cells;
@@ -1393,11 +1394,13 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
     case PC_STAT_OPERAND_COLUMNS: *out = ctx->P_eff; break;
     case PC_STAT_GENES: *out = ctx->n_genes; break;
     case PC_STAT_LEX_ALIGNMENTS: *out = ctx->lex_alignments; break;
-    case PC_STAT_LEX_CELLS: {
+    case PC_STAT_LEX_CELLS:
+    case PC_STAT_LEXR_CELLS: {
         unsigned long long cells = 0;
         if (ctx->d_counters.p) {
             PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG + 1,
+            PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG +
+                                                (which == PC_STAT_LEX_CELLS ? 1 : 2),
                                     sizeof cells, cudaMemcpyDeviceToHost));
         }
         *out = (int64_t)cells;
@@ -1427,8 +1430,9 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
         std::vector<char> reach(PC_NW_NCFG, 0);
         for (int n = 1; n <= 4200; ++n)
             for (int m = 1; m <= 4096; m *= 4) {
-                if (lex && pc_nw_lex_ok(m, n, 0, 0)) reach[pc_nw_choose_cfg(m, n, true, coarse)] = 1;
-                if (!lex || !pc_nw_lex_ok(m, n, 11 * m, 11 * n)) reach[pc_nw_choose_cfg(m, n, false, coarse)] = 1;
+                // cheapest and dearest residues (score bounds 0 and 11 per residue) span the modes
+                reach[pc_nw_choose_cfg(m, n, pc_nw_mode(m, n, 0, 0, lex), coarse)] = 1;
+                reach[pc_nw_choose_cfg(m, n, pc_nw_mode(m, n, 11 * m, 11 * n, lex), coarse)] = 1;
             }
         int64_t count = 0;
         for (char c : reach) count += c;
@@ -1455,7 +1459,7 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8_steps.p, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->d_counters.p) {
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG, 0,
-                                     2 * sizeof(unsigned long long), ctx->stream));
+                                     3 * sizeof(unsigned long long), ctx->stream));
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return PC_OK;

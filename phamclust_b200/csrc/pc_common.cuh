@@ -240,6 +240,9 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 //                        ceil(n / 32K) column chunks, any length
 //   LEX single-pass      c = 56 + g*21 + (K-8)/2,     K in 8..48   (3 registers per column;
 //                        counters inside the score word, for the alignments pc_nw_lex_ok admits)
+//   LEXR (rebased LEX)   c = 140 + (K-16)/2, G = 32,  K in 16..32: 10-bit counters and a 10-bit
+//                        score field that every lane re-centres every few rows (pc_nw_lexr_ok:
+//                        min length < 1024, ref <= 1024 columns, any score range)
 // The chooser only ever picks K >= 16 for G >= 8 (a smaller G covers the same columns with less
 // pipeline fill), and multiples of 4 up to 32 when the 32-code table is in use; only those
 // combinations are instantiated (pc_align.cu).
@@ -247,7 +250,9 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #define PC_NW_LEX_NK 21             // LEX K values per G
 #define PC_NW_MULTI0 (4 * PC_NW_NK) // first multi-chunk config
 #define PC_NW_LEX0 (PC_NW_MULTI0 + 4)
-#define PC_NW_NCFG (PC_NW_LEX0 + 4 * PC_NW_LEX_NK)
+#define PC_NW_LEXR0 (PC_NW_LEX0 + 4 * PC_NW_LEX_NK)
+#define PC_NW_LEXR_NK 9             // G = 32, K = 16, 18 .. 32
+#define PC_NW_NCFG (PC_NW_LEXR0 + PC_NW_LEXR_NK)
 #define PC_NW_KMAX 32
 #define PC_NW_LEX_KMAX 48
 #define PC_NW_COST_PER_CELL 18      // relative cost model (the kernels are ALU-pipe bound)
@@ -260,6 +265,22 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #define PC_NW_LEX_SHIFT (2 * PC_NW_LEX_BITS + 2)
 #define PC_NW_LEX_FLOOR 40          // H^[0][0] sits FLOOR above the most negative score
 #define PC_NW_LEX_ENABLED PC_GAP_TIE_EXTENDS
+// LEXR word: the same layout with 10-bit counters and a 10-bit score field kept centred by
+// rebasing (pc_align.cu).  DP values are Lipschitz -- neighbouring cells differ by at most
+// LIP = max substitution score + open + ext in drifted units -- so a lane that owns K adjacent
+// columns and re-centres on its middle column every R row-steps only ever combines values within
+// LIP * (K/2 + R) + slack of 0: PC_NW_LEXR_WINDOW_OK is the static guarantee (oracle/lex_model.py
+// runs the same schedule on the CPU and reports the largest field value it meets).
+#define PC_NW_LEXR_BITS 10
+#define PC_NW_LEXR_MAXSUB 11        // largest entry of the substitution matrix (W/W)
+#define PC_NW_LEXR_LIP (PC_NW_LEXR_MAXSUB + PC_GAP_OPEN_DEFAULT + PC_GAP_EXTEND_DEFAULT)
+#define PC_NW_LEXR_WINDOW_OK(K, R) \
+    (PC_NW_LEXR_LIP * ((K) / 2 + (R)) + PC_GAP_OPEN_DEFAULT + PC_NW_LEXR_LIP + 8 < (1 << (32 - (2 * PC_NW_LEXR_BITS + 2) - 1)))
+#define PC_NW_LEXR_REBASE(K) ((K) <= 24 ? 8 : 4)   // row-steps between two re-centrings
+// which DP kernel family runs an alignment
+#define PC_NW_MODE_CLASSIC 0
+#define PC_NW_MODE_LEX 1
+#define PC_NW_MODE_LEXR 2
 
 #ifdef __CUDACC__
 #define PC_HD __host__ __device__
@@ -268,7 +289,10 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #endif
 PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
 {
-    if (c >= PC_NW_LEX0) {
+    if (c >= PC_NW_LEXR0) {
+        G = 32;
+        K = 16 + 2 * (c - PC_NW_LEXR0);
+    } else if (c >= PC_NW_LEX0) {
         c -= PC_NW_LEX0;
         G = 4 << (c / PC_NW_LEX_NK);
         K = 8 + 2 * (c % PC_NW_LEX_NK);
@@ -299,14 +323,43 @@ PC_HD inline bool pc_nw_lex_ok(int m, int n, int hi_q, int hi_r)
 #endif
 }
 
+// The rebased LEX kernel takes what the plain one cannot: 10-bit counters (min length < 1024),
+// no condition on the score range, refs of up to 32 lanes x 32 columns.
+PC_HD inline bool pc_nw_lexr_ok(int m, int n)
+{
+#if PC_NW_LEX_ENABLED
+    const int mn = m < n ? m : n;
+    return mn < (1 << PC_NW_LEXR_BITS) && n <= 32 * 32;
+#else
+    return false;
+#endif
+}
+
+// kernel family of an (m-row query, n-column ref) alignment; `allowed`: the 24-code table and
+// the per-gene bounds are available and the caller did not ask for the classic kernel only
+PC_HD inline int pc_nw_mode(int m, int n, int hi_q, int hi_r, bool allowed)
+{
+    if (!allowed) return PC_NW_MODE_CLASSIC;
+    if (n <= 32 * PC_NW_LEX_KMAX && pc_nw_lex_ok(m, n, hi_q, hi_r)) return PC_NW_MODE_LEX;
+    if (pc_nw_lexr_ok(m, n)) return PC_NW_MODE_LEXR;
+    return PC_NW_MODE_CLASSIC;
+}
+
 // cheapest config for an m-row query against n ref columns: pipe slots per
 // alignment ~ chunks x (m + G - 1) row-steps x (K cells + overhead) x G/32 of a warp.
 // Per G the cost of a single-pass config grows with K, so only the smallest K
 // that covers n competes; the LEX grid (when admitted) is cheaper cell for cell
 // and covers everything the classic single-pass grid covers.  coarse: K in
 // multiples of 4 (the kernels of the 32-code table).
-PC_HD inline int pc_nw_choose_cfg(int m, int n, bool lex, bool coarse)
+PC_HD inline int pc_nw_choose_cfg(int m, int n, int mode, bool coarse)
 {
+    if (mode == PC_NW_MODE_LEXR) {
+        int K = (n + 31) / 32;
+        K = (K + 1) & ~1;
+        if (K < 16) K = 16;
+        return PC_NW_LEXR0 + (K - 16) / 2;
+    }
+    const bool lex = mode == PC_NW_MODE_LEX;
     int best = PC_NW_LEX0 - 1;
     long long best_cost = -1;
     const long long per_cell = lex ? PC_NW_LEX_COST_PER_CELL : PC_NW_COST_PER_CELL;

@@ -51,3 +51,37 @@ def test_admission_bound_keeps_every_real_cell_inside_the_score_field():
         assert got == (ident, length, score)
     # counters: min length 511 is the last one admitted (9-bit fields)
     assert lex_model.lex_ok("A" * 511, "G" * 600) and not lex_model.lex_ok("A" * 512, "G" * 600)
+
+
+def test_rebased_lex_word_equals_the_traceback_oracle():
+    """LEXR (nw_lex_kernel<..., B = 10, REBASE>): 10-bit counters next to a 10-bit score field that
+    every lane re-centres every REBASE row-steps.  The model runs the kernel's lane schedule; it
+    must give the oracle's (identical, length, score) and never leave the field's window -- on
+    tie-rich, ordinary and adversarial inputs (all-W sequences climb 11 per residue, the steepest
+    slope the Lipschitz bound PC_NW_LEXR_LIP allows for)."""
+    rng = random.Random(1010)
+    half = 1 << (32 - (2 * 10 + 2) - 1)
+    for G, K, R in ((32, 16, 8), (32, 24, 8), (32, 26, 4), (32, 32, 4)):
+        assert lex_model.lexr_window_ok(10, K, R)
+    assert not lex_model.lexr_window_ok(10, 26, 8) and not lex_model.lexr_window_ok(10, 34, 4)
+    cases = []
+    for t in range(30):
+        alpha = ["AG", "AGS", "WC", "NDB", testdata.AA][t % 5]
+        a = testdata.random_protein(rng, 1, 70, alpha)
+        b = testdata.mutate(rng, a, rng.random() * 0.6, alpha) if t % 2 else testdata.random_protein(rng, 1, 70, alpha)
+        cases.append((a, b, 4, 24, 8))
+        cases.append((a, b, 8, 16, 8))
+    long_a = testdata.random_protein(rng, 640, 640)
+    cases.append((long_a, testdata.mutate(rng, long_a, 0.35), 32, 22, 8))
+    cases += [("W" * 300, "W" * 300, 32, 24, 8), ("W" * 300, "A" * 310, 32, 24, 8), ("W" * 330, "W" * 90, 32, 32, 4),
+              ("WA" * 150, "AW" * 150, 32, 26, 4), ("mktwACDE", "MKTWacde", 4, 16, 8)]
+    for q, r, G, K, R in cases:
+        if len(r) > G * K:
+            continue
+        ident, similar, length, score = nw_c.forward_stats(q, r)
+        got, worst = lex_model.lexr_stats(q, r, G, K, R, bits=10)
+        assert got == (ident, length, score), (q, r, G, K, R)
+        assert worst < half - 8, (worst, G, K, R)
+    got, _ = lex_model.lexr_stats(long_a[:200], long_a[5:190], 32, 16, 8, bits=10, ppos=True)
+    ident, similar, length, score = nw_c.forward_stats(long_a[:200], long_a[5:190])
+    assert got == (ident + similar, length, score)
