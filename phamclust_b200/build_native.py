@@ -26,13 +26,60 @@ def _newest_source_mtime():
     return max(f.stat().st_mtime for f in files)
 
 
+PYPACK_OUT = HERE / "libphamclust_pypack.so"
+BUILD_RECORD = HERE / "build_record.json"
+
+
+def build_pypack(force=False):
+    """gcc: the CPython-API packer (csrc/pc_pypack.c, list[Genome] -> CSR + arena in one walk);
+    resolved against the running interpreter when ctypes.PyDLL loads it."""
+    import sysconfig
+    src = CSRC / "pc_pypack.c"
+    if not force and PYPACK_OUT.exists() and PYPACK_OUT.stat().st_mtime >= src.stat().st_mtime:
+        return PYPACK_OUT, False
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"],
+           "-o", str(PYPACK_OUT), str(src)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("gcc failed building libphamclust_pypack.so")
+    return PYPACK_OUT, True
+
+
 def build(force=False, verbose=False, out=None):
-    """``out``: build a variant (PC_NVCC_EXTRA defines) next to the product library."""
+    """``out``: build a variant (PC_NVCC_EXTRA defines) next to the product library.
+    Writes build_record.json (what was compiled in this call and what was reused, with the
+    sha256 of the product library) so a run can say which build its numbers come from."""
     if out is not None:
         return _compile(pathlib.Path(out), verbose, log=False)
+    _, packed = build_pypack(force)
     if not force and OUT.exists() and OUT.stat().st_mtime >= _newest_source_mtime():
+        _record("reused", packed)
         return OUT
-    return _compile(OUT, verbose, log=True)
+    so = _compile(OUT, verbose, log=True)
+    _record("compiled", packed)
+    return so
+
+
+def library_sha256(path=None):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path or OUT, "rb") as fh:
+        for chunk in iter(lambda: fh.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def _record(mode, pypack_compiled):
+    import json
+    import time
+    try:
+        BUILD_RECORD.write_text(json.dumps({
+            "build_mode": mode, "pypack": "compiled" if pypack_compiled else "reused",
+            "library": OUT.name, "sha256": library_sha256(), "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
+            "nvcc_flags": NVCC_FLAGS}, indent=1) + "\n")
+    except OSError:
+        pass
 
 
 def _compile(OUT, verbose, log):

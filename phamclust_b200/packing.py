@@ -57,14 +57,113 @@ class PackedTable:
         return out
 
 
-def pack_genomes(genomes, with_sequences=True):
-    """list[Genome] (anything with ``.name`` and ``.phams``) -> PackedTable.
+_pypack = None
 
-    One Python-level step per (genome, pham) entry at most: ids come from a list
-    comprehension over the genome's dict, copies / gene lengths from ``map(len, ...)``
-    and the per-entry length sums from one ``np.add.reduceat`` (this pass is on the
-    critical path of ``matrix_de_novo`` and costs more than the GPU work when it is
-    written as a plain double loop)."""
+
+def _pypack_lib():
+    """libphamclust_pypack.so (csrc/pc_pypack.c) through ctypes.PyDLL: the calls keep the GIL
+    and a Python exception set in C is raised here."""
+    global _pypack
+    if _pypack is None:
+        import ctypes
+        import pathlib
+        path = pathlib.Path(__file__).resolve().parent / "libphamclust_pypack.so"
+        if not path.exists():
+            raise ImportError(f"{path} is missing: build it with `python -m phamclust_b200.build_native`")
+        lib = ctypes.PyDLL(str(path))
+        vp = ctypes.c_void_p
+        lib.pcpy_pack.argtypes = [ctypes.py_object, ctypes.py_object, ctypes.c_int, vp]
+        lib.pcpy_pack.restype = vp
+        lib.pcpy_buffers.argtypes = [vp, vp]
+        lib.pcpy_buffers.restype = ctypes.c_int
+        lib.pcpy_free.argtypes = [vp]
+        lib.pcpy_free.restype = None
+        _pypack = lib
+    return _pypack
+
+
+def take_genomes(table, indices):
+    """The genomes ``indices`` (any order, no repeats needed) of ``table`` as their own table, in
+    that order -- random samples for the CPU arm (scripts/benchmark.py:96-100 samples genomes
+    with ``random.sample``, it does not take a prefix)."""
+    idx = np.asarray(indices, dtype=np.int64)
+    lo, hi = table.genome_ptr[idx], table.genome_ptr[idx + 1]
+    counts = hi - lo
+    ptr = np.zeros(len(idx) + 1, dtype=np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    ent = np.repeat(lo - ptr[:-1], counts) + np.arange(int(ptr[-1]))          # source entry ids
+    out = PackedTable([table.names[i] for i in idx.tolist()], table.phams, ptr,
+                      table.pham_id[ent].copy(), table.copies[ent].copy(), table.len_sum[ent].copy(),
+                      meta=dict(table.meta))
+    if table.seq_off is not None:
+        first = np.zeros(len(table.copies) + 1, dtype=np.int64)
+        np.cumsum(table.copies, out=first[1:])
+        c = table.copies[ent].astype(np.int64)
+        g_ptr = np.zeros(len(ent) + 1, dtype=np.int64)
+        np.cumsum(c, out=g_ptr[1:])
+        genes = np.repeat(first[ent] - g_ptr[:-1], c) + np.arange(int(g_ptr[-1]))   # source gene ids
+        glen = table.seq_off[genes + 1] - table.seq_off[genes]
+        out.seq_off = np.zeros(len(genes) + 1, dtype=np.int64)
+        np.cumsum(glen, out=out.seq_off[1:])
+        src = np.repeat(table.seq_off[genes] - out.seq_off[:-1], glen) + np.arange(int(out.seq_off[-1]))
+        out.residues = table.residues[src].copy()
+    return out
+
+
+def pack_genomes(genomes, with_sequences=True):
+    """list[Genome] (anything with ``.name`` and a ``.phams`` dict of lists) -> PackedTable.
+
+    The dicts are walked ONCE, in C (csrc/pc_pypack.c): pham ids in first-seen order, copies,
+    summed translation lengths, and the translations' bytes copied straight from the str objects
+    into the residue arena -- this pass sits on the critical path of ``matrix_de_novo`` and, written
+    in Python, cost more than the GPU work.  Wide (non latin-1) characters raise ValueError."""
+    genomes = genomes if isinstance(genomes, list) else list(genomes)
+    lib = _pypack_lib()
+    names = [genome.name for genome in genomes]
+    sizes = np.zeros(4, dtype=np.int64)
+    vocab = {}
+    owner = _PackOwner(lib, lib.pcpy_pack(genomes, vocab, int(with_sequences), sizes.ctypes.data))
+    _, nnz, n_genes, n_res = (int(v) for v in sizes)
+    ptrs = np.zeros(6, dtype=np.uint64)
+    lib.pcpy_buffers(owner.handle, ptrs.ctypes.data)
+    view = lambda k, count, typestr: np.asarray(_Borrowed(int(ptrs[k]), count, typestr, owner))
+    table = PackedTable(names, list(vocab), view(0, len(genomes) + 1, "<i8"), view(1, nnz, "<i4"),
+                        view(2, nnz, "<u4"), view(3, nnz, "<u4"))
+    if with_sequences:
+        table.seq_off, table.residues = view(4, n_genes + 1, "<i8"), view(5, n_res, "|u1")
+    return table
+
+
+class _PackOwner:
+    """Owns the C buffers of one pcpy_pack; freed when the last array built on them dies."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def __del__(self):
+        if self.handle:
+            self.lib.pcpy_free(self.handle)
+            self.handle = None
+
+
+class _Borrowed:
+    """Array-interface shim: numpy wraps the C buffer in place and keeps this object (and through
+    it the owner of the buffers) alive as the array's base -- the single buffer hand-off."""
+
+    def __init__(self, address, count, typestr, owner):
+        self.owner = owner
+        if count == 0 or not address:
+            self.__array_interface__ = np.empty(0, dtype=np.dtype(typestr)).__array_interface__
+            self._empty = np.empty(0, dtype=np.dtype(typestr))
+            self.__array_interface__ = self._empty.__array_interface__
+        else:
+            self.__array_interface__ = {"data": (address, False), "shape": (count,), "typestr": typestr,
+                                        "version": 3}
+
+
+def pack_genomes_py(genomes, with_sequences=True):
+    """The same packing in plain Python/numpy (the pre-C implementation): kept as the executable
+    specification the C packer is tested against."""
     vocab = {}
     intern_pham = vocab.setdefault
     names, ptr = [], [0]
@@ -92,9 +191,10 @@ def pack_genomes(genomes, with_sequences=True):
                         copies.astype(np.uint32), len_sums.astype(np.uint32))
     if with_sequences:
         table.seq_off = seq_off
-        blob = "".join(seqs).encode("latin-1", errors="replace")
-        if len(blob) != int(table.seq_off[-1]):
-            raise ValueError("translations must be single-byte characters")
+        try:
+            blob = "".join(seqs).encode("latin-1")
+        except UnicodeEncodeError:
+            raise ValueError("translations must be made of single-byte (latin-1) characters") from None
         table.residues = np.frombuffer(blob, dtype=np.uint8).copy()
     return table
 

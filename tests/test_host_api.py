@@ -403,3 +403,68 @@ def test_component_wise_clustering_equals_the_dense_path():
     # unset weights: no component labels, the dense path takes over (and fails like upstream)
     holes = SymMatrix(["a", "b", "c"], is_distance=True)
     assert holes.threshold_components(250001) is None
+
+
+def test_c_packer_equals_python_packer_and_rejects_wide_characters():
+    """pack_genomes walks the Genome dicts once in C (csrc/pc_pypack.c, include/phamclust_pypack.h);
+    the plain-Python packer is its executable specification.  Same arrays, dtypes, vocabulary and
+    names; errors keep the reference's types (genome.py:39-43); a translation with a character
+    outside latin-1 is refused instead of being mangled."""
+    import ctypes
+    import gc
+    from oracle import testdata
+    from phamclust_b200 import packing
+    from phamclust_b200.genome import Genome
+    header = (ROOT / "include" / "phamclust_pypack.h").read_text()
+    declared = set(re.findall(r"^\s*(?:int|void \*|void)\s*\**(pcpy_\w+)\s*\(", header, re.M))
+    lib = ctypes.PyDLL(str(ROOT / "phamclust_b200" / "libphamclust_pypack.so"))
+    assert declared == {"pcpy_pack", "pcpy_buffers", "pcpy_free"} and all(hasattr(lib, n) for n in declared)
+    rows = testdata.genome_rows(seed=3, n_genomes=9, n_phams=14, paralog_p=0.4)
+    genomes = testdata.rows_to_genomes(rows, cls=Genome)
+    genomes.append(Genome("empty"))
+    odd = Genome("odd")
+    odd.phams["zero_copies"] = []
+    odd.add("latin1", "MK\xe9T")
+    genomes.append(odd)
+    for with_sequences in (True, False):
+        a = packing.pack_genomes(genomes, with_sequences)
+        b = packing.pack_genomes_py(genomes, with_sequences)
+        assert a.names == b.names and a.phams == b.phams
+        for key in ("genome_ptr", "pham_id", "copies", "len_sum") + (("seq_off", "residues") if with_sequences else ()):
+            x, y = getattr(a, key), getattr(b, key)
+            assert x.dtype == y.dtype and np.array_equal(x, y), key
+        assert with_sequences or (a.seq_off is None and a.residues is None)
+    keep = packing.pack_genomes(genomes).residues          # outlives its table: the buffers stay alive
+    gc.collect()
+    assert bytes(keep[:3]) == packing.pack_genomes_py(genomes).residues[:3].tobytes()
+    assert packing.pack_genomes([]).n_genomes == 0
+    assert packing.pack_genomes(iter(genomes[:2])).n_genomes == 2
+    wide = Genome("wide")
+    wide.add("p", "MK\u0100")
+    with pytest.raises(ValueError):
+        packing.pack_genomes([wide])
+    with pytest.raises(ValueError):
+        packing.pack_genomes_py([wide])
+    bad = Genome("bad")
+    bad.phams[7] = ["M"]
+    with pytest.raises(TypeError):
+        packing.pack_genomes([bad])
+    bad2 = Genome("bad2")
+    bad2.phams["p"] = [b"M"]
+    with pytest.raises(TypeError):
+        packing.pack_genomes([bad2])
+    with pytest.raises(AttributeError):
+        packing.pack_genomes([object()])
+
+
+def test_take_genomes_is_a_random_access_subset():
+    import random
+    from phamclust_b200 import packing, synthetic
+    table = synthetic.phage_table(120, seed=5)
+    genomes = packing.unpack_genomes(table)
+    idx = random.Random(42).sample(range(120), 37)
+    sub = packing.take_genomes(table, idx)
+    got = packing.unpack_genomes(sub)
+    assert [g.name for g in got] == [genomes[i].name for i in idx]
+    for k, i in enumerate(idx):
+        assert got[k].phams == genomes[i].phams
