@@ -116,6 +116,17 @@ int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
 int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
                       const uint8_t *residues);
 
+/*
+ * Several GPUs: the same arena, but only the genes of the phams that partition
+ * `part` of `n_parts` aligns (the deal of pc_align_accumulate: phams in
+ * descending cost order, snake order over the partitions) are shipped, encoded
+ * and canonicalised -- 1 / n_parts of the bytes and of the host work.  The
+ * partition is fixed until the next load; pc_alignment_identities needs the
+ * whole arena (pc_load_sequences).
+ */
+int pc_load_sequences_part(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
+                           const uint8_t *residues, int part, int n_parts);
+
 /* -------- the path ------------------------------------------------------ */
 /*
  * matrix_de_novo (matrix.py:432-497) for the whole table: writes
@@ -148,6 +159,35 @@ int pc_matrix_rows(pc_ctx *ctx, int metric, int as_distance, int ppos,
  */
 int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
                         uint64_t *acc_dev);
+
+/*
+ * Sparse exchange for several GPUs: instead of a dense
+ * N(N+1)/2 accumulator per rank and an all-reduce, every (pham, genome pair)
+ * unit of partition `part` becomes one 16-byte record
+ *     { index of (i, j) inside the row block of its owner, (matched << 32) | length }
+ * in the bucket of the destination that owns genome row i:
+ * destination d owns rows [row_bounds[d], row_bounds[d+1]), indices count from
+ * idx(row_bounds[d], row_bounds[d]).  records_dev (device, 2 x uint64 per
+ * record, pc_align_units() records at most) is filled bucket after bucket;
+ * dest_counts[d] (host) = records of bucket d.  The caller exchanges the
+ * buckets (ncclSend/Recv all-to-all) and every owner adds what it received with
+ * pc_accumulate_records into the accumulators of ITS rows (n_acc uint64, zeroed
+ * by the caller), which pc_matrix_rows_owned then turns into the row block.
+ * Integer sums: exact, independent of arrival order.
+ */
+int pc_align_units(pc_ctx *ctx, int part, int n_parts, int64_t *n_units);
+int pc_align_contributions(pc_ctx *ctx, int ppos, int part, int n_parts,
+                           int n_dest, const int64_t *row_bounds /* n_dest+1 */,
+                           uint64_t *records_dev, int64_t *dest_counts /* n_dest */);
+int pc_accumulate_records(pc_ctx *ctx, int64_t n_records,
+                          const uint64_t *records_dev, int64_t n_acc,
+                          uint64_t *acc_rows_dev);
+/* pc_matrix_rows with accumulators that hold ONLY rows [row_begin, row_end)
+ * (entry (row_begin, row_begin) first): what a rank owns after the exchange. */
+int pc_matrix_rows_owned(pc_ctx *ctx, int metric, int as_distance, int ppos,
+                         int64_t row_begin, int64_t row_end,
+                         const uint64_t *acc_rows_dev, int32_t *out,
+                         int out_on_device);
 
 /* -------- integer test hooks (bit-exact parity) ------------------------- */
 /*

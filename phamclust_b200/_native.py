@@ -21,7 +21,8 @@ STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h",
 
 EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_stream",
            "pc_set_engine", "pc_set_dp_mode", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",
-           "pc_matrix_rows", "pc_align_accumulate", "pc_numerators",
+           "pc_matrix_rows", "pc_align_accumulate", "pc_numerators", "pc_load_sequences_part", "pc_align_units",
+           "pc_align_contributions", "pc_accumulate_records", "pc_matrix_rows_owned",
            "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters", "pc_stat",
            "pc_write_matrix", "pc_parse_squareform", "pc_scan_tsv", "pc_tsv_intern", "pc_gather_fields",
            "pc_dense_from_micro",
@@ -57,6 +58,11 @@ def load_library():
     lib.pc_matrix_rows.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, i32]
     lib.pc_align_accumulate.argtypes = [vp, i32, i32, i32, vp]
     lib.pc_numerators.argtypes = [vp, i32, i32, vp, vp]
+    lib.pc_load_sequences_part.argtypes = [vp, i64, vp, vp, i32, i32]
+    lib.pc_align_units.argtypes = [vp, i32, i32, vp]
+    lib.pc_align_contributions.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.pc_accumulate_records.argtypes = [vp, i64, vp, i64, vp]
+    lib.pc_matrix_rows_owned.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, i32]
     lib.pc_alignment_identities.argtypes = [vp, i64, vp, vp, vp]
     lib.pc_debug_round6.argtypes = [vp, i64, vp, vp]
     lib.pc_timings.argtypes = [vp, vp, i32]
@@ -155,16 +161,27 @@ class Context:
                                             pid.ctypes.data, cp.ctypes.data, ls.ctypes.data))
         self.n = len(gp) - 1
 
-    def load_sequences(self, table):
+    def load_sequences(self, table, part=0, n_parts=1):
+        """All translations, or (``n_parts`` > 1) only the genes of the phams partition ``part``
+        aligns."""
         so = np.ascontiguousarray(table.seq_off, dtype=np.int64)
         rs = np.ascontiguousarray(table.residues, dtype=np.uint8)
-        self._check(self._lib.pc_load_sequences(self._h, len(so) - 1, so.ctypes.data,
-                                                rs.ctypes.data if rs.size else None))
+        if n_parts > 1:
+            self._check(self._lib.pc_load_sequences_part(self._h, len(so) - 1, so.ctypes.data,
+                                                         rs.ctypes.data if rs.size else None, part, n_parts))
+        else:
+            self._check(self._lib.pc_load_sequences(self._h, len(so) - 1, so.ctypes.data,
+                                                    rs.ctypes.data if rs.size else None))
 
     # ---- the path --------------------------------------------------------------
-    def matrix(self, metric, as_distance=True, ppos=False, out=None):
-        """Packed upper triangle (int32 micro-units) of the whole table, host."""
+    def matrix(self, metric, as_distance=True, ppos=False, out=None, out_device_ptr=None):
+        """Packed upper triangle (int32 micro-units) of the whole table: into a host array
+        (returned), or into caller-owned device memory (``out_device_ptr``)."""
         count = tri_len(self.n)
+        if out_device_ptr is not None:
+            self._check(self._lib.pc_matrix(self._h, _metric_id(metric), int(bool(as_distance)),
+                                            int(bool(ppos)), ctypes.c_void_p(out_device_ptr), 1))
+            return None
         if out is None:
             out = np.empty(count, dtype=np.int32)
         assert out.dtype == np.int32 and out.size == count and out.flags.c_contiguous
@@ -192,6 +209,43 @@ class Context:
     def align_accumulate(self, acc_device_ptr, part=0, n_parts=1, ppos=False):
         self._check(self._lib.pc_align_accumulate(self._h, int(bool(ppos)), part, n_parts,
                                                   ctypes.c_void_p(acc_device_ptr)))
+
+    def align_units(self, part=0, n_parts=1):
+        """Upper bound of the contribution records partition ``part`` emits."""
+        v = ctypes.c_int64()
+        self._check(self._lib.pc_align_units(self._h, part, n_parts, ctypes.byref(v)))
+        return v.value
+
+    def align_contributions(self, records_device_ptr, row_bounds, part=0, n_parts=1, ppos=False):
+        """Align partition ``part`` and write one record per (pham, genome pair) unit into the
+        bucket of the row block (``row_bounds``) that owns it; returns the bucket sizes."""
+        bounds = np.ascontiguousarray(row_bounds, dtype=np.int64)
+        counts = np.zeros(len(bounds) - 1, dtype=np.int64)
+        self._check(self._lib.pc_align_contributions(self._h, int(bool(ppos)), part, n_parts, len(bounds) - 1,
+                                                     bounds.ctypes.data, ctypes.c_void_p(records_device_ptr or 0),
+                                                     counts.ctypes.data))
+        return counts
+
+    def accumulate_records(self, n_records, records_device_ptr, n_acc, acc_device_ptr):
+        self._check(self._lib.pc_accumulate_records(self._h, n_records, ctypes.c_void_p(records_device_ptr or 0),
+                                                    n_acc, ctypes.c_void_p(acc_device_ptr or 0)))
+
+    def matrix_rows_owned(self, metric, as_distance, row_begin, row_end, acc_rows_ptr, out=None,
+                          out_device_ptr=None, ppos=False):
+        """``matrix_rows`` with accumulators that hold only the rows [row_begin, row_end)."""
+        count = tri_len(self.n, row_begin, row_end)
+        if out_device_ptr is not None:
+            self._check(self._lib.pc_matrix_rows_owned(
+                self._h, _metric_id(metric), int(bool(as_distance)), int(bool(ppos)), row_begin,
+                row_end, ctypes.c_void_p(acc_rows_ptr or 0), ctypes.c_void_p(out_device_ptr), 1))
+            return None
+        if out is None:
+            out = np.empty(count, dtype=np.int32)
+        assert out.dtype == np.int32 and out.size == count and out.flags.c_contiguous
+        self._check(self._lib.pc_matrix_rows_owned(
+            self._h, _metric_id(metric), int(bool(as_distance)), int(bool(ppos)), row_begin,
+            row_end, ctypes.c_void_p(acc_rows_ptr or 0), out.ctypes.data, 0))
+        return out
 
     # ---- integer hooks -----------------------------------------------------------
     def numerators(self, metric, ppos=False):

@@ -202,6 +202,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
                       &ctx->d_acc, &ctx->d_out};
     for (DevBuf *b : bufs) devbuf_free(*b);
     for (DevBuf &b : ctx->d_dedup) devbuf_free(b);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     free_plan(ctx->plan);
     for (auto &t : ctx->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
@@ -443,6 +444,7 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
 
     ctx->N = n_genomes; ctx->P = n_phams; ctx->nnz = nnz;
     ctx->h_pham_members.clear();
+    ctx->deal_parts = -1;
     ctx->bits_ready = false;
     ctx->max_copies = max_copies; ctx->max_len_sum = max_len;
     ctx->n_genes_total = gene_cursor;
@@ -509,12 +511,18 @@ static void build_subtab(const pc_ctx *ctx, int ppos, std::vector<int2> &tab)
         }
 }
 
-extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
-                                 const uint8_t *residues)
+static void deal_phams(pc_ctx *ctx, int n_parts);
+
+// part / n_parts: ship, encode and canonicalise only the genes of the phams partition `part`
+// aligns (deal_phams); n_parts == 1 ships everything straight from the caller's arena.
+static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
+                               const uint8_t *residues, int my_part, int n_parts)
 {
-    PC_ENTER(ctx);
     HostTimer host_timer(ctx, PC_T_HOST_SEQS);
     if (!ctx->have_table) return pc_fail(ctx, PC_ESTATE, "pc_load_sequences needs pc_load_table first");
+    if (n_parts < 1 || my_part < 0 || my_part >= n_parts)
+        return pc_fail(ctx, PC_EINVAL, "pc_load_sequences_part: bad partition %d/%d", my_part, n_parts);
+    const bool partial = n_parts > 1;
     if (n_genes != ctx->n_genes_total)
         return pc_fail(ctx, PC_EINVAL, "got %lld genes but the table's copies sum to %lld",
                        (long long)n_genes, (long long)ctx->n_genes_total);
@@ -524,11 +532,24 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     if (total > 0 && !residues) return pc_fail(ctx, PC_EINVAL, "residues is NULL");
 
     dbg_mark("seqs: enter");
-    // the residues go first: the copy runs while the host validates the offsets
-    PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
-    PC_TRY(upload(ctx, ctx->d_raw, residues, (size_t)total));
-    PC_TRY(upload(ctx, ctx->d_raw_off, seq_off, (size_t)n_genes + 1));
-    PC_TRY(pc_stage_end(ctx));
+    // which genes this rank needs: those of the entries whose pham it aligns
+    std::vector<uint8_t> owned;              // per gene (partial loads only)
+    if (partial) {
+        deal_phams(ctx, n_parts);
+        owned.assign((size_t)n_genes, 0);
+        const int To = host_threads(ctx->nnz);
+        run_threads(To, [&](int t) {
+            for (int64_t e = ctx->nnz * t / To; e < ctx->nnz * (t + 1) / To; ++e)
+                if (ctx->h_pham_part[ctx->h_pham_id[e]] == my_part)
+                    for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g) owned[g] = 1;
+        });
+    } else {
+        // the residues go first: the copy runs while the host validates the offsets
+        PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+        PC_TRY(upload(ctx, ctx->d_raw, residues, (size_t)total));
+        PC_TRY(upload(ctx, ctx->d_raw_off, seq_off, (size_t)n_genes + 1));
+        PC_TRY(pc_stage_end(ctx));
+    }
 
     // gene lengths and their 16 B aligned offsets in the code arena, on a few host threads
     std::vector<int32_t> &gene_len = ctx->h_gene_len;
@@ -538,7 +559,7 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     gene_off.resize(n_genes + 1);
     const int T = host_threads(n_genes);
     struct SeqPart {
-        int64_t padded = 0, err_at = INT64_MAX;
+        int64_t padded = 0, err_at = INT64_MAX, raw = 0;
         int32_t max_len = 0;
         std::string err;
     };
@@ -562,8 +583,10 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
                 return;
             }
             gene_len[g] = (int32_t)len;
+            if (partial && !owned[g]) continue;
             me.max_len = std::max(me.max_len, (int32_t)len);
             me.padded += (len + 15) / 16 * 16;
+            me.raw += len;
         }
     });
     int64_t cursor = 0;
@@ -586,10 +609,37 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
         // (metrics.py:136-147 sums them)
         std::vector<SeqPart> chk(T);
         auto elo_of = [&](int t) { return ctx->nnz * t / T; };
+        // partial loads: the owned residues are gathered into page-locked staging (1 / n_parts of
+        // the arena), the device sees length 0 for every other gene
+        std::vector<int64_t> raw_base(T + 1, 0);
+        for (int t = 0; t < T; ++t) raw_base[t + 1] = raw_base[t] + part[t].raw;
+        if (partial) {
+            const size_t need = (size_t)raw_base[T] + 16;
+            if (ctx->h_stage_cap < need) {
+                if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+                ctx->h_stage = nullptr;
+                ctx->h_stage_cap = 0;
+                const size_t cap = need + need / 4;
+                if (cudaHostAlloc(&ctx->h_stage, cap, cudaHostAllocDefault) != cudaSuccess) {
+                    cudaGetLastError();
+                    return pc_fail(ctx, PC_ENOMEM, "no page-locked staging for %zu residue bytes", cap);
+                }
+                ctx->h_stage_cap = cap;
+            }
+            ctx->h_gene_len_dev.assign((size_t)n_genes, 0);
+            ctx->h_raw_off.assign((size_t)n_genes + 1, 0);
+        }
         run_threads(T, [&](int t) {
-            int64_t at = base[t];
+            int64_t at = base[t], raw_at = raw_base[t];
             for (int64_t g = lo_of(t); g < lo_of(t + 1); ++g) {
                 gene_off[g] = at;
+                if (partial) {
+                    ctx->h_raw_off[g] = raw_at;
+                    if (!owned[g]) continue;
+                    ctx->h_gene_len_dev[g] = gene_len[g];
+                    memcpy((uint8_t *)ctx->h_stage + raw_at, residues + seq_off[g], (size_t)gene_len[g]);
+                    raw_at += gene_len[g];
+                }
                 at += ((int64_t)gene_len[g] + 15) / 16 * 16;
             }
             for (int64_t e = elo_of(t); e < elo_of(t + 1); ++e) {
@@ -612,7 +662,15 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
             cudaStreamSynchronize(ctx->stream);
             return pc_fail(ctx, PC_EINVAL, "%s", bad->err.c_str());
         }
+        if (partial) {
+            ctx->h_raw_off[n_genes] = raw_base[T];
+            PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+            PC_TRY(upload(ctx, ctx->d_raw, (const uint8_t *)ctx->h_stage, (size_t)raw_base[T]));
+            PC_TRY(upload(ctx, ctx->d_raw_off, ctx->h_raw_off.data(), (size_t)n_genes + 1));
+            PC_TRY(pc_stage_end(ctx));
+        }
     }
+    const int64_t raw_total = partial ? ctx->h_raw_off[n_genes] : total;
 
     dbg_mark("seqs: lengths validated");
     // residue codes: one per distinct character after case folding (U5); the
@@ -623,9 +681,9 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     {
         PC_TRY(devbuf_reserve(ctx, ctx->d_lut, 256 * sizeof(unsigned int)));
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_lut.p, 0, 256 * sizeof(unsigned int), ctx->stream));
-        if (total > 0) {
-            const int grid = (int)std::min<int64_t>((total / 16 + 255) / 256 + 1, (int64_t)ctx->sm_count * 8);
-            byte_presence_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_raw.as<uint8_t>(), total,
+        if (raw_total > 0) {
+            const int grid = (int)std::min<int64_t>((raw_total / 16 + 255) / 256 + 1, (int64_t)ctx->sm_count * 8);
+            byte_presence_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_raw.as<uint8_t>(), raw_total,
                                                                 ctx->d_lut.as<unsigned int>());
             PC_CUDA(ctx, cudaGetLastError());
             ctx->launches++;
@@ -677,7 +735,8 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     do {
         if ((rc = pc_stage_begin(ctx, PC_T_H2D))) break;
         if ((rc = upload(ctx, ctx->d_gene_off, gene_off.data(), (size_t)n_genes + 1))) break;
-        if ((rc = upload(ctx, ctx->d_gene_len, ctx->h_gene_len.data(), (size_t)n_genes))) break;
+        if ((rc = upload(ctx, ctx->d_gene_len, partial ? ctx->h_gene_len_dev.data() : ctx->h_gene_len.data(),
+                         (size_t)n_genes))) break;
         if ((rc = upload(ctx, d_lut, lut, 256))) break;
         for (int ppos = 0; ppos < 2 && rc == PC_OK; ++ppos) {
             build_subtab(ctx, ppos, tabs[ppos]);
@@ -721,8 +780,24 @@ extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *se
     PC_TRY(pc_stage_end(ctx));
     dbg_mark("seqs: canonical ids");
     ctx->plan.part = ctx->plan.n_parts = -1;
+    ctx->seq_part = my_part;
+    ctx->seq_parts = n_parts;
     ctx->have_seqs = true;
     return PC_OK;
+}
+
+extern "C" int pc_load_sequences(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
+                                 const uint8_t *residues)
+{
+    PC_ENTER(ctx);
+    return load_sequences_impl(ctx, n_genes, seq_off, residues, 0, 1);
+}
+
+extern "C" int pc_load_sequences_part(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_off,
+                                      const uint8_t *residues, int part, int n_parts)
+{
+    PC_ENTER(ctx);
+    return load_sequences_impl(ctx, n_genes, seq_off, residues, part, n_parts);
 }
 
 // ---------------------------------------------------------------------------
@@ -818,41 +893,53 @@ static int contract_rows(pc_ctx *ctx, int metric, int as_distance, int raw, int6
 // ---------------------------------------------------------------------------
 // alignment planning (host) -- which member pairs exist, in which order
 // ---------------------------------------------------------------------------
-static int build_plan(pc_ctx *ctx, int part, int n_parts)
+// CSC member lists (entries grouped by pham, ascending genome order) by a stable counting sort
+// over T entry ranges; built on demand, dropped by pc_load_table.
+static void ensure_pham_members(pc_ctx *ctx)
 {
-    AlignPlan &pl = ctx->plan;
-    if (pl.part == part && pl.n_parts == n_parts) return PC_OK;
-    HostTimer host_timer(ctx, PC_T_HOST_PLAN);
+    if (ctx->h_pham_members.size() == (size_t)ctx->nnz) return;
     const int T = host_threads(ctx->nnz);
     const int64_t P = ctx->P;
     auto entries_of = [&](int t) { return ctx->nnz * t / T; };
     auto phams_of = [&](int t) { return P * t / T; };
-    if (ctx->h_pham_members.size() != (size_t)ctx->nnz) {
-        // CSC by a stable counting sort over T entry ranges: members of a pham in ascending
-        // genome order.  cnt[t][p] = entries of pham p in range t, then their rank offset.
-        ctx->h_pham_members.resize(ctx->nnz);
-        std::vector<std::vector<int32_t>> cnt(T);
-        run_threads(T, [&](int t) {
-            cnt[t].assign(P, 0);
-            for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) cnt[t][ctx->h_pham_id[k]]++;
-        });
-        run_threads(T, [&](int t) {
-            for (int64_t p = phams_of(t); p < phams_of(t + 1); ++p) {
-                int32_t run = 0;
-                for (int u = 0; u < T; ++u) {
-                    const int32_t c = cnt[u][p];
-                    cnt[u][p] = run;
-                    run += c;
-                }
+    // cnt[t][p] = entries of pham p in range t, then their rank offset
+    ctx->h_pham_members.resize(ctx->nnz);
+    std::vector<std::vector<int32_t>> cnt(T);
+    run_threads(T, [&](int t) {
+        cnt[t].assign(P, 0);
+        for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) cnt[t][ctx->h_pham_id[k]]++;
+    });
+    run_threads(T, [&](int t) {
+        for (int64_t p = phams_of(t); p < phams_of(t + 1); ++p) {
+            int32_t run = 0;
+            for (int u = 0; u < T; ++u) {
+                const int32_t c = cnt[u][p];
+                cnt[u][p] = run;
+                run += c;
             }
-        });
-        run_threads(T, [&](int t) {
-            for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) {
-                const int32_t p = ctx->h_pham_id[k];
-                ctx->h_pham_members[ctx->h_pham_ptr[p] + cnt[t][p]++] = k;
-            }
-        });
-    }
+        }
+    });
+    run_threads(T, [&](int t) {
+        for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) {
+            const int32_t p = ctx->h_pham_id[k];
+            ctx->h_pham_members[ctx->h_pham_ptr[p] + cnt[t][p]++] = k;
+        }
+    });
+}
+
+// Which partition aligns which pham: phams held by >= 2 genomes in descending cost order
+// (LPT; cost ~ (summed translation length of the members)^2), dealt in snake order
+// (0..n-1, n-1..0, ...) -- plain round-robin would hand partition 0 the largest pham of every
+// lap.  A function of the TABLE only, so pc_load_sequences_part can decide which genes a rank
+// needs before any plan exists.  ctx->h_deal_order: the phams in deal order; ctx->h_pham_part[p]:
+// owner of pham p or -1.
+static void deal_phams(pc_ctx *ctx, int n_parts)
+{
+    if (ctx->deal_parts == n_parts && ctx->h_pham_part.size() == (size_t)std::max<int64_t>(ctx->P, 1)) return;
+    ensure_pham_members(ctx);
+    const int T = host_threads(ctx->nnz);
+    const int64_t P = ctx->P;
+    auto phams_of = [&](int t) { return P * t / T; };
     struct PhamInfo { int64_t pham; double cost; };
     std::vector<PhamInfo> infos;
     {
@@ -871,7 +958,6 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
         infos.reserve(n);
         for (auto &v : local) infos.insert(infos.end(), v.begin(), v.end());
     }
-    // descending cost (LPT), dealt round-robin over the partitions
     auto by_cost = [](const PhamInfo &x, const PhamInfo &y) {
         if (x.cost != y.cost) return x.cost > y.cost;
         return x.pham < y.pham;
@@ -890,13 +976,30 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
             });
         }
     }
-    // this partition's phams, in snake order (0..P-1, P-1..0, ...): plain round-robin would hand
-    // partition 0 the largest pham of every group of P
-    std::vector<int64_t> mine;
+    ctx->h_pham_part.assign(std::max<int64_t>(P, 1), -1);
+    ctx->h_deal_order.resize(infos.size());
     for (size_t pos = 0; pos < infos.size(); ++pos) {
         const size_t lap = pos / (size_t)n_parts, in_lap = pos % (size_t)n_parts;
-        if ((int)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap) == part) mine.push_back(infos[pos].pham);
+        ctx->h_deal_order[pos] = infos[pos].pham;
+        ctx->h_pham_part[infos[pos].pham] = (int32_t)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap);
     }
+    ctx->deal_parts = n_parts;
+}
+
+static int build_plan(pc_ctx *ctx, int part, int n_parts)
+{
+    AlignPlan &pl = ctx->plan;
+    if (pl.part == part && pl.n_parts == n_parts) return PC_OK;
+    if (ctx->seq_parts > 1 && (ctx->seq_parts != n_parts || ctx->seq_part != part))
+        return pc_fail(ctx, PC_ESTATE, "sequences were loaded for partition %d/%d, the plan asks for %d/%d",
+                       ctx->seq_part, ctx->seq_parts, part, n_parts);
+    HostTimer host_timer(ctx, PC_T_HOST_PLAN);
+    const int T = host_threads(ctx->nnz);
+    deal_phams(ctx, n_parts);
+    // this partition's phams, in deal (descending cost) order
+    std::vector<int64_t> mine;
+    for (const int64_t p : ctx->h_deal_order)
+        if (ctx->h_pham_part[p] == part) mine.push_back(p);
     std::vector<int64_t> ph_mem_off(mine.size() + 1, 0), ph_unit_off(mine.size() + 1, 0);
     for (size_t x = 0; x < mine.size(); ++x) {
         const int64_t m = ctx->h_pham_ptr[mine[x] + 1] - ctx->h_pham_ptr[mine[x]];
@@ -980,15 +1083,17 @@ static int ensure_spill(pc_ctx *ctx, int max_qlen, NwArgs &a, int cfg)
     return PC_OK;
 }
 
-extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
-                                   uint64_t *acc_dev)
+// Plan partition part/n_parts, bucket its units by DP config and run every alignment: on return
+// `u` describes the units and d_hitlen holds (matched << 16 | columns) per task, ready for the
+// best-match pass (dense gather or contribution records).  *empty: nothing to align.
+static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u, bool *empty)
 {
-    PC_ENTER(ctx);
     if (!ctx->have_seqs) return pc_fail(ctx, PC_ESTATE, "aai/peq need pc_load_sequences first");
-    if (n_parts < 1 || part < 0 || part >= n_parts || !acc_dev)
-        return pc_fail(ctx, PC_EINVAL, "pc_align_accumulate: bad partition %d/%d", part, n_parts);
+    if (n_parts < 1 || part < 0 || part >= n_parts)
+        return pc_fail(ctx, PC_EINVAL, "alignment partition %d/%d does not exist", part, n_parts);
     PC_TRY(build_plan(ctx, part, n_parts));
     AlignPlan &pl = ctx->plan;
+    *empty = pl.n_tasks == 0;
     if (pl.n_tasks == 0) return PC_OK;
     if (pl.n_tasks >= (1ll << 40)) return pc_fail(ctx, PC_EINVAL, "too many alignments");
     PC_TRY(devbuf_reserve(ctx, ctx->d_task_q, (size_t)pl.n_tasks * sizeof(int32_t)));
@@ -997,7 +1102,6 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     PC_TRY(ensure_counters(ctx));
     PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_NCFG, ctx->stream));
 
-    UnitArgs u;
     u.ph_mem_off = pl.ph_mem_off.as<int64_t>();
     u.ph_unit_off = pl.ph_unit_off.as<int64_t>();
     u.n_ph = pl.n_ph;
@@ -1081,10 +1185,81 @@ extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
     for (int c = 0; c < PC_NW_NCFG; ++c) ctx->alignments += (int64_t)cfg_info[c];   // distinct sequence pairs
     for (int c = PC_NW_LEX0; c < PC_NW_NCFG; ++c) ctx->lex_alignments += (int64_t)cfg_info[c];
     ctx->logical_alignments += pl.n_tasks;
+    return PC_OK;
+}
 
+extern "C" int pc_align_accumulate(pc_ctx *ctx, int ppos, int part, int n_parts,
+                                   uint64_t *acc_dev)
+{
+    PC_ENTER(ctx);
+    if (!acc_dev) return pc_fail(ctx, PC_EINVAL, "pc_align_accumulate: acc_dev is NULL");
+    UnitArgs u;
+    bool empty = false;
+    PC_TRY(align_tasks(ctx, ppos, part, n_parts, u, &empty));
+    if (empty) return PC_OK;
     PC_TRY(pc_stage_begin(ctx, PC_T_GATHER));
     PC_TRY(pc_launch_gather_units(ctx, u, ctx->d_hitlen.as<uint32_t>(),
                                   reinterpret_cast<unsigned long long *>(acc_dev)));
+    PC_TRY(pc_stage_end(ctx));
+    return maybe_collect(ctx);
+}
+
+extern "C" int pc_align_units(pc_ctx *ctx, int part, int n_parts, int64_t *n_units)
+{
+    PC_ENTER(ctx);
+    if (!n_units) return pc_fail(ctx, PC_EINVAL, "pc_align_units: n_units is NULL");
+    if (!ctx->have_seqs) return pc_fail(ctx, PC_ESTATE, "aai/peq need pc_load_sequences first");
+    if (n_parts < 1 || part < 0 || part >= n_parts)
+        return pc_fail(ctx, PC_EINVAL, "alignment partition %d/%d does not exist", part, n_parts);
+    PC_TRY(build_plan(ctx, part, n_parts));
+    *n_units = ctx->plan.n_units;
+    return PC_OK;
+}
+
+extern "C" int pc_align_contributions(pc_ctx *ctx, int ppos, int part, int n_parts, int n_dest,
+                                      const int64_t *row_bounds, uint64_t *records_dev,
+                                      int64_t *dest_counts)
+{
+    PC_ENTER(ctx);
+    if (n_dest < 1 || n_dest > PC_MAX_DEST || !row_bounds || !dest_counts)
+        return pc_fail(ctx, PC_EINVAL, "pc_align_contributions: 1..%d destination row blocks", PC_MAX_DEST);
+    if (row_bounds[0] != 0 || row_bounds[n_dest] != ctx->N)
+        return pc_fail(ctx, PC_EINVAL, "pc_align_contributions: row_bounds must run from 0 to n_genomes");
+    for (int d = 0; d < n_dest; ++d) {
+        dest_counts[d] = 0;
+        if (row_bounds[d] > row_bounds[d + 1]) return pc_fail(ctx, PC_EINVAL, "row_bounds is not monotone");
+    }
+    UnitArgs u;
+    bool empty = false;
+    PC_TRY(align_tasks(ctx, ppos, part, n_parts, u, &empty));
+    if (empty || ctx->plan.n_units == 0) return PC_OK;
+    if (!records_dev) return pc_fail(ctx, PC_EINVAL, "pc_align_contributions: records_dev is NULL");
+    DestArgs d;
+    d.n_dest = n_dest;
+    for (int k = 0; k <= n_dest; ++k) d.bounds[k] = row_bounds[k];
+    PC_TRY(devbuf_reserve(ctx, ctx->d_dest, sizeof(unsigned long long) * 2 * PC_MAX_DEST));
+    unsigned long long counts[PC_MAX_DEST];
+    PC_TRY(pc_stage_begin(ctx, PC_T_GATHER));
+    PC_TRY(pc_launch_emit_units(ctx, u, ctx->d_hitlen.as<uint32_t>(), d, ctx->d_dest.as<unsigned long long>(),
+                                reinterpret_cast<unsigned long long *>(records_dev)));
+    PC_TRY(pc_stage_end(ctx));
+    PC_CUDA(ctx, cudaMemcpyAsync(counts, ctx->d_dest.p, sizeof(unsigned long long) * n_dest,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n_dest; ++k) dest_counts[k] = (int64_t)counts[k];
+    return maybe_collect(ctx);
+}
+
+extern "C" int pc_accumulate_records(pc_ctx *ctx, int64_t n_records, const uint64_t *records_dev,
+                                     int64_t n_acc, uint64_t *acc_rows_dev)
+{
+    PC_ENTER(ctx);
+    if (n_records < 0 || n_acc < 0 || (n_records > 0 && (!records_dev || !acc_rows_dev)))
+        return pc_fail(ctx, PC_EINVAL, "pc_accumulate_records: bad arguments");
+    if (n_records == 0) return PC_OK;
+    PC_TRY(pc_stage_begin(ctx, PC_T_GATHER));
+    PC_TRY(pc_launch_accumulate_records(ctx, n_records, reinterpret_cast<const unsigned long long *>(records_dev),
+                                        n_acc, reinterpret_cast<unsigned long long *>(acc_rows_dev)));
     PC_TRY(pc_stage_end(ctx));
     return maybe_collect(ctx);
 }
@@ -1192,6 +1367,20 @@ extern "C" int pc_matrix_rows(pc_ctx *ctx, int metric, int as_distance, int ppos
     return maybe_collect(ctx);
 }
 
+extern "C" int pc_matrix_rows_owned(pc_ctx *ctx, int metric, int as_distance, int ppos,
+                                    int64_t row_begin, int64_t row_end, const uint64_t *acc_rows_dev,
+                                    int32_t *out, int out_on_device)
+{
+    PC_ENTER(ctx);
+    if (row_begin < 0 || row_end > ctx->N || row_begin > row_end)
+        return pc_fail(ctx, PC_EINVAL, "bad row range [%lld,%lld)", (long long)row_begin, (long long)row_end);
+    // the kernels index the accumulators by the packed-triangle index of the pair: hand them the
+    // address entry (0, 0) WOULD have if the owned slice were part of a whole triangle (only the
+    // entries of rows [row_begin, row_end) are ever read)
+    const uint64_t *base = acc_rows_dev ? acc_rows_dev - pc_tri_index(ctx->N, row_begin, row_begin) : nullptr;
+    return pc_matrix_rows(ctx, metric, as_distance, ppos, row_begin, row_end, base, out, out_on_device);
+}
+
 static int full_accumulate(pc_ctx *ctx, int ppos)
 {
     const size_t bytes = (size_t)slice_len(ctx, 0, ctx->N) * sizeof(uint64_t);
@@ -1246,6 +1435,8 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
 {
     PC_ENTER(ctx);
     if (!ctx->have_seqs) return pc_fail(ctx, PC_ESTATE, "pc_alignment_identities needs pc_load_sequences first");
+    if (ctx->seq_parts > 1)
+        return pc_fail(ctx, PC_ESTATE, "pc_alignment_identities needs ALL genes (pc_load_sequences, not _part)");
     if (n_tasks < 0 || (n_tasks > 0 && (!query_gene || !ref_gene || !out)))
         return pc_fail(ctx, PC_EINVAL, "pc_alignment_identities: bad arguments");
     if (n_tasks == 0) return PC_OK;

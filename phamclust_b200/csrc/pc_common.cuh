@@ -107,6 +107,13 @@ struct UnitArgs {
     uint64_t ht_mask;                 // capacity - 1 (power of two)
 };
 
+// destination row blocks of the contribution records (one per rank of the node, at most)
+#define PC_MAX_DEST 64
+struct DestArgs {
+    int n_dest;
+    int64_t bounds[PC_MAX_DEST + 1];   // block d owns genome rows [bounds[d], bounds[d+1])
+};
+
 // ---------------------------------------------------------------------------
 // the context
 // ---------------------------------------------------------------------------
@@ -150,6 +157,14 @@ struct pc_ctx {
     std::vector<std::vector<int32_t>> h_stamp;   // per host thread: epoch + genome that last listed the pham
     int32_t stamp_epoch = 0;
     std::vector<int64_t> h_pham_members;  // entry ids grouped by pham, genome ascending
+    std::vector<int32_t> h_pham_part;     // pham -> partition that aligns it (-1: held by < 2 genomes)
+    std::vector<int64_t> h_deal_order;    // phams held by >= 2 genomes, descending cost
+    int deal_parts = -1;                  // n_parts the deal above was made for
+    int seq_part = 0, seq_parts = 1;      // which partition's genes pc_load_sequences[_part] shipped
+    void *h_stage = nullptr;              // page-locked staging of the owned residues (partial loads)
+    size_t h_stage_cap = 0;
+    std::vector<int32_t> h_gene_len_dev;  // partial loads: gene lengths as the device sees them (0 = not shipped)
+    std::vector<int64_t> h_raw_off;       // partial loads: offsets into the staged residues
     uint32_t max_copies = 0, max_len_sum = 0;
     int64_t n_genes_total = 0;
 
@@ -192,6 +207,7 @@ struct pc_ctx {
     AlignPlan plan;
     DevBuf d_task_q, d_task_r, d_hitlen, d_score, d_spill, d_counters, d_perm;
     DevBuf d_acc;                                  // uint64 accumulators (single-GPU path)
+    DevBuf d_dest;                                 // [2][PC_MAX_DEST] record counts / write cursors per destination
     DevBuf d_out;                                  // int32 result staging
 
     // ---- measurement ----
@@ -221,6 +237,10 @@ int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u);
 int pc_launch_scatter_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r);
 int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen,
                            unsigned long long *acc);
+int pc_launch_emit_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen, const DestArgs &d,
+                         unsigned long long *dest_counts /*[2][PC_MAX_DEST]*/, unsigned long long *records);
+int pc_launch_accumulate_records(pc_ctx *ctx, int64_t n_records, const unsigned long long *records,
+                                 int64_t n_acc, unsigned long long *acc);
 int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
                            int64_t row_begin, int64_t row_end,
                            const unsigned long long *acc, int32_t *out,

@@ -269,9 +269,34 @@ __global__ void finalize_tasks_kernel(const UnitArgs u, int32_t *__restrict__ ta
 
 // For each anchor gene keep the candidate with the best matched/length ratio,
 // ties -> the LAST candidate (sorted(...)[-1] on a stable sort, metrics.py:223);
-// ratios are compared exactly by cross-multiplication.  The unit's sums go to
-// acc[idx(ga, gb)] as (matched << 32) | length with ONE 64-bit integer atomic:
-// exact and order independent.
+// ratios are compared exactly by cross-multiplication.  Returns the unit's sums
+// packed as (matched << 32) | length (0: nothing to add).
+__device__ __forceinline__ unsigned long long unit_best_matches(const UnitArgs &u, const uint32_t *__restrict__ hitlen,
+                                                                const UnitShape &s)
+{
+    unsigned long long sum_hit = 0, sum_len = 0;
+    for (int x = 0; x < s.n_anchor; ++x) {
+        unsigned long long best_hit = 0, best_len = 0;
+        bool have = false;
+        const uint32_t cq = (uint32_t)u.canon[s.anchor0 + x];
+        for (int y = 0; y < s.n_other; ++y) {
+            const uint32_t cr = (uint32_t)u.canon[s.other0 + y];
+            const uint64_t slot = ht_find(u.ht_keys, u.ht_mask, ((uint64_t)cq << 32) | cr);
+            const uint32_t v = hitlen[u.ht_vals[slot]];
+            const unsigned long long hit = v >> 16, len = v & 0xffffu;
+            if (len == 0) continue;           // undefined upstream (0-length alignment)
+            if (!have || hit * best_len >= best_hit * len) {
+                best_hit = hit; best_len = len; have = true;
+            }
+        }
+        sum_hit += best_hit;
+        sum_len += best_len;
+    }
+    return sum_len ? ((sum_hit << 32) | sum_len) : 0ull;
+}
+
+// Single GPU / dense exchange: the unit's sums go to acc[idx(ga, gb)] with ONE 64-bit integer
+// atomic: exact and order independent.
 __global__ void gather_units_kernel(const UnitArgs u, const uint32_t *__restrict__ hitlen,
                                     unsigned long long *__restrict__ acc)
 {
@@ -279,28 +304,119 @@ __global__ void gather_units_kernel(const UnitArgs u, const uint32_t *__restrict
     for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
          unit < u.n_units; unit += stride) {
         const Unit t = decode_unit(u, unit);
-        const UnitShape s = unit_shape(t);
-        unsigned long long sum_hit = 0, sum_len = 0;
-        for (int x = 0; x < s.n_anchor; ++x) {
-            unsigned long long best_hit = 0, best_len = 0;
-            bool have = false;
-            const uint32_t cq = (uint32_t)u.canon[s.anchor0 + x];
-            for (int y = 0; y < s.n_other; ++y) {
-                const uint32_t cr = (uint32_t)u.canon[s.other0 + y];
-                const uint64_t slot = ht_find(u.ht_keys, u.ht_mask, ((uint64_t)cq << 32) | cr);
-                const uint32_t v = hitlen[u.ht_vals[slot]];
-                const unsigned long long hit = v >> 16, len = v & 0xffffu;
-                if (len == 0) continue;           // undefined upstream (0-length alignment)
-                if (!have || hit * best_len >= best_hit * len) {
-                    best_hit = hit; best_len = len; have = true;
-                }
-            }
-            sum_hit += best_hit;
-            sum_len += best_len;
-        }
-        if (sum_len)
-            atomicAdd(acc + pc_tri_index(u.n_genomes, t.ga, t.gb), (sum_hit << 32) | sum_len);
+        const unsigned long long v = unit_best_matches(u, hitlen, unit_shape(t));
+        if (v) atomicAdd(acc + pc_tri_index(u.n_genomes, t.ga, t.gb), v);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Sparse exchange (several GPUs): instead of adding into a dense N(N+1)/2 accumulator that
+// every rank would have to hold and all-reduce, each unit becomes ONE 16-byte record
+//   { index of (ga, gb) inside the row block of its owner, (matched << 32) | length }
+// written into the bucket of the rank that owns genome row ga.  The buckets are exchanged with
+// one all-to-all (only pairs that share a pham exist: < 3 % of the triangle on clustered tables)
+// and the owner adds what it receives into the accumulators of ITS rows only.
+// Pass 1 counts records per destination, pass 2 writes them behind warp-aggregated cursors.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int dest_of_row(const DestArgs &d, int row)
+{
+    int b = 0;
+    while (b + 1 < d.n_dest && d.bounds[b + 1] <= row) ++b;
+    return b;
+}
+
+__global__ void count_units_kernel(const UnitArgs u, const DestArgs d, unsigned long long *__restrict__ counts)
+{
+    __shared__ unsigned int s_cnt[PC_MAX_DEST];
+    if (threadIdx.x < PC_MAX_DEST) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; unit < u.n_units; unit += stride) {
+        const Unit t = decode_unit(u, unit);
+        atomicAdd(&s_cnt[dest_of_row(d, t.ga)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < d.n_dest && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// cursors[k] = first record slot of destination k (exclusive scan of the counts)
+__global__ void scan_dest_kernel(int n_dest, const unsigned long long *__restrict__ counts,
+                                 unsigned long long *__restrict__ cursors)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int k = 0; k < n_dest; ++k) { cursors[k] = run; run += counts[k]; }
+    }
+}
+
+__global__ void emit_units_kernel(const UnitArgs u, const uint32_t *__restrict__ hitlen, const DestArgs d,
+                                  unsigned long long *__restrict__ cursors, ulonglong2 *__restrict__ records)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // warp-uniform trip count: every lane of a warp takes part in the match / shuffle below
+    for (int64_t first = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); first < u.n_units; first += stride) {
+        const int64_t unit = first + lane;
+        const bool valid = unit < u.n_units;
+        int dest = PC_MAX_DEST;                       // lanes past the end form their own group
+        ulonglong2 rec = make_ulonglong2(0, 0);
+        if (valid) {
+            const Unit t = decode_unit(u, unit);
+            dest = dest_of_row(d, t.ga);
+            rec.x = (unsigned long long)(pc_tri_index(u.n_genomes, t.ga, t.gb) -
+                                         pc_tri_index(u.n_genomes, d.bounds[dest], d.bounds[dest]));
+            rec.y = unit_best_matches(u, hitlen, unit_shape(t));
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, dest);
+        const int leader = __ffs((int)peers) - 1;
+        unsigned long long base = 0;
+        if (valid && lane == leader) base = atomicAdd(cursors + dest, (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) records[base + __popc(peers & ((1u << lane) - 1u))] = rec;
+    }
+}
+
+__global__ void accumulate_records_kernel(int64_t n_records, const ulonglong2 *__restrict__ records,
+                                          int64_t n_acc, unsigned long long *__restrict__ acc)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_records; k += stride) {
+        const ulonglong2 r = records[k];
+        if (r.y && (int64_t)r.x < n_acc) atomicAdd(acc + r.x, r.y);
+    }
+}
+
+int pc_launch_emit_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen, const DestArgs &d,
+                         unsigned long long *dest_counts, unsigned long long *records)
+{
+    if (u.n_units <= 0) return PC_OK;
+    PC_CUDA(ctx, cudaMemsetAsync(dest_counts, 0, sizeof(unsigned long long) * 2 * PC_MAX_DEST, ctx->stream));
+    int64_t blocks = (u.n_units + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    const int grid = (int)std::max<int64_t>(1, blocks < cap ? blocks : cap);
+    count_units_kernel<<<grid, 256, 0, ctx->stream>>>(u, d, dest_counts);
+    PC_CUDA(ctx, cudaGetLastError());
+    scan_dest_kernel<<<1, 32, 0, ctx->stream>>>(d.n_dest, dest_counts, dest_counts + PC_MAX_DEST);
+    PC_CUDA(ctx, cudaGetLastError());
+    emit_units_kernel<<<grid, 256, 0, ctx->stream>>>(u, hitlen, d, dest_counts + PC_MAX_DEST,
+                                                    reinterpret_cast<ulonglong2 *>(records));
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    return PC_OK;
+}
+
+int pc_launch_accumulate_records(pc_ctx *ctx, int64_t n_records, const unsigned long long *records,
+                                 int64_t n_acc, unsigned long long *acc)
+{
+    if (n_records <= 0) return PC_OK;
+    int64_t blocks = (n_records + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    const int grid = (int)std::max<int64_t>(1, blocks < cap ? blocks : cap);
+    accumulate_records_kernel<<<grid, 256, 0, ctx->stream>>>(n_records, reinterpret_cast<const ulonglong2 *>(records),
+                                                            n_acc, acc);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PC_OK;
 }
 
 int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u)

@@ -1,32 +1,38 @@
 """Multi-GPU sharding of the matrix build: one process per GPU, plumbing by
 ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tests).
 
-How the path shards:
+How the path shards; the reference's only parallelism is a process pool over
+genome pairs (/root/reference/src/phamclust/matrix.py:471-491):
 
-* gcs / jc / pocp / af -- independent output tiles.  Every rank holds the
-  whole (small) packed table; rank r computes a contiguous block of genome
-  ROWS of the upper triangle chosen so that every rank owns the same number of
-  pairs.  No collective during compute; ONE all-gather of the row blocks at the
-  end assembles the packed triangle.
-* aai / peq -- independent alignments.  Phams are dealt round-robin (in
-  descending cost order) over the ranks; each rank aligns its phams' member
-  pairs and scatter-adds best matches into dense int64 pair accumulators
-  ``(matched << 32) | length``.  ONE integer all-reduce (exact, order
-  independent) merges them, then the row-block epilogue + all-gather as above.
+* gcs / jc / pocp / af -- independent output tiles.  Every rank holds the (small) packed table;
+  rank r computes a contiguous block of genome ROWS of the upper triangle.  The blocks are cut
+  by WORK, not by pair count: the int8 engine only streams the K blocks a tile's two genome
+  groups have in common, so late rows (whose phams sit in more K blocks) cost more than early
+  ones (``contraction_row_weights``).  No collective during compute.
+* aai / peq -- independent alignments.  Phams are dealt over the ranks in descending cost order;
+  each rank ships and canonicalises only the genes of ITS phams, aligns their member pairs and
+  turns every (pham, genome pair) best match into one 16-byte record addressed to the rank that
+  owns the pair's row.  ONE all-to-all moves the records (only pairs that share a pham exist:
+  a few per cent of the triangle), the owner adds them into accumulators of its rows only --
+  per-rank accumulator memory is 1/N of the triangle, nothing dense is reduced -- and runs the
+  row-block epilogue.
 
-When the consumer of the matrix is the HOST (the reference hands it to host
-clustering), the all-gather is the wrong exchange: ``sharded_matrix_to_host``
-lets every rank copy its finished row block straight from its GPU into ONE
-triangle in POSIX shared memory (``SharedTriangle``, page-locked by every rank),
-over that GPU's own PCIe link and in parallel with the others -- no device-side
-assembly, no single-link D2H of the whole triangle.
+Assembly of the row blocks, two consumers:
 
-The compute callables are injectable so the host logic (partitioning,
-all-reduce, assembly) is covered on CPU with world_size-2 gloo.
+* device (``sharded_matrix``): one all-gather over NVLink, every rank ends up with the triangle;
+* host (``sharded_matrix_to_host``; what the reference does next is host clustering): every rank
+  copies its finished block from its own GPU over its own PCIe link into ONE triangle in POSIX
+  shared memory (``SharedTriangle``) -- no device-side assembly, no single-link D2H.
+
+``ShardedBuilder`` is the one implementation of a rank's share; ``bench.py`` times exactly its
+methods.  The per-rank compute is injectable (``backend_ops``) so that partitioning, exchange and
+assembly are covered on CPU with world_size-2 gloo.
 """
 import os
 
 import numpy as np
+
+ALIGN_METRICS = ("aai", "peq")
 
 
 def _dist():
@@ -51,29 +57,72 @@ def tri_offset(n, i):
     return i * n - (i * (i - 1)) // 2
 
 
-def row_partition(n, world):
-    """Row boundaries b[0..world] such that rows [b[r], b[r+1]) hold (nearly)
-    the same number of upper-triangle entries for every rank."""
-    total = n * (n + 1) // 2
+def row_partition(n, world, row_weight=None):
+    """Row boundaries b[0..world]: rows [b[r], b[r+1]) carry (nearly) the same share of the
+    total weight for every rank.  ``row_weight[i]`` defaults to the number of upper-triangle
+    entries of row i (n - i): equal pair counts."""
+    if row_weight is None:
+        total = n * (n + 1) // 2
+        bounds = [0]
+        for r in range(1, world):
+            want = total * r // world
+            lo, hi = bounds[-1], n              # smallest i with tri_offset(n, i) >= want
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if tri_offset(n, mid) >= want:
+                    hi = mid
+                else:
+                    lo = mid + 1
+            bounds.append(lo)
+        bounds.append(n)
+        return bounds
+    w = np.asarray(row_weight, dtype=np.float64)
+    assert w.shape == (n,) and (w >= 0).all()
+    cum = np.concatenate(([0.0], np.cumsum(w)))
     bounds = [0]
     for r in range(1, world):
-        want = total * r // world
-        # smallest i with tri_offset(n, i) >= want
-        lo, hi = bounds[-1], n
-        while lo < hi:
-            mid = (lo + hi) // 2
-            if tri_offset(n, mid) >= want:
-                hi = mid
-            else:
-                lo = mid + 1
-        bounds.append(lo)
+        cut = int(np.searchsorted(cum, cum[-1] * r / world, side="left"))
+        bounds.append(min(max(cut, bounds[-1]), n))
     bounds.append(n)
     return bounds
 
 
+def contraction_row_weights(table, group=128, block=128, tile_cols=256, out_cost=48.0):
+    """Estimated cost of every genome row of the shared-count contraction under the block-sparse
+    K schedule of the int8 engine (csrc/pc_contract_i8.cu): a (128-row, 256-column) tile streams
+    the K blocks (128 operand columns) that its row group and one of its column groups both
+    occupy, then pays a K-independent epilogue (``out_cost`` K-block equivalents: TMEM drain,
+    fp64 normalise, 4 B/pair store).  Operand columns follow the library's order: phams held by
+    >= 2 genomes, by first genome.  Returns float64 [n_genomes]."""
+    n = len(table.genome_ptr) - 1
+    pham_id = np.asarray(table.pham_id, dtype=np.int64)
+    n_phams = int(table.n_phams)
+    counts = np.bincount(pham_id, minlength=n_phams)
+    first = np.full(n_phams, len(pham_id), dtype=np.int64)
+    seen, first_at = np.unique(pham_id, return_index=True)
+    first[seen] = first_at
+    eligible = np.nonzero(counts >= 2)[0]
+    col = np.full(n_phams, -1, dtype=np.int64)
+    col[eligible[np.argsort(first[eligible], kind="stable")]] = np.arange(len(eligible))
+    entry_col = col[pham_id]
+    entry_genome = np.repeat(np.arange(n), np.diff(table.genome_ptr))
+    keep = entry_col >= 0
+    n_groups = (n + group - 1) // group
+    n_blocks = max(1, (len(eligible) + block - 1) // block)
+    occ = np.zeros((n_groups, n_blocks), dtype=np.float32)
+    occ[entry_genome[keep] // group, entry_col[keep] // block] = 1.0
+    common = occ @ occ.T                                   # K blocks two groups have in common
+    per_col_tile = tile_cols // group
+    work = np.zeros(n_groups)
+    for g in range(n_groups):
+        tiles = common[g, g:]
+        # a column tile spans `per_col_tile` groups: it visits the union, bounded by the sum
+        work[g] = tiles.sum() / per_col_tile * 1.3 + out_cost * ((n_groups - g) / per_col_tile)
+    return np.repeat(work / group, group)[:n].astype(np.float64)
+
+
 def assemble(n, bounds, shards):
-    """Concatenate per-rank row-block slices (already trimmed) into the packed
-    triangle."""
+    """Concatenate per-rank row-block slices (already trimmed) into the packed triangle."""
     out = np.empty(n * (n + 1) // 2, dtype=np.int32)
     for r, shard in enumerate(shards):
         lo, hi = tri_offset(n, bounds[r]), tri_offset(n, bounds[r + 1])
@@ -81,41 +130,106 @@ def assemble(n, bounds, shards):
     return out
 
 
-def sharded_matrix(table, metric, as_distance=True, ppos=False, backend_ops=None):
-    """Packed int32 micro-unit triangle computed by all ranks of the default
-    process group; every rank returns the full triangle (host numpy).
+class ShardedBuilder:
+    """This rank's share of one matrix build (the default process group's world).
 
-    ``backend_ops`` (tests): object with ``device``, ``accumulate(part, n_parts)
-    -> int64 tensor`` and ``rows(r0, r1, acc) -> int32 tensor``; the default
-    drives libphamclust_b200 on this rank's GPU.
+    ``ops`` drives the rank's device (``_GpuOps``) or, in the CPU tests, the oracle:
+        load(table, part, n_parts)                        host buffers -> device
+        rows(r0, r1, acc_rows) -> int32 tensor            row block [r0, r1) of the triangle
+        rows_to_host(r0, r1, acc_rows, out)               the same, written into a host view
+        contributions(part, n_parts, bounds) -> (records int64 [k, 2] grouped by destination,
+                                                 counts per destination)            aai / peq
+        accumulate(records, r0, r1) -> int64 tensor       accumulators of rows [r0, r1) only
     """
-    import torch
-    dist = _dist()
-    rank, world = dist.get_rank(), dist.get_world_size()
-    n = len(table.genome_ptr) - 1
-    ops = backend_ops or _GpuOps(table, metric, as_distance, ppos)
-    bounds = row_partition(n, world)
-    acc = None
-    if metric in ("aai", "peq"):
-        acc = ops.accumulate(rank, world)
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM)       # exact integer sum
-    local = ops.rows(bounds[rank], bounds[rank + 1], acc)
-    # equal-sized shards for all_gather: pad to the largest block
-    sizes = [tri_offset(n, bounds[r + 1]) - tri_offset(n, bounds[r]) for r in range(world)]
-    width = max(sizes)
-    padded = torch.zeros(width, dtype=torch.int32, device=local.device)
-    padded[:local.numel()] = local
-    gathered = torch.empty(world * width, dtype=torch.int32, device=local.device)
-    dist.all_gather_into_tensor(gathered, padded)
-    host = gathered.cpu().numpy().reshape(world, width)
-    return assemble(n, bounds, [host[r] for r in range(world)])
+
+    def __init__(self, table, metric, as_distance=True, ppos=False, backend_ops=None, balance="work"):
+        dist = _dist()
+        self.dist = dist
+        grouped = dist.is_available() and dist.is_initialized()
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if grouped else (0, 1)
+        self.table, self.metric = table, metric
+        self.n = len(table.genome_ptr) - 1
+        self.align = metric in ALIGN_METRICS
+        self.ops = backend_ops or _GpuOps(metric, as_distance, ppos)
+        if self.align or balance != "work" or self.world == 1:
+            # aai/peq: the row-block stage is the dense epilogue, whose cost is the pair count
+            self.bounds = row_partition(self.n, self.world)
+        else:
+            self.bounds = row_partition(self.n, self.world, contraction_row_weights(table))
+        self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.sizes = [tri_offset(self.n, self.bounds[r + 1]) - tri_offset(self.n, self.bounds[r])
+                      for r in range(self.world)]
+        self.exchange_records = 0           # records this rank received in the last exchange
+
+    def load(self, table=None):
+        """Host buffers -> this rank's device: the table, and for aai/peq only the genes of the
+        phams this rank aligns."""
+        self.ops.load(table if table is not None else self.table, self.rank, self.world)
+
+    def accumulators(self):
+        """aai/peq: align this rank's phams, exchange the contribution records, return the
+        accumulators of this rank's rows (None for the other metrics)."""
+        if not self.align:
+            return None
+        import torch
+        dist = self.dist
+        records, counts = self.ops.contributions(self.rank, self.world, self.bounds)
+        if self.world > 1:
+            send_counts = torch.as_tensor(np.asarray(counts, dtype=np.int64), device=records.device)
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts)
+            recv_counts = recv_counts.tolist()
+            received = torch.empty((int(sum(recv_counts)), 2), dtype=torch.int64, device=records.device)
+            dist.all_to_all_single(received, records[:int(sum(counts))], recv_counts, [int(c) for c in counts])
+        else:
+            received = records[:int(sum(counts))]
+        self.exchange_records = int(received.shape[0])
+        return self.ops.accumulate(received, self.r0, self.r1)
+
+    def row_block(self):
+        """This rank's rows of the packed triangle on its device (int32 tensor)."""
+        return self.ops.rows(self.r0, self.r1, self.accumulators())
+
+    def row_block_to_host(self, out):
+        """... written straight into ``out`` (a host view of exactly this block)."""
+        acc = self.accumulators()
+        if self.r1 > self.r0:
+            self.ops.rows_to_host(self.r0, self.r1, acc, out)
+
+    def all_gather(self, local, gathered=None):
+        """Device consumer: every rank receives every row block (padded to the widest)."""
+        import torch
+        width = max(max(self.sizes), 1)
+        padded = local
+        if local.numel() != width:
+            padded = torch.zeros(width, dtype=torch.int32, device=local.device)
+            padded[:local.numel()] = local
+        if self.world == 1:
+            return padded
+        if gathered is None:
+            gathered = torch.empty(self.world * width, dtype=torch.int32, device=local.device)
+        self.dist.all_gather_into_tensor(gathered, padded)
+        return gathered
+
+    def assemble_host(self, gathered):
+        width = max(max(self.sizes), 1)
+        host = gathered.cpu().numpy().reshape(self.world, width)
+        return assemble(self.n, self.bounds, [host[r] for r in range(self.world)])
+
+
+def sharded_matrix(table, metric, as_distance=True, ppos=False, backend_ops=None):
+    """Packed int32 micro-unit triangle computed by all ranks of the default process group;
+    every rank returns the full triangle (host numpy)."""
+    builder = ShardedBuilder(table, metric, as_distance, ppos, backend_ops)
+    builder.load()
+    return builder.assemble_host(builder.all_gather(builder.row_block()))
 
 
 class SharedTriangle:
     """The packed int32 triangle of an n-genome matrix in POSIX shared memory:
     created by rank 0, attached by every rank of the node; with a GPU present each
     rank page-locks the rows it will write (``pin_rows=(r0, r1)``, rounded out to
-    whole pages; ``None`` = its ``row_partition`` block) so that its D2H is a
+    whole pages; ``None`` = its pair-balanced ``row_partition`` block) so that its D2H is a
     full-speed DMA.  ``array`` is the numpy view; ``close()`` unmaps, rank 0 also
     unlinks."""
 
@@ -180,34 +294,27 @@ class SharedTriangle:
             self._shm.unlink()
 
 
-def sharded_matrix_to_host(table, metric, shared, as_distance=True, ppos=False, backend_ops=None):
-    """Every rank computes its row block and copies it from its own GPU straight
-    into ``shared`` (a SharedTriangle); returns after a barrier, when the whole
-    triangle is in host memory (``shared.array``, valid on every rank of the node).
-
-    ``backend_ops`` (tests): object with ``accumulate(part, n_parts) -> int64
-    tensor`` and ``rows_to_host(r0, r1, acc, out)`` filling the int32 numpy view
-    ``out``; the default drives libphamclust_b200 on this rank's GPU.
-    """
-    dist = _dist()
-    rank, world = dist.get_rank(), dist.get_world_size()
-    n = len(table.genome_ptr) - 1
-    ops = backend_ops or _GpuOps(table, metric, as_distance, ppos)
-    bounds = row_partition(n, world)
-    acc = None
-    if metric in ("aai", "peq"):
-        acc = ops.accumulate(rank, world)
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM)       # exact integer sum
-    ops.rows_to_host(bounds[rank], bounds[rank + 1], acc, shared.rows(bounds[rank], bounds[rank + 1]))
-    dist.barrier()
+def sharded_matrix_to_host(table, metric, shared=None, as_distance=True, ppos=False, backend_ops=None,
+                           builder=None):
+    """Every rank computes its row block and copies it from its own GPU straight into
+    ``shared`` (a SharedTriangle pinned for the builder's rows); returns after a barrier, when
+    the whole triangle is in host memory (``shared.array``, valid on every rank of the node)."""
+    if builder is None:
+        builder = ShardedBuilder(table, metric, as_distance, ppos, backend_ops)
+        builder.load()
+    if shared is None:
+        shared = SharedTriangle(builder.n, pin_rows=(builder.r0, builder.r1))
+    builder.row_block_to_host(shared.rows(builder.r0, builder.r1))
+    if builder.world > 1:
+        builder.dist.barrier()
     return shared.array
 
 
 class _GpuOps:
-    """The real thing: this rank's GPU through the C ABI, on torch's stream so
-    that NCCL collectives order after the kernels."""
+    """The real thing: this rank's GPU through the C ABI, on torch's stream so that NCCL
+    collectives order after the kernels."""
 
-    def __init__(self, table, metric, as_distance, ppos):
+    def __init__(self, metric, as_distance, ppos):
         import torch
         from phamclust_b200.matrix import get_context
         self.torch = torch
@@ -216,31 +323,50 @@ class _GpuOps:
         self.device = torch.device("cuda", local_rank)
         self.ctx = get_context(local_rank)
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        self.ctx.load_table(table)
-        if metric in ("aai", "peq"):
-            self.ctx.load_sequences(table)
         self.metric, self.as_distance, self.ppos = metric, as_distance, ppos
+        self.n = 0
+        self._records = None
+        self._acc = None
+
+    def load(self, table, part, n_parts):
+        self.ctx.load_table(table)
         self.n = len(table.genome_ptr) - 1
+        if self.metric in ALIGN_METRICS:
+            if table.seq_off is None:
+                raise ValueError(f"metric {self.metric} needs translations")
+            self.ctx.load_sequences(table, part, n_parts)
 
-    def accumulate(self, part, n_parts):
-        acc = self.torch.zeros(self.n * (self.n + 1) // 2, dtype=self.torch.int64,
-                               device=self.device)
-        self.ctx.align_accumulate(acc.data_ptr(), part=part, n_parts=n_parts, ppos=self.ppos)
-        return acc
+    def contributions(self, part, n_parts, bounds):
+        torch = self.torch
+        n_units = self.ctx.align_units(part, n_parts)
+        if self._records is None or self._records.shape[0] < n_units:
+            self._records = torch.empty((max(n_units, 1), 2), dtype=torch.int64, device=self.device)
+        counts = self.ctx.align_contributions(self._records.data_ptr(), bounds, part, n_parts, ppos=self.ppos)
+        return self._records, counts
 
-    def rows(self, r0, r1, acc):
+    def accumulate(self, records, r0, r1):
+        torch = self.torch
         count = tri_offset(self.n, r1) - tri_offset(self.n, r0)
-        out = self.torch.empty(max(count, 1), dtype=self.torch.int32, device=self.device)
+        if self._acc is None or self._acc.numel() != max(count, 1):
+            self._acc = torch.empty(max(count, 1), dtype=torch.int64, device=self.device)
+        self._acc.zero_()
+        self.ctx.accumulate_records(int(records.shape[0]), records.data_ptr(), count, self._acc.data_ptr())
+        return self._acc
+
+    def rows(self, r0, r1, acc_rows, out=None):
+        count = tri_offset(self.n, r1) - tri_offset(self.n, r0)
+        if out is None:
+            out = self.torch.empty(max(count, 1), dtype=self.torch.int32, device=self.device)
         if count:
-            self.ctx.matrix_rows(self.metric, self.as_distance, r0, r1,
-                                 acc_ptr=acc.data_ptr() if acc is not None else None,
-                                 out_device_ptr=out.data_ptr(), ppos=self.ppos)
+            self.ctx.matrix_rows_owned(self.metric, self.as_distance, r0, r1,
+                                       acc_rows.data_ptr() if acc_rows is not None else None,
+                                       out_device_ptr=out.data_ptr(), ppos=self.ppos)
         return out[:count]
 
-    def rows_to_host(self, r0, r1, acc, out):
+    def rows_to_host(self, r0, r1, acc_rows, out):
         """Row block computed on this GPU, D2H by the library into ``out`` (page-locked
         shared memory: a full-speed DMA on this GPU's own link)."""
         if r1 > r0:
-            self.ctx.matrix_rows(self.metric, self.as_distance, r0, r1,
-                                 acc_ptr=acc.data_ptr() if acc is not None else None, out=out,
-                                 ppos=self.ppos)
+            self.ctx.matrix_rows_owned(self.metric, self.as_distance, r0, r1,
+                                       acc_rows.data_ptr() if acc_rows is not None else None, out=out,
+                                       ppos=self.ppos)

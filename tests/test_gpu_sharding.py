@@ -1,0 +1,145 @@
+"""The several-GPU data plane on real hardware.
+
+* One GPU is enough to check the kernels behind the exchange: partition by partition, ship only
+  that partition's genes (pc_load_sequences_part), emit its contribution records
+  (pc_align_contributions), route the buckets by hand to their owners, accumulate
+  (pc_accumulate_records) and run the owned-rows epilogue (pc_matrix_rows_owned) -- the assembled
+  triangle must equal the single-partition dense path entry for entry, and the oracle.
+* With two GPUs visible, two NCCL ranks run ``ShardedBuilder`` for real (all-to-all of the
+  records, all-gather of the row blocks, the shared host triangle) and compare the WHOLE triangle
+  with the 1-GPU result -- array_equal, not a checksum.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import pham_oracle as po
+from phamclust_b200 import distributed, synthetic
+from phamclust_b200._native import tri_len
+from phamclust_b200.packing import unpack_genomes
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("n_parts,metric", [(2, "peq"), (3, "aai"), (5, "peq")])
+def test_partitioned_records_equal_the_dense_path(gpu_ctx, n_parts, metric):
+    torch = _torch()
+    dev = torch.device("cuda", gpu_ctx.device)
+    table = synthetic.phage_table(260, seed=11, genomes_per_cluster=40, pool=90)
+    n = table.n_genomes
+    gpu_ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        gpu_ctx.load_table(table)
+        gpu_ctx.load_sequences(table)
+        dense = gpu_ctx.matrix(metric, as_distance=True)
+        hit_d, len_d = gpu_ctx.numerators("aai")
+        bounds = distributed.row_partition(n, n_parts)
+        accs = [torch.zeros(max(tri_len(n, bounds[d], bounds[d + 1]), 1), dtype=torch.int64, device=dev)
+                for d in range(n_parts)]
+        total_records = 0
+        for part in range(n_parts):
+            gpu_ctx.load_sequences(table, part, n_parts)           # only this partition's genes
+            n_units = gpu_ctx.align_units(part, n_parts)
+            records = torch.empty((max(n_units, 1), 2), dtype=torch.int64, device=dev)
+            counts = gpu_ctx.align_contributions(records.data_ptr(), bounds, part, n_parts)
+            assert int(counts.sum()) == n_units
+            total_records += n_units
+            start = 0
+            for d in range(n_parts):                               # the all-to-all, by hand
+                bucket = records[start:start + int(counts[d])].contiguous()
+                start += int(counts[d])
+                if bucket.shape[0]:
+                    assert int(bucket[:, 0].min()) >= 0 and int(bucket[:, 0].max()) < accs[d].numel()
+                gpu_ctx.accumulate_records(int(bucket.shape[0]), bucket.data_ptr(), accs[d].numel(), accs[d].data_ptr())
+        assert total_records > 0
+        gpu_ctx.load_sequences(table, 0, n_parts)
+        got = np.concatenate([
+            gpu_ctx.matrix_rows_owned(metric, True, bounds[d], bounds[d + 1], accs[d].data_ptr())
+            for d in range(n_parts) if bounds[d + 1] > bounds[d]])
+        assert np.array_equal(got, dense)
+        # the integer sums themselves
+        acc_all = torch.cat([a[:tri_len(n, bounds[d], bounds[d + 1])] for d, a in enumerate(accs)]).cpu().numpy()
+        off_diag = np.ones(tri_len(n), dtype=bool)
+        off_diag[[distributed.tri_offset(n, i) for i in range(n)]] = False
+        assert np.array_equal((acc_all >> 32)[off_diag], hit_d.astype(np.int64)[off_diag])
+        assert np.array_equal((acc_all & 0xFFFFFFFF)[off_diag], len_d.astype(np.int64)[off_diag])
+        # and a few rows against the oracle
+        genomes = unpack_genomes(table)
+        for i, j in ((0, 1), (3, 39), (41, 77), (100, 119), (200, 259)):
+            want = po.round6_micro(po.METRICS[metric](genomes[i], genomes[j], as_distance=True))
+            assert abs(int(dense[distributed.tri_offset(n, i) + j - i]) - want) <= 1
+        # a plan for another partition than the one whose genes are on the device is refused
+        with pytest.raises(ValueError):
+            gpu_ctx.align_units(1, n_parts)
+    finally:
+        gpu_ctx.set_stream(0, external=False)
+        gpu_ctx.load_table(table)
+        gpu_ctx.load_sequences(table)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, queue):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank),
+                      RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        out = {}
+        for metric, table in (("peq", synthetic.phage_table(300, seed=5)),
+                              ("jc", synthetic.sparse_table(1500, 9000, seed=6))):
+            n = table.n_genomes
+            got = distributed.sharded_matrix(table, metric)
+            builder = distributed.ShardedBuilder(table, metric)
+            builder.load()
+            shared = distributed.SharedTriangle(n, pin_rows=(builder.r0, builder.r1))
+            try:
+                host = distributed.sharded_matrix_to_host(table, metric, shared, builder=builder).copy()
+                dist.barrier()
+            finally:
+                shared.close()
+            assert np.array_equal(host, got)
+            out[metric] = (got, builder.bounds, builder.exchange_records)
+        queue.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_nccl_ranks_equal_one_gpu(gpu_ctx):
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 visible GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from phamclust_b200 import packed_matrix
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for metric, table in (("peq", synthetic.phage_table(300, seed=5)),
+                          ("jc", synthetic.sparse_table(1500, 9000, seed=6))):
+        single = packed_matrix(table, metric)
+        for rank in (0, 1):
+            got, bounds, records = results[rank][metric]
+            assert np.array_equal(got, single), (metric, rank)
+            assert bounds[0] == 0 and bounds[-1] == table.n_genomes
+        if metric == "peq":
+            assert results[0][metric][2] + results[1][metric][2] > 0
