@@ -556,7 +556,7 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
         per_launch_ms = contract_ms / launches
         af_limbs = 1 if int(table.len_sum.max(initial=0)) <= 255 else 2
         limbs = {"gcs": 1, "jc": 1, "pocp": 2, "af": 2 * af_limbs}[metric]     # K multiplier of the operand
-        if (engine or "auto") in ("i8mma", "auto"):
+        if (engine or "auto") in ("i8mma", "i8mma_v1", "auto"):
             # algorithmic int8 ops: 2 * K * N(N+1)/2 with K = P (gcs/jc), 2P (pocp), 2P per af limb
             # K counts only phams held by >= 2 genomes: single-genome phams can never be
             # shared and get no operand column (exact)
@@ -690,7 +690,7 @@ def main():
     ap.add_argument("--metric", default=None)
     ap.add_argument("--genomes", type=int, default=None)
     ap.add_argument("--phams", type=int, default=None)
-    ap.add_argument("--engine", default=None, choices=[None, "auto", "popc", "i8mma"])
+    ap.add_argument("--engine", default=None, choices=[None, "auto", "popc", "i8mma", "i8mma_v1"])
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extras", default="auto", choices=["auto", "none"],

@@ -64,7 +64,9 @@ enum {
 enum {
     PC_ENGINE_AUTO = 0,
     PC_ENGINE_POPC = 1, /* bit-packed AND + POPC tile kernel                */
-    PC_ENGINE_I8MMA = 2 /* int8 tcgen05.mma (TMA -> smem -> TMEM) GEMM      */
+    PC_ENGINE_I8MMA = 2,/* int8 tcgen05.mma GEMM: persistent CTA pairs (cta_group::2),
+                           double-buffered TMEM accumulators, device tile queue          */
+    PC_ENGINE_I8MMA_V1 = 3 /* the round-1 kernel: one tile per CTA (comparisons only)    */
 };
 
 /* -------- lifetime ------------------------------------------------------ */

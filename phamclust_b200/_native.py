@@ -14,7 +14,7 @@ _HERE = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ.get("PHAMCLUST_B200_LIB") or _HERE / "libphamclust_b200.so")
 
 METRIC_IDS = {"gcs": 0, "jc": 1, "pocp": 2, "af": 3, "aai": 4, "peq": 5}
-ENGINE_IDS = {"auto": 0, "popc": 1, "i8mma": 2}
+ENGINE_IDS = {"auto": 0, "popc": 1, "i8mma": 2, "i8mma_v1": 3}
 DP_MODE_IDS = {"auto": 0, "classic": 1}
 STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h",
           "host_table", "host_seqs", "host_plan")

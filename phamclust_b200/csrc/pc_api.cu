@@ -196,6 +196,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_pham_col, &ctx->d_copies, &ctx->d_len_sum,
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
                       &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_i8_occ, &ctx->d_i8_steps, &ctx->d_codes,
+                      &ctx->d_p2_tiles, &ctx->d_p2_masks, &ctx->d_p2_keys, &ctx->d_p2_ids, &ctx->d_p2_temp, &ctx->d_dest,
                       &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_canon, &ctx->d_gene_hi, &ctx->d_subtab[0],
                       &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
                       &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
@@ -231,7 +232,7 @@ extern "C" int pc_set_stream(pc_ctx *ctx, void *cuda_stream, int external)
 extern "C" int pc_set_engine(pc_ctx *ctx, int engine)
 {
     PC_ENTER(ctx);
-    if (engine < PC_ENGINE_AUTO || engine > PC_ENGINE_I8MMA)
+    if (engine < PC_ENGINE_AUTO || engine > PC_ENGINE_I8MMA_V1)
         return pc_fail(ctx, PC_EINVAL, "unknown engine %d", engine);
     ctx->engine = engine;
     return PC_OK;
@@ -878,7 +879,7 @@ static int contract_rows(pc_ctx *ctx, int metric, int as_distance, int raw, int6
     // AUTO: the tensor-core engine whenever the weights fit its limb layout
     int engine = ctx->engine;
     if (engine == PC_ENGINE_AUTO) engine = pc_i8_supported(ctx, metric) ? PC_ENGINE_I8MMA : PC_ENGINE_POPC;
-    if (engine == PC_ENGINE_I8MMA) {
+    if (engine == PC_ENGINE_I8MMA || engine == PC_ENGINE_I8MMA_V1) {
         PC_TRY(pc_i8_contract(ctx, metric, ep));
         return PC_OK;
     }

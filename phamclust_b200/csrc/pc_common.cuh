@@ -185,6 +185,7 @@ struct pc_ctx {
     int64_t i8_dense_steps = 0;                    // ... and what the dense K schedule would have issued
     DevBuf d_i8_steps;                             // u64: 128 x 256 x 128 MMA groups issued since the reset
     int i8_kind = -1; int64_t i8_K = 0, i8_rows = 0;
+    DevBuf d_p2_tiles, d_p2_masks, d_p2_keys, d_p2_ids, d_p2_temp;   // tile queue of the persistent pair kernel
 
     // ---- sequences ----
     int64_t n_genes = 0;
@@ -251,6 +252,8 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
 int pc_launch_gene_bound(pc_ctx *ctx, const int *rowmax32, int32_t *gene_hi);
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
 int pc_i8_supported(const pc_ctx *ctx, int metric);
+int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_bytes, int64_t rows_pad,
+                        int occ_words, int occ_shift, const EpilogueArgs &ep);
 int pc_build_canonical_genes(pc_ctx *ctx);
 
 // DP kernel configs: a subgroup of G lanes per alignment (G in {4,8,16,32}), K ref

@@ -1,4 +1,7 @@
-// pc_contract_i8.cu -- K1/K2/K3 as an int8 tcgen05 GEMM: S = M_a . M_b^T over
+// pc_contract_i8.cu -- operand packing of the int8 tensor engine + the round-1 kernel (one tile
+// per CTA, engine PC_ENGINE_I8MMA_V1; the default engine is the persistent CTA-pair kernel of
+// pc_contract_i8p.cu, which this file's pc_i8_contract dispatches to).
+// K1/K2/K3 as an int8 tcgen05 GEMM: S = M_a . M_b^T over
 // the dense genome x pham operand, s32 accumulators in TMEM, TMA-fed, with the
 // per-metric normalisation + Python-exact rounding (K6) fused into the epilogue
 // so that only the upper-triangle tiles of the result are ever written.
@@ -15,14 +18,15 @@
 // the row tile reads segment t while the column tile reads segment B and vice
 // versa, limb t accumulating into its own TMEM accumulator.
 //
-// CTA = one (128*MT) x 256 output tile (UMMA M=128, N=256, K=32 per
+// V1 CTA = one (128*MT) x 256 output tile (UMMA M=128, N=256, K=32 per
 // instruction, cta_group::1; MT = 2 row tiles sharing one column tile whenever a
 // single accumulator per row tile suffices -- r1 ncu showed the 128x256 tile at
 // 55 % tensor / 55 % L2 throughput, i.e. limited by operand traffic from L2, and
-// the taller tile moves 1.5x fewer bytes per MAC), 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
-// elected lane each), warps 2-9 = epilogue (tcgen05.ld 32x32b; a warp may only
-// touch TMEM lane quadrant warp%4, two warps share a quadrant and split the columns).  4-stage 48 KB smem ring (128B-swizzled 128-byte K
-// slabs), mbarrier full/empty pairs, tcgen05.commit releases the slots.
+// the taller tile moves 1.5x fewer bytes per MAC), 448 threads: warp 0 = TMA producer,
+// warp 1 = MMA issuer (one elected lane each), warps 2-13 = epilogue (tcgen05.ld 32x32b; a warp
+// may only touch TMEM lane quadrant warp%4, three warps share a quadrant and split the columns).
+// 3-stage (MT = 2, 64 KB per stage) or 4-stage (MT = 1, 48 KB) smem ring of 128B-swizzled
+// 128-byte K slabs, mbarrier full/empty pairs, tcgen05.commit releases the slots.
 // Tensor-pipe bound: 2*K*128*256 int8 ops per tile.
 //
 // Block sparsity: pack_i8_kernel also records which (128-genome group, 128-column
@@ -36,6 +40,7 @@
 #include <cuda.h>
 
 #include "pc_common.cuh"
+#include "pc_tcgen05.cuh"
 
 #define I8_BM 128
 #define I8_BN 256
@@ -67,100 +72,6 @@ struct I8Args {
     unsigned long long *tile_steps;   // += MT per K block visited (one 128 x 256 x 128 MMA group each)
     EpilogueArgs ep;
 };
-
-// ---------------------------------------------------------------------------
-// PTX wrappers (sm_100a)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    const uint32_t addr = smem_u32(bar);
-    while (!done) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
-                                            int32_t c0, int32_t c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0),
-        "r"(c1)
-        : "memory");
-}
-
-__device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr)
-{
-    // cute::UMMA::SmemDescriptor, K-major, SWIZZLE_128B: rows are 128 B, groups
-    // of 8 rows are SBO = 1024 B apart, LBO = 1 (unused with swizzle), version 1
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address
-    d |= (uint64_t)1 << 16;                             // leading byte offset (16 B units)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
-    d |= (uint64_t)1 << 46;                             // version = 1 (Blackwell)
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
-
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                        uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                     smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // instruction descriptor: D = s32, A = B = unsigned 8 bit, K-major, N = 256, M = 128
 __device__ __forceinline__ constexpr uint32_t i8_idesc()
@@ -334,7 +245,7 @@ i8_contract_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (n_steps) atomicAdd(a.tile_steps, (unsigned long long)n_steps * MT);
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue: warps 2..13, TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
         const int et = threadIdx.x - 64;              // 0 .. 32*I8_EPI_WARPS-1
         constexpr int EPI_GROUPS = I8_EPI_WARPS / 4;  // warps sharing one TMEM lane quadrant
@@ -506,6 +417,8 @@ int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep)
         ctx->i8_kind = kind;
         ctx->i8_K = row_bytes;
     }
+    if (ctx->engine != PC_ENGINE_I8MMA_V1)       // default: the persistent CTA-pair kernel
+        return pc_i8_pair_contract(ctx, n_limbs, p_pad, row_bytes, rows_pad, occ_words, occ_shift, ep);
     CUtensorMap map_a, map_b;
     PC_TRY(make_map(ctx, &map_a, ctx->d_i8.p, row_bytes, rows_pad, I8_BM));
     PC_TRY(make_map(ctx, &map_b, ctx->d_i8.p, row_bytes, rows_pad, I8_BN));

@@ -31,26 +31,43 @@ def test_i8_engine_matches_popc_and_oracle(gpu_ctx, n, p, seed):
             oracle_num = po.table_numerators(table, key)[iu].copy()
             oracle_num[iu[0] == iu[1]] = 0
             assert np.array_equal(want_num, oracle_num), key
-            gpu_ctx.set_engine("i8mma")
-            assert np.array_equal(gpu_ctx.numerators(key), want_num), key
-            for d in (True, False):
-                assert np.array_equal(gpu_ctx.matrix(key, as_distance=d), want[d]), (key, d)
-            # row blocks through the int8 engine recompose as well
-            if n > 128:
-                parts = [gpu_ctx.matrix_rows(key, True, r0, r1) for r0, r1 in ((0, 100), (100, 129), (129, n))]
-                assert np.array_equal(np.concatenate(parts), want[True]), key
+            for engine in ("i8mma", "i8mma_v1"):       # persistent CTA-pair kernel, round-1 kernel
+                gpu_ctx.set_engine(engine)
+                assert np.array_equal(gpu_ctx.numerators(key), want_num), (key, engine)
+                for d in (True, False):
+                    assert np.array_equal(gpu_ctx.matrix(key, as_distance=d), want[d]), (key, d, engine)
+                # row blocks through the int8 engine recompose as well
+                if n > 128:
+                    parts = [gpu_ctx.matrix_rows(key, True, r0, r1) for r0, r1 in ((0, 100), (100, 129), (129, n))]
+                    assert np.array_equal(np.concatenate(parts), want[True]), (key, engine)
     finally:
         gpu_ctx.set_engine("auto")
 
 
 def test_i8_engine_at_benchmark_size(gpu_ctx):
-    table = synthetic.sparse_table(4000, 60000, seed=1)
+    """Many tiles per CTA pair (the persistent kernel's accumulator ring and tile queue wrap many
+    times), every metric layout (1 segment, [C|B], two af limbs), against the popc engine; 60 random
+    rows of the shared counts also against the array oracle."""
+    table = _with_lengths(synthetic.sparse_table(4000, 60000, seed=1), 12)
     gpu_ctx.load_table(table)
+    n = table.n_genomes
     try:
-        gpu_ctx.set_engine("popc")
-        want = gpu_ctx.matrix("jc")
+        for key in CHEAP:
+            gpu_ctx.set_engine("popc")
+            want = gpu_ctx.matrix(key)
+            for engine in ("i8mma", "i8mma_v1"):
+                gpu_ctx.set_engine(engine)
+                assert np.array_equal(gpu_ctx.matrix(key), want), (key, engine)
         gpu_ctx.set_engine("i8mma")
-        assert np.array_equal(gpu_ctx.matrix("jc"), want)
+        num = gpu_ctx.numerators("gcs")
+        dense = po.table_numerators(table, "gcs")
+        rng = np.random.default_rng(5)
+        for i in rng.choice(n, size=60, replace=False).tolist():
+            lo = i * n - (i * (i - 1)) // 2
+            got = num[lo:lo + n - i].copy()
+            want_row = dense[i, i:].copy()
+            want_row[0] = 0
+            assert np.array_equal(got, want_row), i
     finally:
         gpu_ctx.set_engine("auto")
 
