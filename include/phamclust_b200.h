@@ -295,6 +295,23 @@ int pc_gather_fields(const char *buf, int64_t n, const int64_t *start,
  */
 int pc_dense_from_micro(int64_t n, const int32_t *micro, const int64_t *order,
                         int kind, void *out);
+/*
+ * SymMatrix.medoid / anti_medoid (matrix.py:81-127) without a dense N x N: per node (storage
+ * order) the exact integer sum, in micro-units, of every weight it appears in while the upper
+ * half is iterated -- the diagonal twice, as upstream.  PC_EINVAL on an unset weight.
+ */
+int pc_node_sums(int64_t n, const int32_t *micro, int64_t *sums);
+/*
+ * One single-genome FASTA file in memory -> (pham, translation) records without building Genome
+ * dicts (fasta.py:4-40, genome.py:66-83, scripts/phamclust.py:50-83): pham names appended to
+ * name_out, rstrip()ped and concatenated sequence lines to seq_out, fields[4r..4r+3] = name
+ * begin/end, sequence begin/end; used[0..1] = bytes written.  Returns the number of records, or
+ * -1 (no leading '>'), -2 (header field without exactly one '='), -3 (no pham= field), -4 (out of
+ * capacity), -5 (non-ASCII sequence byte).
+ */
+int64_t pc_scan_fasta(const char *buf, int64_t len, int64_t max_records, int64_t *fields,
+                      uint8_t *name_out, int64_t name_cap, uint8_t *seq_out, int64_t seq_cap,
+                      int64_t *used);
 const char *pc_io_last_error(void);
 
 #ifdef __cplusplus

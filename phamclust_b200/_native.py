@@ -25,7 +25,7 @@ EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_strea
            "pc_align_contributions", "pc_accumulate_records", "pc_matrix_rows_owned",
            "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters", "pc_stat",
            "pc_write_matrix", "pc_parse_squareform", "pc_scan_tsv", "pc_tsv_intern", "pc_gather_fields",
-           "pc_dense_from_micro",
+           "pc_dense_from_micro", "pc_node_sums", "pc_scan_fasta",
            "pc_io_last_error")
 
 _lib = None
@@ -77,6 +77,9 @@ def load_library():
     lib.pc_tsv_intern.argtypes = [ctypes.c_char_p, i64, vp, i32, vp, vp]
     lib.pc_tsv_intern.restype = ctypes.c_int64
     lib.pc_gather_fields.argtypes = [ctypes.c_char_p, i64, vp, vp, ctypes.c_uint8, vp]
+    lib.pc_node_sums.argtypes = [i64, vp, vp]
+    lib.pc_scan_fasta.argtypes = [ctypes.c_char_p, i64, i64, vp, vp, i64, vp, i64, vp]
+    lib.pc_scan_fasta.restype = ctypes.c_int64
     lib.pc_io_last_error.argtypes = []
     lib.pc_io_last_error.restype = ctypes.c_char_p
     _lib = lib

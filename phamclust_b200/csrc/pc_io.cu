@@ -144,10 +144,27 @@ extern "C" int pc_parse_squareform(const char *buf, int64_t len, int64_t n, int3
         for (int64_t j = 0; j <= i; ++j) {
             if (p >= eol) { g_io_error = "squareform row is too short"; return PC_EINVAL; }
             ++p;                                      // the tab
+            // the field is buf[p, q): up to the next tab or the end of THIS line; it is copied out
+            // so that strtod can neither run into the next row (it skips leading whitespace,
+            // newlines included) nor accept what float() refuses for a weight (nan, inf, hex)
+            int64_t q = p;
+            while (q < eol && buf[q] != '\t') ++q;
+            char field[64];
+            const int64_t flen = q - p;
+            bool plain = flen > 0 && flen < (int64_t)sizeof field;
+            for (int64_t k = 0; plain && k < flen; ++k) {
+                const char c = buf[p + k];
+                plain = (c >= '0' && c <= '9') || c == '.' || c == '-' || c == '+' || c == 'e' || c == 'E' ||
+                        (c == '\r' && k == flen - 1);
+            }
+            if (!plain) { g_io_error = "could not convert string to float"; return PC_EINVAL; }
+            memcpy(field, buf + p, (size_t)flen);
+            field[flen] = 0;
+            if (field[flen - 1] == '\r') field[flen - 1] = 0;
             char *endp = nullptr;
-            const double v = strtod(buf + p, &endp);
-            if (endp == buf + p) { g_io_error = "could not convert string to float"; return PC_EINVAL; }
-            p = endp - buf;
+            const double v = strtod(field, &endp);     // digits, sign, '.', exponent only: locale-proof for '.'
+            if (endp == field || *endp != 0) { g_io_error = "could not convert string to float"; return PC_EINVAL; }
+            p = q;
             if (!(v >= 0.0 && v <= 1.0)) { g_io_error = "weight not in [0.0, 1.0]"; return PC_EINVAL; }
             micro_out[tri(n, j, i)] = (int32_t)round6_micro_host(v);
         }
@@ -296,3 +313,120 @@ extern "C" int pc_dense_from_micro(int64_t n, const int32_t *micro, const int64_
     return PC_OK;
 }
 
+
+// Per node, the sum of every weight it appears in while iterating the upper half of the
+// matrix -- the diagonal counts twice, exactly the lists SymMatrix.medoid builds upstream
+// (matrix.py:81-96) -- as exact integers in micro-units, in STORAGE order, in one pass over the
+// packed triangle (no dense N x N).  PC_EINVAL if a weight is unset / out of range.
+extern "C" int pc_node_sums(int64_t n, const int32_t *micro, int64_t *sums)
+{
+    if (n < 0 || (n > 0 && (!micro || !sums))) {
+        g_io_error = "pc_node_sums: bad arguments";
+        return PC_EINVAL;
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = n < 2048 ? 1 : (int)std::max(1u, std::min(8u, hw));
+    std::vector<std::vector<int64_t>> part((size_t)T);
+    std::vector<int> bad((size_t)T, 0);
+    // rows are dealt so that every thread sees about the same number of entries
+    auto row_of = [&](int t) {
+        const double frac = (double)t / T;
+        return (int64_t)std::llround((double)n * (1.0 - std::sqrt(1.0 - frac)));
+    };
+    auto body = [&](int t) {
+        std::vector<int64_t> &acc = part[t];
+        acc.assign((size_t)n, 0);
+        const int64_t r0 = t == 0 ? 0 : row_of(t), r1 = t == T - 1 ? n : row_of(t + 1);
+        for (int64_t i = r0; i < r1; ++i) {
+            const int32_t *row = micro + (i * n - (i * (i - 1)) / 2);
+            int64_t own = 0;
+            for (int64_t j = i; j < n; ++j) {
+                const int32_t v = row[j - i];
+                if ((uint32_t)v > 1000000u) bad[t] = 1;
+                own += v;
+                acc[j] += v;                 // as target (j == i: the diagonal's second appearance)
+            }
+            acc[i] += own;                   // as source
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(body, t);
+    body(0);
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < T; ++t)
+        if (bad[t]) { g_io_error = "pc_node_sums: unset or out-of-range weight"; return PC_EINVAL; }
+    for (int64_t k = 0; k < n; ++k) {
+        int64_t v = 0;
+        for (int t = 0; t < T; ++t) v += part[t][k];
+        sums[k] = v;
+    }
+    return PC_OK;
+}
+
+// One single-genome FASTA file held in memory (fasta.py:4-40 + genome.py:66-83): per record
+// the pham named by the first `pham=` field of the header (fields split on '|', each exactly one
+// '=') and the sequence with every line rstrip()ped and concatenated.  Pham names are appended to
+// name_out, sequences to seq_out; fields[4r..] = name begin/end (in name_out), seq begin/end (in
+// seq_out).  Lines end at '\n', '\r\n' or a lone '\r' (Python's universal newlines).  Returns the
+// number of records or: -1 the file does not start with '>', -2 a header field without exactly one
+// '=', -3 no pham field, -4 out of capacity, -5 a sequence byte outside ASCII (the text-mode
+// reader upstream would decode it to a character that does not fit one arena byte).
+extern "C" int64_t pc_scan_fasta(const char *buf, int64_t len, int64_t max_records, int64_t *fields,
+                                 uint8_t *name_out, int64_t name_cap, uint8_t *seq_out, int64_t seq_cap,
+                                 int64_t *used /* [2]: name bytes, seq bytes */)
+{
+    auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
+    int64_t pos = 0, rec = -1, n_name = 0, n_seq = 0;
+    if (len == 0) { used[0] = used[1] = 0; return 0; }    // upstream: next() on an empty file raises; the caller decides
+    while (pos < len) {
+        int64_t eol = pos;
+        while (eol < len && buf[eol] != '\n' && buf[eol] != '\r') ++eol;
+        int64_t next = eol + 1;
+        if (eol < len && buf[eol] == '\r' && eol + 1 < len && buf[eol + 1] == '\n') next = eol + 2;
+        int64_t end = eol;
+        while (end > pos && is_space(buf[end - 1])) --end;
+        if (buf[pos] == '>') {
+            if (++rec >= max_records) { g_io_error = "pc_scan_fasta: too many records"; return -4; }
+            // header = line[1:].rstrip(); fields split on '|'
+            int64_t f0 = pos + 1;
+            bool found = false;
+            const int64_t hend = std::max(end, f0);
+            for (int64_t p = f0; !found;) {
+                int64_t q = p;
+                while (q < hend && buf[q] != '|') ++q;
+                int64_t eq = -1, n_eq = 0;
+                for (int64_t k = p; k < q; ++k)
+                    if (buf[k] == '=') { if (eq < 0) eq = k; ++n_eq; }
+                if (n_eq != 1) { g_io_error = "FASTA header fields must look like key=value"; return -2; }
+                if (eq - p == 4 && memcmp(buf + p, "pham", 4) == 0) {
+                    const int64_t vlen = q - (eq + 1);
+                    if (n_name + vlen > name_cap) { g_io_error = "pc_scan_fasta: name buffer too small"; return -4; }
+                    memcpy(name_out + n_name, buf + eq + 1, (size_t)vlen);
+                    fields[4 * rec + 0] = n_name;
+                    fields[4 * rec + 1] = n_name + vlen;
+                    n_name += vlen;
+                    found = true;
+                }
+                if (q >= hend) break;
+                p = q + 1;
+            }
+            if (!found) { g_io_error = "unable to get pham from FASTA header"; return -3; }
+            fields[4 * rec + 2] = fields[4 * rec + 3] = n_seq;
+        } else {
+            if (rec < 0) { g_io_error = "records in FASTA files must start with '>'"; return -1; }
+            const int64_t slen = end - pos;
+            if (n_seq + slen > seq_cap) { g_io_error = "pc_scan_fasta: sequence buffer too small"; return -4; }
+            for (int64_t k = 0; k < slen; ++k) {
+                const unsigned char c = (unsigned char)buf[pos + k];
+                if (c >= 0x80) { g_io_error = "translations must be made of single-byte characters"; return -5; }
+                seq_out[n_seq + k] = c;
+            }
+            n_seq += slen;
+            fields[4 * rec + 3] = n_seq;
+        }
+        pos = next;
+    }
+    used[0] = n_name;
+    used[1] = n_seq;
+    return rec + 1;
+}

@@ -8,6 +8,9 @@ def read_fasta(filename):
     header, chunks = None, []
     with open(filename, "r") as handle:
         first = True
+        if handle.read(1) == "":         # upstream: next() on an empty file inside a generator (fasta.py:17)
+            raise RuntimeError("generator raised StopIteration")
+        handle.seek(0)
         for line in handle:
             if first and line[0] != ">":
                 raise ValueError("records in FASTA files must start with '>'")

@@ -86,23 +86,67 @@ class SymMatrix:
         """Per node, ``average`` of every weight it appears in while iterating the
         upper half -- the diagonal is seen as source AND target, so it counts twice
         (matrix.py:81-96); summed in the reference's order so ties break alike."""
-        full = self.to_ndarray()
-        out = {}
-        for k, name in enumerate(self._nodes):
-            row = full[k]
-            weights = list(row[:k]) + [row[k], row[k]] + list(row[k + 1:])
-            out[name] = average([float(w) for w in weights])
-        return out
+        return {name: self._reference_average(k) for k, name in enumerate(self._nodes)}
+
+    def _row_micro(self, k):
+        """Row k (traversal order) of the full symmetric matrix, int32 micro-units."""
+        order = np.fromiter((self._index[x] for x in self._nodes), dtype=np.int64, count=len(self._nodes))
+        p = order[k]
+        lo, hi = np.minimum(order, p), np.maximum(order, p)
+        return self._micro[self._offsets[lo] + (hi - lo)]
+
+    def _reference_average(self, k):
+        """The float the reference computes for node k: ``statistics.average`` over the list
+        [w(0,k) .. w(k-1,k), w(k,k), w(k,k), w(k,k+1) ..] in that order (matrix.py:84-96)."""
+        row = self._row_micro(k)
+        if (row == _UNSET).any():
+            raise TypeError("unsupported operand type(s): matrix holds unset weights")
+        vals = (row.astype(np.float64) / 1e6).tolist()
+        return average(vals[:k] + [vals[k], vals[k]] + vals[k + 1:])
+
+    def _central(self, smallest, first):
+        """(name, average) of the node with the smallest / largest average weight, ties
+        resolved as ``sorted(...)[0]`` (first in traversal order) or ``[-1]`` (last) would.
+
+        No dense N x N and no per-edge Python: exact integer row sums come from ONE pass over
+        the packed triangle in the library (pc_node_sums).  Two nodes whose integer sums differ
+        (by >= 1e-6) cannot be reordered by the float noise of upstream's summation (< 1e-11 at
+        50 000 nodes), so only nodes with EQUAL integer sums are ranked with upstream's own
+        float arithmetic."""
+        n = len(self._store)
+        sums = np.empty(n, dtype=np.int64)
+        lib = _native.load_library()
+        micro = np.ascontiguousarray(self._micro)
+        if lib.pc_node_sums(n, micro.ctypes.data, sums.ctypes.data):
+            raise TypeError("unsupported operand type(s): matrix holds unset weights")
+        order = np.fromiter((self._index[x] for x in self._nodes), dtype=np.int64, count=n)
+        t_sums = sums[order]
+        best = t_sums.min() if smallest else t_sums.max()
+        tied = np.nonzero(t_sums == best)[0].tolist()
+        ranked = [(self._reference_average(k), k) for k in tied]
+        # sorted() is stable: among equal averages [0] is the first in traversal order, [-1] the last
+        values = [v for v, _ in ranked]
+        target = min(values) if smallest else max(values)
+        ks = [k for v, k in ranked if v == target]
+        k = ks[0] if first else ks[-1]
+        return self._nodes[k], self._reference_average(k)
 
     @property
     def medoid(self):
-        ranked = sorted(self._node_averages().items(), key=lambda x: x[1])
-        return ranked[0] if self.is_distance else ranked[-1]
+        """matrix.py:81-104: distance -> smallest average, ``sorted(...)[0]``; similarity ->
+        largest, ``sorted(...)[-1]``."""
+        if len(self._store) == 0:
+            raise IndexError("list index out of range")
+        return self._central(smallest=True, first=True) if self.is_distance else \
+            self._central(smallest=False, first=False)
 
     @property
     def anti_medoid(self):
-        ranked = sorted(self._node_averages().items(), key=lambda x: x[1])
-        return ranked[-1] if self.is_distance else ranked[0]
+        """matrix.py:106-127."""
+        if len(self._store) == 0:
+            raise IndexError("list index out of range")
+        return self._central(smallest=False, first=False) if self.is_distance else \
+            self._central(smallest=True, first=True)
 
     @property
     def statistics(self):

@@ -219,6 +219,118 @@ def unpack_genomes(table):
     return genomes
 
 
+def _table_from_rows(names, row_genome, row_name, n_names, name_of, lens, residues_of, with_sequences):
+    """Rows (genome id, pham-name id, translation length) in input order -> PackedTable with the
+    semantics of the reference loaders followed by ``pack_genomes``: entries = distinct
+    (genome, pham) in order of first appearance inside the genome, paralogs in input order, pham
+    ids in the order ``pack_genomes`` would meet them.  ``name_of(ids)`` -> list of pham names;
+    ``residues_of(row_order, lens)`` -> uint8 arena of the rows' translations in that order."""
+    n_genomes = len(names)
+    key = row_genome.astype(np.int64) * max(n_names, 1) + row_name
+    uniq, first_row, row_entry = np.unique(key, return_index=True, return_inverse=True)
+    entry_genome = uniq // max(n_names, 1)
+    entry_name = uniq % max(n_names, 1)
+    order = np.lexsort((first_row, entry_genome))
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order))
+    row_slot = rank[row_entry]
+    row_order = np.argsort(row_slot, kind="stable")          # genes in CSR-entry order, input order inside
+    copies = np.bincount(row_slot, minlength=len(order)).astype(np.uint32)
+    len_sum = np.bincount(row_slot, weights=lens, minlength=len(order)).astype(np.uint32)
+    ptr = np.zeros(n_genomes + 1, dtype=np.int64)
+    np.cumsum(np.bincount(entry_genome, minlength=n_genomes), out=ptr[1:])
+    # pham ids in the order pack_genomes would meet them (genome by genome, CSR order)
+    csr_name = entry_name[order]
+    met, met_at = np.unique(csr_name, return_index=True)
+    vocab_rank = np.empty(max(n_names, 1), dtype=np.int64)
+    vocab_order = met[np.argsort(met_at, kind="stable")]      # interned name ids in vocabulary order
+    vocab_rank[vocab_order] = np.arange(len(vocab_order))
+    pham_id = vocab_rank[csr_name].astype(np.int32)
+    table = PackedTable(names, name_of(vocab_order), ptr, pham_id, copies, len_sum)
+    if with_sequences:
+        glen = np.ascontiguousarray(lens[row_order], dtype=np.int64)
+        table.seq_off = np.concatenate(([0], np.cumsum(glen))).astype(np.int64)
+        table.residues = residues_of(row_order, glen)
+    return table
+
+
+def table_from_fasta_dir(dirpath, with_sequences=True):
+    """A directory of single-genome FASTA files straight into a PackedTable, without Genome
+    dicts.  Same semantics as ``load_genomes_from_fasta_dir``
+    (scripts/phamclust.py:50-83: suffix .fasta/.faa/.fa, name = file stem, duplicate stem ->
+    ValueError, directory order) + ``Genome.load`` (genome.py:66-83: first ``pham=`` field wins,
+    none -> GenomeLoadError) + ``read_fasta`` (fasta.py:4-40: lines rstrip()ped and joined)
+    followed by ``pack_genomes``.  Every file is scanned once in the library (pc_scan_fasta);
+    Python only loops over FILES."""
+    import logging
+    import pathlib
+    from phamclust_b200 import _native
+    from phamclust_b200.genome import GenomeLoadError
+    lib = _native.load_library()
+    names, seen = [], set()
+    row_genome, name_fields, lens_all, name_blobs, seq_blobs = [], [], [], [], []
+    name_base = 0
+    for f in pathlib.Path(dirpath).iterdir():
+        if f.suffix not in (".fasta", ".faa", ".fa"):
+            logging.debug(f"{f} does not appear to be FASTA - skipping")
+            continue
+        if f.is_dir():
+            logging.debug(f"{f} appears to be a directory - skipping")
+            continue
+        if f.stem in seen:
+            raise ValueError(f"duplicate genome name detected {f.stem}")
+        seen.add(f.stem)
+        data = f.read_bytes()
+        if not data:                     # upstream: next() on an empty file inside a generator (fasta.py:17)
+            raise RuntimeError("generator raised StopIteration")
+        max_rec = data.count(b">") + 1
+        fields = np.empty((max_rec, 4), dtype=np.int64)
+        name_out = np.empty(len(data) + 1, dtype=np.uint8)
+        seq_out = np.empty(len(data) + 1, dtype=np.uint8)
+        used = np.zeros(2, dtype=np.int64)
+        rc = int(lib.pc_scan_fasta(data, len(data), max_rec, fields.ctypes.data, name_out.ctypes.data,
+                                   len(name_out), seq_out.ctypes.data, len(seq_out), used.ctypes.data))
+        if rc < 0:
+            msg = lib.pc_io_last_error().decode()
+            raise (GenomeLoadError if rc == -3 else ValueError)(msg)
+        fields = fields[:rc]
+        g = len(names)
+        names.append(f.stem)
+        row_genome.append(np.full(rc, g, dtype=np.int32))
+        name_fields.append(fields[:, 0:2] + name_base)
+        lens_all.append(fields[:, 3] - fields[:, 2])
+        name_blobs.append(name_out[:int(used[0])].tobytes())
+        seq_blobs.append(seq_out[:int(used[1])].copy() if with_sequences else None)
+        name_base += int(used[0])
+    rows = int(sum(len(x) for x in row_genome))
+    row_genome = np.concatenate(row_genome) if row_genome else np.zeros(0, dtype=np.int32)
+    lens = np.concatenate(lens_all) if lens_all else np.zeros(0, dtype=np.int64)
+    blob = b"".join(name_blobs)
+    # pham names interned in first-seen order by the library (the TSV helper: column 1 of a
+    # 6-wide field table)
+    six = np.zeros((max(rows, 1), 6), dtype=np.int64)
+    if rows:
+        six[:rows, 2:4] = np.concatenate(name_fields)
+    row_name = np.empty(rows, dtype=np.int32)
+    first_name_row = np.empty(max(rows, 1), dtype=np.int64)
+    n_names = int(lib.pc_tsv_intern(blob, rows, six.ctypes.data, 1, row_name.ctypes.data,
+                                    first_name_row.ctypes.data)) if rows else 0
+    if n_names < 0:
+        raise ValueError(lib.pc_io_last_error().decode())
+
+    def name_of(ids):
+        return [blob[b:e].decode() for b, e in six[first_name_row[ids], 2:4].tolist()]
+
+    def residues_of(row_order, glen):
+        arena = np.concatenate([b for b in seq_blobs if b is not None]) if seq_blobs else np.zeros(0, dtype=np.uint8)
+        start = np.concatenate(([0], np.cumsum(lens)))[:-1]          # rows are laid out in input order
+        out_off = np.concatenate(([0], np.cumsum(glen)))
+        src = np.repeat(start[row_order] - out_off[:-1], glen) + np.arange(int(out_off[-1]))
+        return arena[src]
+
+    return _table_from_rows(names, row_genome, row_name, n_names, name_of, lens, residues_of, with_sequences)
+
+
 def table_from_tsv(filepath, with_sequences=True):
     """2/3-column TSV straight into a PackedTable, without materialising Genome
     dicts.  Same semantics as ``load_genomes_from_tsv``
@@ -248,40 +360,19 @@ def table_from_tsv(filepath, with_sequences=True):
     if n_genomes < 0 or n_names < 0:
         raise ValueError(lib.pc_io_last_error().decode())
     names = [data[b:e].decode() for b, e in fields[first_genome_row[:n_genomes], 0:2].tolist()]
-    # entries = distinct (genome, pham); CSR order = by genome (first seen), then by the first
-    # row of the pham inside that genome
-    key = row_genome.astype(np.int64) * max(n_names, 1) + row_name
-    uniq, first_row, row_entry = np.unique(key, return_index=True, return_inverse=True)
-    entry_genome = uniq // max(n_names, 1)
-    entry_name = uniq % max(n_names, 1)
-    order = np.lexsort((first_row, entry_genome))
-    rank = np.empty(len(order), dtype=np.int64)
-    rank[order] = np.arange(len(order))
-    row_slot = rank[row_entry]
-    row_order = np.argsort(row_slot, kind="stable")          # genes in CSR-entry order, file order inside
-    copies = np.bincount(row_slot, minlength=len(order)).astype(np.uint32)
     t0, t1 = fields[:, 4], fields[:, 5]
     lens = np.where(t0 < 0, 1, t1 - t0)
-    len_sum = np.bincount(row_slot, weights=lens, minlength=len(order)).astype(np.uint32)
-    ptr = np.zeros(n_genomes + 1, dtype=np.int64)
-    np.cumsum(np.bincount(entry_genome, minlength=n_genomes), out=ptr[1:])
-    # pham ids in the order pack_genomes would meet them (genome by genome, CSR order)
-    csr_name = entry_name[order]
-    met, met_at = np.unique(csr_name, return_index=True)
-    vocab_rank = np.empty(max(n_names, 1), dtype=np.int64)
-    vocab_order = met[np.argsort(met_at, kind="stable")]      # interned name ids in vocabulary order
-    vocab_rank[vocab_order] = np.arange(len(vocab_order))
-    pham_id = vocab_rank[csr_name].astype(np.int32)
-    phams = [data[b:e].decode() for b, e in fields[first_name_row[vocab_order], 2:4].tolist()]
-    table = PackedTable(names, phams, ptr, pham_id, copies, len_sum)
-    if with_sequences:
-        glen = np.ascontiguousarray(lens[row_order], dtype=np.int64)
-        table.seq_off = np.concatenate(([0], np.cumsum(glen))).astype(np.int64)
+
+    def name_of(ids):
+        return [data[b:e].decode() for b, e in fields[first_name_row[ids], 2:4].tolist()]
+
+    def residues_of(row_order, glen):
         starts = np.ascontiguousarray(t0[row_order], dtype=np.int64)
-        res = np.empty(int(table.seq_off[-1]), dtype=np.uint8)
+        res = np.empty(int(glen.sum()), dtype=np.uint8)
         # every translation's bytes ("M" for 2-column rows), one memcpy per gene in the library
         if lib.pc_gather_fields(data, len(starts), starts.ctypes.data, glen.ctypes.data, ord("M"),
                                 res.ctypes.data):
             raise ValueError(lib.pc_io_last_error().decode())
-        table.residues = res
-    return table
+        return res
+
+    return _table_from_rows(names, row_genome, row_name, n_names, name_of, lens, residues_of, with_sequences)

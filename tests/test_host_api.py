@@ -468,3 +468,93 @@ def test_take_genomes_is_a_random_access_subset():
     assert [g.name for g in got] == [genomes[i].name for i in idx]
     for k, i in enumerate(idx):
         assert got[k].phams == genomes[i].phams
+
+
+def test_fasta_dir_streams_into_the_same_table(tmp_path, reference):
+    """table_from_fasta_dir (files scanned in the library, no Genome dicts) == the reference
+    loader (scripts/phamclust.py:50-83 -> Genome.load -> read_fasta) followed by pack_genomes:
+    wrapped and unwrapped sequence lines, CRLF, trailing blanks, extra header fields, paralogs,
+    non-FASTA files and sub-directories skipped; the loader's error cases keep their types."""
+    import random
+    from phamclust_b200 import packing
+    from phamclust_b200.genome import GenomeLoadError
+    rows = testdata.genome_rows(seed=8, n_genomes=10, n_phams=18, paralog_p=0.4)
+    genomes = testdata.rows_to_genomes(rows, cls=Genome)
+    rng = random.Random(1)
+    for g in genomes:
+        with open(tmp_path / f"{g.name}{rng.choice(['.faa', '.fasta', '.fa'])}", "w", newline="") as fh:
+            for pham, seqs in g.phams.items():
+                for k, sq in enumerate(seqs):
+                    nl = rng.choice(["\n", "\r\n"])
+                    fh.write(f">name={g.name}|pham={pham}|n={k}  {nl}")
+                    width = rng.choice([7, 60, 10 ** 6])
+                    for i in range(0, len(sq), width):
+                        fh.write(sq[i:i + width] + rng.choice(["", " ", "\t"]) + nl)
+    (tmp_path / "notes.txt").write_text("not fasta")
+    (tmp_path / "sub.fa").mkdir()
+    ours = load_genomes_from_fasta_dir(tmp_path)
+    # the reference's Genome.load + read_fasta on the same files (its directory loader sits in
+    # scripts/phamclust.py, which needs plotly to import)
+    for g in ours:
+        theirs = reference.genome.Genome(g.name)
+        theirs.load(next(f for f in tmp_path.iterdir() if f.stem == g.name and f.is_file()))
+        assert theirs.phams == g.phams
+    want = packing.pack_genomes(ours)
+    for with_sequences in (True, False):
+        got = packing.table_from_fasta_dir(tmp_path, with_sequences)
+        assert got.names == want.names and got.phams == want.phams
+        for key in ("genome_ptr", "pham_id", "copies", "len_sum") + (("seq_off", "residues") if with_sequences else ()):
+            assert np.array_equal(getattr(got, key), getattr(want, key)), key
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    (bad / "a.fa").write_text(">name=a|n=1\nMK\n")
+    with pytest.raises(GenomeLoadError):
+        packing.table_from_fasta_dir(bad)
+    (bad / "a.fa").write_text("MK\n>pham=x\nMK\n")
+    with pytest.raises(ValueError):
+        packing.table_from_fasta_dir(bad)
+    (bad / "a.fa").write_text(">pham=x|junk\nMK\n")          # upstream stops at the first pham= field
+    assert packing.table_from_fasta_dir(bad).phams == ["x"]
+    (bad / "a.fa").write_text(">junk|pham=x\nMK\n")
+    with pytest.raises(ValueError):
+        packing.table_from_fasta_dir(bad)
+    (bad / "a.fa").write_text(">junk=1=2|pham=x\nMK\n")
+    with pytest.raises(ValueError):
+        packing.table_from_fasta_dir(bad)
+    (bad / "a.fa").write_text(">pham=x\nMK\n")
+    (bad / "a.faa").write_text(">pham=x\nMK\n")
+    with pytest.raises(ValueError):
+        packing.table_from_fasta_dir(bad)
+
+
+def test_medoid_on_the_packed_triangle_equals_the_reference(reference):
+    """medoid / anti_medoid from exact integer row sums of the packed triangle (pc_node_sums) with
+    upstream's float arithmetic only among tied nodes: same (name, value) as the verbatim
+    reference class (matrix.py:81-127) for distances and similarities, permuted traversal
+    order, exact ties (first / last in traversal order as ``sorted`` would) and single nodes."""
+    ref_matrix = reference.matrix
+    rng = np.random.default_rng(12)
+    for n, tie in ((1, False), (2, False), (7, False), (40, False), (25, True), (300, False)):
+        names = [f"g{k:03d}" for k in range(n)]
+        if tie:
+            vals = rng.integers(0, 4, size=(n, n)) * 250000          # lots of equal sums
+        else:
+            vals = rng.integers(0, 1000001, size=(n, n))
+        vals = np.triu(vals, 1)
+        vals = vals + vals.T
+        for is_distance in (True, False):
+            diag = 0 if is_distance else 1000000
+            ours = SymMatrix(list(names), is_distance=is_distance)
+            theirs = ref_matrix.SymMatrix(list(names), is_distance=is_distance)
+            for i in range(n):
+                for j in range(i, n):
+                    w = (diag if i == j else int(vals[i, j])) / 1e6
+                    ours.set_weight(names[i], names[j], w)
+                    theirs.set_weight(names[i], names[j], w)
+            for order in (list(names), list(rng.permutation(names))):
+                if n > 2 and order != names:
+                    ours.reorder(list(order))
+                    theirs.reorder(list(order))
+                assert ours.nodes == theirs.nodes
+                assert ours.medoid == theirs.medoid, (n, tie, is_distance)
+                assert ours.anti_medoid == theirs.anti_medoid, (n, tie, is_distance)
