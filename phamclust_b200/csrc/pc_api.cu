@@ -196,7 +196,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_entry_genome, &ctx->d_pham_id, &ctx->d_pham_col, &ctx->d_copies, &ctx->d_len_sum,
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
                       &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_i8_occ, &ctx->d_i8_steps, &ctx->d_codes,
-                      &ctx->d_p2_tiles, &ctx->d_p2_masks, &ctx->d_p2_keys, &ctx->d_p2_ids, &ctx->d_p2_temp, &ctx->d_dest,
+                      &ctx->d_p2_tiles, &ctx->d_p2_masks, &ctx->d_p2_keys, &ctx->d_p2_ids, &ctx->d_p2_temp, &ctx->d_p2_sync, &ctx->d_dest,
                       &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_canon, &ctx->d_gene_hi, &ctx->d_subtab[0],
                       &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
                       &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
@@ -272,7 +272,13 @@ static int host_threads(int64_t work)
         if (t >= 1) return std::min(t, 64);
     }
     if (work < 100000) return 1;
-    const unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = std::thread::hardware_concurrency();
+    // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char *lws = getenv("LOCAL_WORLD_SIZE")) {
+        const int ranks = atoi(lws);
+        if (ranks > 1) hw = std::max(1u, hw / (unsigned)ranks);
+        return (int)std::max(1u, std::min(8u, hw));
+    }
     return (int)std::max(1u, std::min(8u, hw / 2));
 }
 
@@ -537,6 +543,7 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
     std::vector<uint8_t> owned;              // per gene (partial loads only)
     if (partial) {
         deal_phams(ctx, n_parts);
+        dbg_mark("seqs: phams dealt");
         owned.assign((size_t)n_genes, 0);
         const int To = host_threads(ctx->nnz);
         run_threads(To, [&](int t) {
@@ -657,6 +664,7 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
             }
         });
         gene_off[n_genes] = cursor;
+        dbg_mark("seqs: offsets + staging");
         for (int t = 0; t < T; ++t)
             if (chk[t].err_at != INT64_MAX && (!bad || chk[t].err_at < bad->err_at)) bad = &chk[t];
         if (bad) {

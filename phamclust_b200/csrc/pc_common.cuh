@@ -185,7 +185,7 @@ struct pc_ctx {
     int64_t i8_dense_steps = 0;                    // ... and what the dense K schedule would have issued
     DevBuf d_i8_steps;                             // u64: 128 x 256 x 128 MMA groups issued since the reset
     int i8_kind = -1; int64_t i8_K = 0, i8_rows = 0;
-    DevBuf d_p2_tiles, d_p2_masks, d_p2_keys, d_p2_ids, d_p2_temp;   // tile queue of the persistent pair kernel
+    DevBuf d_p2_tiles, d_p2_masks, d_p2_keys, d_p2_ids, d_p2_temp, d_p2_sync;   // tile queue of the persistent pair kernel
 
     // ---- sequences ----
     int64_t n_genes = 0;

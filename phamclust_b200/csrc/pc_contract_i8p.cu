@@ -69,6 +69,9 @@ struct P2Args {
     const uint32_t *masks;
     int n_tiles;
     unsigned long long *tile_steps;
+    // rounds in lock step (L2 reuse): sync[0] = sum of n_steps over the queue (written by the
+    // build kernel), sync[1 + r] = producers that have reached round r
+    unsigned int *sync;
     EpilogueArgs ep;
 };
 
@@ -84,7 +87,8 @@ __device__ __forceinline__ constexpr uint32_t p2_idesc()
 __global__ void p2_build_tiles_kernel(const uint32_t *__restrict__ occ, int occ_words, int occ_shift,
                                       int64_t kb_per_seg, int n_pass, int tile_row0, int n_row_tiles,
                                       int n_col_tiles, P2Tile *__restrict__ tiles, uint32_t *__restrict__ masks,
-                                      uint32_t *__restrict__ keys, int32_t *__restrict__ ids, int *__restrict__ counter)
+                                      uint32_t *__restrict__ keys, int32_t *__restrict__ ids, int *__restrict__ counter,
+                                      unsigned int *__restrict__ total_steps)
 {
     // one warp per candidate tile (bi, bj); tiles strictly below the diagonal do not exist
     const int lane = threadIdx.x & 31;
@@ -123,6 +127,7 @@ __global__ void p2_build_tiles_kernel(const uint32_t *__restrict__ occ, int occ_
         const uint32_t w = (uint32_t)min(t.n_steps >> P2_ORDER_SHIFT, 1023);
         keys[slot] = (blk << 10) | w;
         ids[slot] = slot;
+        if (t.n_steps) atomicAdd(total_steps, (unsigned int)min(t.n_steps, 1 << 16));
     }
 }
 
@@ -221,7 +226,27 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
             int s = 0;
             uint32_t ph = 0;
             const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0);       // the LEADER's full barriers
+            // Rounds in lock step.  The tiles of one round form a compact block of the tile grid
+            // and share operand strips, but a strip only stays in L2 for a window of K (a
+            // 256-genome strip is 15 MB at C3, 51 MB at C5): the sharing is real only while the
+            // pairs stream the same K range at the same time.  Left alone the pairs drift apart
+            // by whole tiles within a few rounds (C5, 8 GPUs: DRAM-bound at 45 % tensor), so every
+            // producer waits at the start of a round until all producers of the grid have issued
+            // the last load of the previous one.  All CTAs are co-resident (one per SM), so the
+            // spin cannot deadlock.  Launches that hardly use the tensor core (clustered tables:
+            // most tiles are empty) skip it -- there a round lasts microseconds.
+            const bool lock_step = a.sync[0] >= (unsigned int)a.n_tiles * 64u;
+            const unsigned int n_producers = 2u * (unsigned int)n_clusters;
             for (int round = 0; round * n_clusters < a.n_tiles; ++round) {
+                if (lock_step) {
+                    unsigned int *ctr = a.sync + 1 + round;
+                    atomicAdd(ctr, 1u);
+                    unsigned int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+                        if (seen < n_producers) __nanosleep(200);
+                    } while (seen < n_producers);
+                }
                 const int q = p2_queue_slot(round, cluster, n_clusters);
                 if (q >= a.n_tiles) continue;
                 const P2Tile t = a.tiles[a.order[q]];
@@ -437,6 +462,8 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
     PC_TRY(devbuf_reserve(ctx, ctx->d_p2_masks, (size_t)max_tiles * occ_words * sizeof(uint32_t)));
     PC_TRY(devbuf_reserve(ctx, ctx->d_p2_keys, (size_t)max_tiles * 2 * sizeof(uint32_t) + 16));
     PC_TRY(devbuf_reserve(ctx, ctx->d_p2_ids, (size_t)max_tiles * 2 * sizeof(int32_t)));
+    const size_t sync_words = (size_t)max_tiles + 8;              // >= 1 + number of rounds
+    PC_TRY(devbuf_reserve(ctx, ctx->d_p2_sync, sync_words * sizeof(unsigned int)));
     uint32_t *keys_in = ctx->d_p2_keys.as<uint32_t>(), *keys_out = keys_in + max_tiles;
     int *counter = reinterpret_cast<int *>(keys_in + 2 * max_tiles);
     int32_t *ids_in = ctx->d_p2_ids.as<int32_t>(), *ids_out = ids_in + max_tiles;
@@ -453,13 +480,15 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
 
     PC_TRY(pc_stage_begin(ctx, PC_T_CONTRACT));
     PC_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+    PC_CUDA(ctx, cudaMemsetAsync(ctx->d_p2_sync.p, 0, sync_words * sizeof(unsigned int), ctx->stream));
     {
         const int64_t threads = cand * 32;
         const int grid = (int)((threads + 255) / 256);
         p2_build_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_i8_occ.as<uint32_t>(), occ_words, occ_shift,
                                                             kb_per_seg, n_pass, tile_row0, n_row_tiles, n_col_tiles,
                                                             ctx->d_p2_tiles.as<P2Tile>(), ctx->d_p2_masks.as<uint32_t>(),
-                                                            keys_in, ids_in, counter);
+                                                            keys_in, ids_in, counter,
+                                                            ctx->d_p2_sync.as<unsigned int>());
         PC_CUDA(ctx, cudaGetLastError());
     }
     PC_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->d_p2_temp.p, temp_bytes, keys_in, keys_out, ids_in,
@@ -474,6 +503,7 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
     args.masks = ctx->d_p2_masks.as<uint32_t>();
     args.n_tiles = (int)max_tiles;
     args.tile_steps = ctx->d_i8_steps.as<unsigned long long>();
+    args.sync = ctx->d_p2_sync.as<unsigned int>();
     args.ep = ep;
     PC_CUDA(ctx, cudaFuncSetAttribute(i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
     // one CTA pair per TPC; fewer when there are fewer tiles than pairs
