@@ -191,6 +191,23 @@ int pc_matrix_rows_owned(pc_ctx *ctx, int metric, int as_distance, int ppos,
                          const uint64_t *acc_rows_dev, int32_t *out,
                          int out_on_device);
 
+/*
+ * The triangle kept in HBM for its first consumer.  What the pipeline does
+ * next is thresholded clustering (scripts/phamclust.py:300-317, clustering.py:27); these calls
+ * answer its questions without shipping N(N+1)/2 values: pc_matrix_resident computes into a
+ * ctx-owned device buffer (valid until the next pc_matrix_resident / pc_load_table);
+ * pc_resident_threshold_edges returns the off-diagonal pairs (i < j, storage order) with weight
+ * <= max_micro as int32 pairs -- *n_edges is the number FOUND, which may exceed cap (call again
+ * with more room); pc_resident_gather reads entries by packed index; pc_resident_fetch copies the
+ * whole triangle after all.  Host pointers.
+ */
+int pc_matrix_resident(pc_ctx *ctx, int metric, int as_distance, int ppos);
+int pc_resident_threshold_edges(pc_ctx *ctx, int32_t max_micro, int64_t cap,
+                                int32_t *edges_host /* 2 * cap */, int64_t *n_edges);
+int pc_resident_gather(pc_ctx *ctx, int64_t n_idx, const int64_t *tri_index_host,
+                       int32_t *out_host);
+int pc_resident_fetch(pc_ctx *ctx, int32_t *out_host);
+
 /* -------- integer test hooks (bit-exact parity) ------------------------- */
 /*
  * Numerators the reference computes as Python ints, packed triangle, host:
@@ -218,6 +235,16 @@ int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks,
  * rounding against CPython's round() on the GPU itself.
  */
 int pc_debug_round6(pc_ctx *ctx, int64_t n, const double *x, int32_t *out);
+
+/*
+ * The fused epilogue of gcs/jc/pocp/af (metrics.py:45-53, 75-80, 110-115, 152-157 +
+ * matrix.py:323) on caller-chosen operands: out = the production path (integer arithmetic, fp64
+ * only on exact ties), out_f64 = the fp64 path that restates CPython's arithmetic; the tests
+ * compare both with CPython itself.  Host memory.
+ */
+int pc_debug_metric_micro(pc_ctx *ctx, int metric, int as_distance, int64_t n,
+                          const int32_t *numer, const int32_t *den_i,
+                          const int32_t *den_j, int32_t *out, int32_t *out_f64);
 
 /* -------- measurement --------------------------------------------------- */
 enum {

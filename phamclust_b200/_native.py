@@ -23,7 +23,8 @@ EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_strea
            "pc_set_engine", "pc_set_dp_mode", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",
            "pc_matrix_rows", "pc_align_accumulate", "pc_numerators", "pc_load_sequences_part", "pc_align_units",
            "pc_align_contributions", "pc_accumulate_records", "pc_matrix_rows_owned",
-           "pc_alignment_identities", "pc_debug_round6", "pc_timings", "pc_counters", "pc_reset_counters", "pc_stat",
+           "pc_matrix_resident", "pc_resident_threshold_edges", "pc_resident_gather", "pc_resident_fetch",
+           "pc_alignment_identities", "pc_debug_round6", "pc_debug_metric_micro", "pc_timings", "pc_counters", "pc_reset_counters", "pc_stat",
            "pc_write_matrix", "pc_parse_squareform", "pc_scan_tsv", "pc_tsv_intern", "pc_gather_fields",
            "pc_dense_from_micro", "pc_node_sums", "pc_scan_fasta",
            "pc_io_last_error")
@@ -63,8 +64,13 @@ def load_library():
     lib.pc_align_contributions.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     lib.pc_accumulate_records.argtypes = [vp, i64, vp, i64, vp]
     lib.pc_matrix_rows_owned.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, i32]
+    lib.pc_matrix_resident.argtypes = [vp, i32, i32, i32]
+    lib.pc_resident_threshold_edges.argtypes = [vp, i32, i64, vp, vp]
+    lib.pc_resident_gather.argtypes = [vp, i64, vp, vp]
+    lib.pc_resident_fetch.argtypes = [vp, vp]
     lib.pc_alignment_identities.argtypes = [vp, i64, vp, vp, vp]
     lib.pc_debug_round6.argtypes = [vp, i64, vp, vp]
+    lib.pc_debug_metric_micro.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp]
     lib.pc_timings.argtypes = [vp, vp, i32]
     lib.pc_counters.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.pc_reset_counters.argtypes = [vp]
@@ -163,6 +169,7 @@ class Context:
         self._check(self._lib.pc_load_table(self._h, len(gp) - 1, table.n_phams, gp.ctypes.data,
                                             pid.ctypes.data, cp.ctypes.data, ls.ctypes.data))
         self.n = len(gp) - 1
+        self.resident_generation = getattr(self, "resident_generation", 0) + 1   # the resident matrix is gone
 
     def load_sequences(self, table, part=0, n_parts=1):
         """All translations, or (``n_parts`` > 1) only the genes of the phams partition ``part``
@@ -250,6 +257,37 @@ class Context:
             row_end, ctypes.c_void_p(acc_rows_ptr or 0), out.ctypes.data, 0))
         return out
 
+    # ---- the triangle kept in HBM ---------------------------------------------------
+    def matrix_resident(self, metric, as_distance=True, ppos=False):
+        """Compute the whole triangle into the ctx's own device buffer (no D2H); returns a
+        generation number that the queries below check."""
+        self._check(self._lib.pc_matrix_resident(self._h, _metric_id(metric), int(bool(as_distance)), int(bool(ppos))))
+        self.resident_generation = getattr(self, "resident_generation", 0) + 1
+        return self.resident_generation
+
+    def resident_threshold_edges(self, max_micro):
+        """(i, j) storage indices, i < j, of the pairs with weight <= max_micro; int32 [k, 2]."""
+        cap = max(1024, 4 * self.n)
+        while True:
+            edges = np.empty((cap, 2), dtype=np.int32)
+            found = ctypes.c_int64()
+            self._check(self._lib.pc_resident_threshold_edges(self._h, int(max_micro), cap, edges.ctypes.data,
+                                                              ctypes.byref(found)))
+            if found.value <= cap:
+                return edges[:found.value]
+            cap = found.value
+
+    def resident_gather(self, tri_index):
+        idx = np.ascontiguousarray(tri_index, dtype=np.int64)
+        out = np.empty(idx.size, dtype=np.int32)
+        self._check(self._lib.pc_resident_gather(self._h, idx.size, idx.ctypes.data, out.ctypes.data))
+        return out
+
+    def resident_fetch(self):
+        out = np.empty(tri_len(self.n), dtype=np.int32)
+        self._check(self._lib.pc_resident_fetch(self._h, out.ctypes.data))
+        return out
+
     # ---- integer hooks -----------------------------------------------------------
     def numerators(self, metric, ppos=False):
         count = tri_len(self.n)
@@ -272,6 +310,17 @@ class Context:
         out = np.empty(x.size, dtype=np.int32)
         self._check(self._lib.pc_debug_round6(self._h, x.size, x.ctypes.data, out.ctypes.data))
         return out
+
+    def debug_metric_micro(self, metric, as_distance, numer, den_i, den_j):
+        """(production path, fp64 path) of the cheap-metric epilogue on the given operands."""
+        a = np.ascontiguousarray(numer, dtype=np.int32)
+        b = np.ascontiguousarray(den_i, dtype=np.int32)
+        c = np.ascontiguousarray(den_j, dtype=np.int32)
+        out, out64 = np.empty(a.size, dtype=np.int32), np.empty(a.size, dtype=np.int32)
+        self._check(self._lib.pc_debug_metric_micro(self._h, _metric_id(metric), int(bool(as_distance)), a.size,
+                                                    a.ctypes.data, b.ctypes.data, c.ctypes.data,
+                                                    out.ctypes.data, out64.ctypes.data))
+        return out, out64
 
     # ---- measurement ---------------------------------------------------------------
     def timings(self):

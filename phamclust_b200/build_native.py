@@ -13,7 +13,7 @@ import sys
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libphamclust_b200.so"
-SOURCES = ["pc_api.cu", "pc_contract_popc.cu", "pc_contract_i8.cu", "pc_contract_i8p.cu", "pc_align.cu", "pc_gather.cu",
+SOURCES = ["pc_api.cu", "pc_contract_popc.cu", "pc_contract_i8.cu", "pc_contract_i8p.cu", "pc_align.cu", "pc_gather.cu", "pc_resident.cu",
            "pc_io.cu", "pc_dedup.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",

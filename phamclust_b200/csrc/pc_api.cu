@@ -197,6 +197,7 @@ extern "C" void pc_destroy(pc_ctx *ctx)
                       &ctx->d_den_phams, &ctx->d_den_genes, &ctx->d_den_len, &ctx->d_bits,
                       &ctx->d_planes, &ctx->d_terms, &ctx->d_numer, &ctx->d_i8, &ctx->d_i8_occ, &ctx->d_i8_steps, &ctx->d_codes,
                       &ctx->d_p2_tiles, &ctx->d_p2_masks, &ctx->d_p2_keys, &ctx->d_p2_ids, &ctx->d_p2_temp, &ctx->d_p2_sync, &ctx->d_dest,
+                      &ctx->d_resident, &ctx->d_res_edges, &ctx->d_res_idx, &ctx->d_res_vals,
                       &ctx->d_gene_off, &ctx->d_gene_len, &ctx->d_raw, &ctx->d_raw_off, &ctx->d_lut, &ctx->d_canon, &ctx->d_gene_hi, &ctx->d_subtab[0],
                       &ctx->d_subtab[1], &ctx->d_task_q, &ctx->d_task_r, &ctx->d_hitlen,
                       &ctx->d_score, &ctx->d_spill, &ctx->d_counters, &ctx->d_perm,
@@ -452,6 +453,7 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     ctx->N = n_genomes; ctx->P = n_phams; ctx->nnz = nnz;
     ctx->h_pham_members.clear();
     ctx->deal_parts = -1;
+    ctx->resident_n = -1;
     ctx->bits_ready = false;
     ctx->max_copies = max_copies; ctx->max_len_sum = max_len;
     ctx->n_genes_total = gene_cursor;
@@ -1412,6 +1414,76 @@ extern "C" int pc_matrix(pc_ctx *ctx, int metric, int as_distance, int ppos,
                           out_on_device);
 }
 
+// ---------------------------------------------------------------------------
+// the resident triangle (pc_resident.cu)
+// ---------------------------------------------------------------------------
+extern "C" int pc_matrix_resident(pc_ctx *ctx, int metric, int as_distance, int ppos)
+{
+    PC_ENTER(ctx);
+    PC_TRY(check_metric(ctx, metric));
+    ctx->resident_n = -1;
+    PC_TRY(devbuf_reserve(ctx, ctx->d_resident, (size_t)slice_len(ctx, 0, ctx->N) * sizeof(int32_t)));
+    PC_TRY(pc_matrix(ctx, metric, as_distance, ppos, ctx->d_resident.as<int32_t>(), 1));
+    ctx->resident_n = ctx->N;
+    return PC_OK;
+}
+
+static int need_resident(pc_ctx *ctx)
+{
+    if (ctx->resident_n < 0 || ctx->resident_n != ctx->N)
+        return pc_fail(ctx, PC_ESTATE, "no resident matrix (pc_matrix_resident, and no table load since)");
+    return PC_OK;
+}
+
+extern "C" int pc_resident_threshold_edges(pc_ctx *ctx, int32_t max_micro, int64_t cap, int32_t *edges_host,
+                                           int64_t *n_edges)
+{
+    PC_ENTER(ctx);
+    PC_TRY(need_resident(ctx));
+    if (cap < 0 || !n_edges || (cap > 0 && !edges_host))
+        return pc_fail(ctx, PC_EINVAL, "pc_resident_threshold_edges: bad arguments");
+    PC_TRY(devbuf_reserve(ctx, ctx->d_res_edges, (size_t)std::max<int64_t>(cap, 1) * sizeof(int2) + 16));
+    unsigned long long *count = reinterpret_cast<unsigned long long *>(ctx->d_res_edges.as<int2>() + std::max<int64_t>(cap, 1));
+    PC_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(unsigned long long), ctx->stream));
+    PC_TRY(pc_stage_begin(ctx, PC_T_EPILOGUE));
+    PC_TRY(pc_launch_threshold_edges(ctx, ctx->d_resident.as<int32_t>(), ctx->resident_n, max_micro, count,
+                                     ctx->d_res_edges.as<int2>(), cap));
+    PC_TRY(pc_stage_end(ctx));
+    unsigned long long found = 0;
+    PC_CUDA(ctx, cudaMemcpyAsync(&found, count, sizeof found, cudaMemcpyDeviceToHost, ctx->stream));
+    PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_edges = (int64_t)found;                      // may exceed cap: the caller retries with more room
+    const int64_t have = std::min<int64_t>((int64_t)found, cap);
+    if (have > 0) PC_TRY(download(ctx, edges_host, ctx->d_res_edges.p, (size_t)have * sizeof(int2)));
+    return maybe_collect(ctx);
+}
+
+extern "C" int pc_resident_gather(pc_ctx *ctx, int64_t n_idx, const int64_t *tri_index_host, int32_t *out_host)
+{
+    PC_ENTER(ctx);
+    PC_TRY(need_resident(ctx));
+    if (n_idx < 0 || (n_idx > 0 && (!tri_index_host || !out_host)))
+        return pc_fail(ctx, PC_EINVAL, "pc_resident_gather: bad arguments");
+    if (n_idx == 0) return PC_OK;
+    const int64_t total = slice_len(ctx, 0, ctx->N);
+    for (int64_t k = 0; k < n_idx; ++k)
+        if (tri_index_host[k] < 0 || tri_index_host[k] >= total)
+            return pc_fail(ctx, PC_EINVAL, "pc_resident_gather: index %lld outside the triangle", (long long)tri_index_host[k]);
+    PC_TRY(upload(ctx, ctx->d_res_idx, tri_index_host, (size_t)n_idx));
+    PC_TRY(devbuf_reserve(ctx, ctx->d_res_vals, (size_t)n_idx * sizeof(int32_t)));
+    PC_TRY(pc_launch_gather_entries(ctx, ctx->d_resident.as<int32_t>(), n_idx, ctx->d_res_idx.as<int64_t>(),
+                                    ctx->d_res_vals.as<int32_t>()));
+    return download(ctx, out_host, ctx->d_res_vals.p, (size_t)n_idx * sizeof(int32_t));
+}
+
+extern "C" int pc_resident_fetch(pc_ctx *ctx, int32_t *out_host)
+{
+    PC_ENTER(ctx);
+    PC_TRY(need_resident(ctx));
+    if (!out_host) return pc_fail(ctx, PC_EINVAL, "pc_resident_fetch: out is NULL");
+    return download(ctx, out_host, ctx->d_resident.p, (size_t)slice_len(ctx, 0, ctx->N) * sizeof(int32_t));
+}
+
 extern "C" int pc_numerators(pc_ctx *ctx, int metric, int ppos, int32_t *out_num,
                              int32_t *out_aux)
 {
@@ -1549,6 +1621,45 @@ extern "C" int pc_debug_round6(pc_ctx *ctx, int64_t n, const double *x, int32_t 
     }
     devbuf_free(dx);
     devbuf_free(dout);
+    return rc;
+}
+
+// both arithmetic paths of the cheap-metric epilogue on caller-chosen operands (test hook)
+__global__ void pc_debug_metric_kernel(int metric, int as_distance, int64_t n, const int32_t *numer,
+                                       const int32_t *den_i, const int32_t *den_j, int32_t *out, int32_t *out_f64)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[k] = pc_cheap_metric_micro(metric, as_distance, numer[k], den_i[k], den_j[k]);
+    out_f64[k] = numer[k] > 0 ? pc_cheap_metric_micro_f64(metric, as_distance, numer[k], (int64_t)den_i[k] + den_j[k])
+                              : (as_distance ? 1000000 : 0);
+}
+
+extern "C" int pc_debug_metric_micro(pc_ctx *ctx, int metric, int as_distance, int64_t n, const int32_t *numer,
+                                     const int32_t *den_i, const int32_t *den_j, int32_t *out, int32_t *out_f64)
+{
+    PC_ENTER(ctx);
+    if (n < 0 || metric < PC_GCS || metric > PC_AF || (n > 0 && (!numer || !den_i || !den_j || !out || !out_f64)))
+        return pc_fail(ctx, PC_EINVAL, "pc_debug_metric_micro: bad arguments");
+    if (n == 0) return PC_OK;
+    DevBuf a, b, c, d, e;
+    int rc = PC_OK;
+    do {
+        if ((rc = upload(ctx, a, numer, (size_t)n))) break;
+        if ((rc = upload(ctx, b, den_i, (size_t)n))) break;
+        if ((rc = upload(ctx, c, den_j, (size_t)n))) break;
+        if ((rc = devbuf_reserve(ctx, d, (size_t)n * sizeof(int32_t)))) break;
+        if ((rc = devbuf_reserve(ctx, e, (size_t)n * sizeof(int32_t)))) break;
+        pc_debug_metric_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(metric, as_distance ? 1 : 0, n,
+            a.as<int32_t>(), b.as<int32_t>(), c.as<int32_t>(), d.as<int32_t>(), e.as<int32_t>());
+        ctx->launches++;
+        if (cudaMemcpyAsync(out, d.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(out_f64, e.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = pc_fail(ctx, PC_ECUDA, "pc_debug_metric_micro failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } while (0);
+    cudaStreamSynchronize(ctx->stream);
+    devbuf_free(a); devbuf_free(b); devbuf_free(c); devbuf_free(d); devbuf_free(e);
     return rc;
 }
 

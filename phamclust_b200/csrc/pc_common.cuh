@@ -210,6 +210,8 @@ struct pc_ctx {
     DevBuf d_acc;                                  // uint64 accumulators (single-GPU path)
     DevBuf d_dest;                                 // [2][PC_MAX_DEST] record counts / write cursors per destination
     DevBuf d_out;                                  // int32 result staging
+    DevBuf d_resident, d_res_edges, d_res_idx, d_res_vals;   // the triangle kept in HBM + its query scratch
+    int64_t resident_n = -1;                       // genomes of the resident triangle (-1: none)
 
     // ---- measurement ----
     std::vector<StageTimer> timers;
@@ -250,6 +252,9 @@ int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
                      const int64_t *gene_off, const int32_t *gene_len,
                      const uint8_t *code_lut, int64_t n_genes, uint8_t *codes);
 int pc_launch_gene_bound(pc_ctx *ctx, const int *rowmax32, int32_t *gene_hi);
+int pc_launch_threshold_edges(pc_ctx *ctx, const int32_t *tri, int64_t n, int32_t max_micro,
+                              unsigned long long *count, int2 *edges, int64_t cap);
+int pc_launch_gather_entries(pc_ctx *ctx, const int32_t *tri, int64_t n_idx, const int64_t *idx, int32_t *out);
 int pc_i8_contract(pc_ctx *ctx, int metric, const EpilogueArgs &ep);
 int pc_i8_supported(const pc_ctx *ctx, int metric);
 int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_bytes, int64_t rows_pad,
@@ -445,22 +450,63 @@ __device__ __forceinline__ int pc_finish_micro(double similarity, int as_distanc
     return pc_round6_micro(as_distance ? 1.0 - similarity : similarity);
 }
 
-// fused epilogue for one pair of the cheap metrics (both contraction engines)
+// round-half-even(p * 10^6 / q) in integer arithmetic, for 0 <= p <= q < 2^31, q > 0; *tie is set
+// when the exact quotient ends in .5 (then the caller must ask the fp64 path, see below).
+__device__ __forceinline__ int pc_ratio_micro_int(uint32_t p, uint32_t q, bool *tie)
+{
+    // estimate from fp32 (relative error < 5e-7 -> at most 1 off), then exact 64-bit remainder
+    uint32_t est = (uint32_t)(__fdividef((float)p, (float)q) * 1e6f);
+    long long rem = (long long)p * 1000000ll - (long long)est * (long long)q;
+    while (rem < 0) { rem += q; --est; }
+    while (rem >= (long long)q) { rem -= q; ++est; }
+    const long long twice = 2 * rem;
+    *tie = twice == (long long)q;
+    return (int)(twice > (long long)q ? est + 1 : est);
+}
+
+// fp64 reference path: exactly CPython's arithmetic (IEEE divide, 1.0 - x, round(x, 6))
+static __device__ __noinline__ int pc_cheap_metric_micro_f64(int metric, int as_distance, int numer, int64_t den)
+{
+    double sim;
+    if (metric == PC_GCS)
+        sim = (2.0 * (double)numer) / (double)den;            // metrics.py:45-48
+    else if (metric == PC_JC)
+        sim = (double)numer / (double)(den - numer);          // |S u T| = |S|+|T|-|S n T|
+    else
+        sim = (double)numer / (double)den;                    // metrics.py:110, :152
+    return pc_finish_micro(sim, as_distance);
+}
+
+// fused epilogue for one pair of the cheap metrics (both contraction engines).
+//
+// The reference computes similarity = p / q in doubles and stores round(1.0 - similarity, 6)
+// (metrics.py:50-53, matrix.py:323).  On this GPU fp64 issues about one warp instruction per 26
+// cycles per SM (ncu: the contraction's epilogue warps sat in math-pipe throttle and a 128 x 256
+// half tile took 135 us to normalise -- longer than its 100 us of MMAs at C3), so the value is
+// computed in integers instead: the exact rational (q - p) * 10^6 / q rounded half-even.  The two
+// agree unless the exact quotient ends in .5: the double path's total error is below 1.2e-10
+// micro-units (two roundings of relative size 2^-53, times 10^6) while a non-tie quotient stays at
+// least 1 / (2 q) > 2.3e-10 away from the rounding boundary for q < 2^31.  Exact ties (q a multiple
+// of 128, about 1 % of pairs) and out-of-range operands take the fp64 path, which is CPython's
+// arithmetic verbatim.
 __device__ __forceinline__ int pc_cheap_metric_micro(int metric, int as_distance, int numer,
                                                      int den_i, int den_j)
 {
     // numer: shared phams (gcs, jc) or conserved genes / residues (pocp, af)
-    double sim = 0.0;
-    if (numer > 0) {
-        const int64_t den = (int64_t)den_i + (int64_t)den_j;
-        if (metric == PC_GCS)
-            sim = (2.0 * (double)numer) / (double)den;            // metrics.py:45-48
-        else if (metric == PC_JC)
-            sim = (double)numer / (double)(den - numer);          // |S u T| = |S|+|T|-|S n T|
-        else
-            sim = (double)numer / (double)den;                    // metrics.py:110, :152
+    if (numer <= 0) return as_distance ? 1000000 : 0;          // no shared pham: similarity 0.0 exactly
+    const int64_t den = (int64_t)den_i + (int64_t)den_j;
+    int64_t p = numer, q = den;
+    if (metric == PC_GCS) p = 2 * (int64_t)numer;
+    else if (metric == PC_JC) q = den - numer;
+    if (p <= q && q < (1ll << 31)) {
+        bool tie;
+        const int micro = pc_ratio_micro_int((uint32_t)(as_distance ? q - p : p), (uint32_t)q, &tie);
+        if (!tie) return micro;
     }
-    return pc_finish_micro(sim, as_distance);
+    return pc_cheap_metric_micro_f64(metric, as_distance, numer, den);
 }
+
+__global__ void pc_debug_metric_kernel(int metric, int as_distance, int64_t n, const int32_t *numer,
+                                       const int32_t *den_i, const int32_t *den_j, int32_t *out, int32_t *out_f64);
 
 #endif

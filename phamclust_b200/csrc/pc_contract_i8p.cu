@@ -72,6 +72,7 @@ struct P2Args {
     // rounds in lock step (L2 reuse): sync[0] = sum of n_steps over the queue (written by the
     // build kernel), sync[1 + r] = producers that have reached round r
     unsigned int *sync;
+    int lock_mode;         // 0: lock step when the launch is tensor-heavy, 1: always, 2: never
     EpilogueArgs ep;
 };
 
@@ -85,23 +86,29 @@ __device__ __forceinline__ constexpr uint32_t p2_idesc()
 // tile queue: one entry + occupancy mask per upper-triangle tile of the launch
 // ---------------------------------------------------------------------------
 __global__ void p2_build_tiles_kernel(const uint32_t *__restrict__ occ, int occ_words, int occ_shift,
-                                      int64_t kb_per_seg, int n_pass, int tile_row0, int n_row_tiles,
-                                      int n_col_tiles, P2Tile *__restrict__ tiles, uint32_t *__restrict__ masks,
+                                      int64_t kb_per_seg, int n_pass, int pairs, int n_groups, int tile_row0,
+                                      int n_row_tiles, int n_col_tiles, P2Tile *__restrict__ tiles,
+                                      uint32_t *__restrict__ masks,
                                       uint32_t *__restrict__ keys, int32_t *__restrict__ ids, int *__restrict__ counter,
-                                      unsigned int *__restrict__ total_steps)
+                                      unsigned int *__restrict__ total_steps, int order_by_work)
 {
-    // one warp per candidate tile (bi, bj); tiles strictly below the diagonal do not exist
+    // one warp per candidate tile (bi, bj) of 256 * pairs rows x 256 columns; tiles strictly below
+    // the diagonal do not exist
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= (int64_t)n_row_tiles * n_col_tiles) return;
     const int bi = tile_row0 + (int)(warp / n_col_tiles), bj = (int)(warp % n_col_tiles);
-    if (bj < bi) return;
+    if (bj < bi * pairs) return;
     int slot = 0;
     if (lane == 0) slot = atomicAdd(counter, 1);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     long long steps = 0;
     for (int w = lane; w < occ_words; w += 32) {
-        const uint32_t rows = occ[(int64_t)(2 * bi) * occ_words + w] | occ[(int64_t)(2 * bi + 1) * occ_words + w];
+        uint32_t rows = 0;
+        for (int u = 0; u < 2 * pairs; ++u) {
+            const int g = 2 * pairs * bi + u;                 // 128-genome group; past the table: empty
+            if (g < n_groups) rows |= occ[(int64_t)g * occ_words + w];
+        }
         const uint32_t cols = occ[(int64_t)(2 * bj) * occ_words + w] | occ[(int64_t)(2 * bj + 1) * occ_words + w];
         uint32_t bits = rows & cols;
         masks[(int64_t)slot * occ_words + w] = bits;
@@ -123,9 +130,9 @@ __global__ void p2_build_tiles_kernel(const uint32_t *__restrict__ occ, int occ_
         // 15 MB at C3; sorted by work alone every tile pulled its own two strips from DRAM: 4.0 GB
         // read for 0.6 GB of operand).  Blocks of 8 row tiles x 9 column tiles, late rows first
         // (their genomes occupy the most K blocks: the long tiles), longest first inside a block.
-        const uint32_t blk = (uint32_t)(bi / P2_ORDER_ROWS) * 4096u + (uint32_t)(4095 - min(bj / P2_ORDER_COLS, 4095));
+        const uint32_t blk = (uint32_t)(bi * pairs / P2_ORDER_ROWS) * 4096u + (uint32_t)(4095 - min(bj / P2_ORDER_COLS, 4095));
         const uint32_t w = (uint32_t)min(t.n_steps >> P2_ORDER_SHIFT, 1023);
-        keys[slot] = (blk << 10) | w;
+        keys[slot] = order_by_work ? (uint32_t)t.n_steps : ((blk << 10) | w);
         ids[slot] = slot;
         if (t.n_steps) atomicAdd(total_steps, (unsigned int)min(t.n_steps, 1 << 16));
     }
@@ -174,8 +181,17 @@ __device__ __forceinline__ void p2_for_each_block(const P2Args &a, const uint32_
     }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
-i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
+// PAIRS = 2: a cluster of FOUR CTAs = two CTA pairs working on two vertically adjacent tiles
+// (512 rows x 256 columns).  Both pairs need the same B tile, so each CTA fetches only a QUARTER
+// of it (64 rows) and the TMA multicasts that quarter into the smem of its counterpart in the
+// other pair: 24 KB per CTA and K block cross the L2 -> SM fabric instead of 32 KB.  ncu had the
+// single-pair kernel at the fabric's cap (11.9 TB/s into the SMs, tensor pipe 68 %).  The two
+// pairs stream the union of their K blocks in lock step: a stage is refilled only after BOTH
+// pairs' MMAs have released it (empty barriers count 2 commits, multicast to all four CTAs).
+template <int PAIRS>
+__global__ void __launch_bounds__(P2_THREADS, 1)
+i8_pair_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_quarter,
+               const P2Args a)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -191,7 +207,9 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
-    const bool leader = cta_rank == 0;
+    const uint32_t pair = cta_rank >> 1, half_rank = cta_rank & 1u;       // which pair, which half of its tile
+    const uint32_t leader_rank = pair * 2;                                 // the CTA that issues this pair's MMAs
+    const bool leader = half_rank == 0;
     const int n_clusters = (int)cluster_count_x();
     const int cluster = (int)cluster_id_x();
     const int acc_per_tile = a.n_limbs <= 1 ? 1 : a.n_limbs;            // host guarantees <= 2
@@ -201,7 +219,7 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < P2_STAGES; ++s) {
             mbar_init(full_bar + s, 1);                // the leader's producer arrives (+ 64 KB of tx from BOTH CTAs)
-            mbar_init(empty_bar + s, 1);               // one multicast commit
+            mbar_init(empty_bar + s, PAIRS);           // one multicast commit per pair of the cluster
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar + s, 1);
@@ -225,7 +243,7 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0);       // the LEADER's full barriers
+            const uint32_t full0 = mapa_u32(smem_u32(full_bar), leader_rank);   // this pair's LEADER's full barriers
             // Rounds in lock step.  The tiles of one round form a compact block of the tile grid
             // and share operand strips, but a strip only stays in L2 for a window of K (a
             // 256-genome strip is 15 MB at C3, 51 MB at C5): the sharing is real only while the
@@ -235,8 +253,8 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
             // the last load of the previous one.  All CTAs are co-resident (one per SM), so the
             // spin cannot deadlock.  Launches that hardly use the tensor core (clustered tables:
             // most tiles are empty) skip it -- there a round lasts microseconds.
-            const bool lock_step = a.sync[0] >= (unsigned int)a.n_tiles * 64u;
-            const unsigned int n_producers = 2u * (unsigned int)n_clusters;
+            const bool lock_step = a.lock_mode == 1 || (a.lock_mode == 0 && a.sync[0] >= (unsigned int)a.n_tiles * 64u);
+            const unsigned int n_producers = 2u * PAIRS * (unsigned int)n_clusters;
             for (int round = 0; round * n_clusters < a.n_tiles; ++round) {
                 if (lock_step) {
                     unsigned int *ctr = a.sync + 1 + round;
@@ -252,8 +270,8 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
                 const P2Tile t = a.tiles[a.order[q]];
                 if (t.n_steps == 0) continue;
                 const uint32_t *mask = a.masks + (int64_t)t.mask_slot * a.occ_words;
-                const int32_t a_row = t.bi * 256 + (int)cta_rank * P2_BM;
-                const int32_t b_row = t.bj * P2_BN + (int)cta_rank * (P2_BN / 2);
+                const int32_t a_row = t.bi * (256 * PAIRS) + (int)pair * 256 + (int)half_rank * P2_BM;
+                const int32_t b_row = t.bj * P2_BN + (int)half_rank * (P2_BN / 2);
                 p2_for_each_block(a, mask, [&](int64_t a_col, int64_t b_col) {
                     mbar_wait(empty_bar + s, ph ^ 1);
                     const uint32_t bar = full0 + (uint32_t)s * 8u;
@@ -269,7 +287,16 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
                                      "r"((uint32_t)(2 * P2_STAGE_BYTES))
                                      : "memory");
                     tma_load_2d_pair(dst, &map, bar, (int32_t)a_col, a_row);
-                    tma_load_2d_pair(dst + P2_A_BYTES, &map, bar, (int32_t)b_col, b_row);
+                    if (PAIRS == 1) {
+                        tma_load_2d_pair(dst + P2_A_BYTES, &map, bar, (int32_t)b_col, b_row);
+                    } else {
+                        // this CTA's quarter of the B tile, to itself and to the CTA of the other
+                        // pair that holds the same half; each destination's 8 KB complete on the
+                        // full barrier of ITS pair's leader
+                        const uint16_t dests = (uint16_t)((1u << half_rank) | (1u << (2 + half_rank)));
+                        tma_load_2d_pair_multicast(dst + P2_A_BYTES + pair * (P2_B_BYTES / 2), &map_quarter, bar,
+                                                   (int32_t)b_col, b_row + (int)pair * (P2_BN / 4), dests);
+                    }
                     if (++s == P2_STAGES) { s = 0; ph ^= 1; }
                 });
             }
@@ -306,11 +333,11 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
                         for (int kk = 0; kk < P2_BK / 32; ++kk)
                             umma_i8_pair(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc,
                                          (first && kk == 0) ? 0u : 1u);
-                        umma_commit_pair(empty_bar + s, 3);            // frees the slot in both CTAs
+                        umma_commit_pair(empty_bar + s, PAIRS == 1 ? 3 : 15);   // frees the slot in every CTA of the cluster
                         if (++s == P2_STAGES) { s = 0; ph ^= 1; }
                     }
                 }
-                umma_commit_pair(tmem_full_bar + acc_stage, 3);        // accumulators complete, both CTAs
+                umma_commit_pair(tmem_full_bar + acc_stage, (uint16_t)(3u << leader_rank));   // accumulators complete, both CTAs of the pair
                 issued += (unsigned long long)t.n_steps;
                 if (++acc_stage == acc_stages) { acc_stage = 0; acc_ph ^= 1; }
             }
@@ -325,7 +352,7 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
         const int64_t n = ep.n;
         const int64_t out_base = pc_tri_index(n, ep.row_begin, ep.row_begin);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t tmem_empty0 = mapa_u32(smem_u32(tmem_empty_bar), 0);   // the leader's barriers
+        const uint32_t tmem_empty0 = mapa_u32(smem_u32(tmem_empty_bar), leader_rank);   // this pair's leader's barriers
         int32_t *xp = s_xpose + ew * 32 * 33;
         int acc_stage = 0;
         uint32_t acc_ph = 0;
@@ -346,7 +373,8 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const P2Args a)
                 mbar_wait(tmem_full_bar + acc_stage, acc_ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            const int64_t row0 = (int64_t)t.bi * 256 + (int64_t)cta_rank * P2_BM + quad * 32;   // first row of this warp
+            const int64_t row0 = (int64_t)t.bi * (256 * PAIRS) + (int64_t)pair * 256 + (int64_t)half_rank * P2_BM +
+                                 quad * 32;                                                  // first row of this warp
             const int64_t i = row0 + lane;
             const bool row_ok = i < n && i >= ep.row_begin && i < ep.row_end;
             const int den_i = (row_ok && !ep.raw) ? ep.den[i] : 0;
@@ -418,7 +446,7 @@ typedef CUresult (*PFN_encodeTiled2)(CUtensorMap *, CUtensorMapDataType, cuuint3
                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int p2_make_map(pc_ctx *ctx, CUtensorMap *map, void *base, int64_t row_bytes, int64_t rows)
+static int p2_make_map(pc_ctx *ctx, CUtensorMap *map, void *base, int64_t row_bytes, int64_t rows, int box_rows)
 {
     static PFN_encodeTiled2 encode = nullptr;
     if (!encode) {
@@ -431,7 +459,7 @@ static int p2_make_map(pc_ctx *ctx, CUtensorMap *map, void *base, int64_t row_by
     }
     const cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-    const cuuint32_t box[2] = {(cuuint32_t)P2_BK, (cuuint32_t)P2_BM};        // 128 B x 128 rows: A and half B
+    const cuuint32_t box[2] = {(cuuint32_t)P2_BK, (cuuint32_t)box_rows};     // 128 B x 128 rows (A, half B) or 64 (quarter B)
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -446,17 +474,50 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
 {
     const int64_t kb_per_seg = p_pad / P2_BK;
     const int n_pass = n_limbs == 0 ? 1 : 2 * n_limbs;
+    // two pairs per cluster (B tile multicast) whenever the device can keep (nearly) all SMs busy
+    // with clusters of four; PC_I8_PAIRS=1|2 overrides
+    static int pairs_choice = 0, clusters_of[3] = {0, 0, 0};
+    if (!pairs_choice) {
+        for (int pr = 1; pr <= 2; ++pr) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * pr * 64);
+            cfg.blockDim = dim3(P2_THREADS);
+            cfg.dynamicSmemBytes = P2_SMEM_BYTES;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2 * pr; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (pr == 1) {
+                PC_CUDA(ctx, cudaFuncSetAttribute(i8_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+                PC_CUDA(ctx, cudaOccupancyMaxActiveClusters(&n, i8_pair_kernel<1>, &cfg));
+            } else {
+                PC_CUDA(ctx, cudaFuncSetAttribute(i8_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+                PC_CUDA(ctx, cudaOccupancyMaxActiveClusters(&n, i8_pair_kernel<2>, &cfg));
+            }
+            clusters_of[pr] = n;
+        }
+        pairs_choice = (clusters_of[2] * 4 * 100 >= ctx->sm_count * 94) ? 2 : 1;
+        if (const char *env = getenv("PC_I8_PAIRS")) {
+            const int v = atoi(env);
+            if ((v == 1 || v == 2) && clusters_of[v] > 0) pairs_choice = v;
+        }
+    }
+    const int pairs = pairs_choice;
+    const int rows_per_tile = 256 * pairs;
+    const int n_groups = (int)(rows_pad / 128);
     const int n_col_tiles = (int)((ctx->N + P2_BN - 1) / P2_BN);
-    const int tile_row0 = (int)(ep.row_begin / 256);
-    const int tile_row1 = (int)((ep.row_end + 255) / 256);
+    const int tile_row0 = (int)(ep.row_begin / rows_per_tile);
+    const int tile_row1 = (int)((ep.row_end + rows_per_tile - 1) / rows_per_tile);
     const int n_row_tiles = tile_row1 - tile_row0;
     const int64_t cand = (int64_t)n_row_tiles * n_col_tiles;
-    // upper bound of the real tiles: those with bj >= bi
+    // the real tiles: those with bj >= bi * pairs
     int64_t max_tiles = 0;
-    for (int bi = tile_row0; bi < tile_row1; ++bi) max_tiles += std::max(0, n_col_tiles - bi);
+    for (int bi = tile_row0; bi < tile_row1; ++bi) max_tiles += std::max(0, n_col_tiles - bi * pairs);
     if (max_tiles <= 0) return PC_OK;
     for (int bi = tile_row0; bi < tile_row1; ++bi)          // statistics: what a dense K schedule would issue
-        ctx->i8_dense_steps += (int64_t)std::max(0, n_col_tiles - bi) * kb_per_seg * n_pass * 2;
+        ctx->i8_dense_steps += (int64_t)std::max(0, n_col_tiles - bi * pairs) * kb_per_seg * n_pass * 2 * pairs;
 
     PC_TRY(devbuf_reserve(ctx, ctx->d_p2_tiles, (size_t)max_tiles * sizeof(P2Tile)));
     PC_TRY(devbuf_reserve(ctx, ctx->d_p2_masks, (size_t)max_tiles * occ_words * sizeof(uint32_t)));
@@ -475,8 +536,9 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
         PC_TRY(devbuf_reserve(ctx, ctx->d_i8_steps, sizeof(unsigned long long)));
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8_steps.p, 0, sizeof(unsigned long long), ctx->stream));
     }
-    CUtensorMap map;
-    PC_TRY(p2_make_map(ctx, &map, ctx->d_i8.p, row_bytes, rows_pad));
+    CUtensorMap map, map_quarter;
+    PC_TRY(p2_make_map(ctx, &map, ctx->d_i8.p, row_bytes, rows_pad, P2_BM));
+    PC_TRY(p2_make_map(ctx, &map_quarter, ctx->d_i8.p, row_bytes, rows_pad, P2_BN / 4));
 
     PC_TRY(pc_stage_begin(ctx, PC_T_CONTRACT));
     PC_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
@@ -485,10 +547,12 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
         const int64_t threads = cand * 32;
         const int grid = (int)((threads + 255) / 256);
         p2_build_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_i8_occ.as<uint32_t>(), occ_words, occ_shift,
-                                                            kb_per_seg, n_pass, tile_row0, n_row_tiles, n_col_tiles,
+                                                            kb_per_seg, n_pass, pairs, n_groups, tile_row0, n_row_tiles,
+                                                            n_col_tiles,
                                                             ctx->d_p2_tiles.as<P2Tile>(), ctx->d_p2_masks.as<uint32_t>(),
                                                             keys_in, ids_in, counter,
-                                                            ctx->d_p2_sync.as<unsigned int>());
+                                                            ctx->d_p2_sync.as<unsigned int>(),
+                                                            getenv("PC_I8_ORDER") && atoi(getenv("PC_I8_ORDER")) == 1);
         PC_CUDA(ctx, cudaGetLastError());
     }
     PC_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->d_p2_temp.p, temp_bytes, keys_in, keys_out, ids_in,
@@ -504,12 +568,25 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
     args.n_tiles = (int)max_tiles;
     args.tile_steps = ctx->d_i8_steps.as<unsigned long long>();
     args.sync = ctx->d_p2_sync.as<unsigned int>();
+    args.lock_mode = getenv("PC_I8_LOCK") ? atoi(getenv("PC_I8_LOCK")) : 0;
     args.ep = ep;
-    PC_CUDA(ctx, cudaFuncSetAttribute(i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
-    // one CTA pair per TPC; fewer when there are fewer tiles than pairs
-    int clusters = ctx->sm_count / 2;
+    // one cluster (CTA pair, or two pairs) per TPC group that can host it; fewer when there are fewer tiles
+    int clusters = clusters_of[pairs];
     if ((int64_t)clusters > max_tiles) clusters = (int)max_tiles;
-    i8_pair_kernel<<<2 * clusters, P2_THREADS, P2_SMEM_BYTES, ctx->stream>>>(map, args);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs * clusters));
+    cfg.blockDim = dim3(P2_THREADS);
+    cfg.dynamicSmemBytes = P2_SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2 * pairs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (pairs == 1)
+        PC_CUDA(ctx, cudaLaunchKernelEx(&cfg, i8_pair_kernel<1>, map, map_quarter, args));
+    else
+        PC_CUDA(ctx, cudaLaunchKernelEx(&cfg, i8_pair_kernel<2>, map, map_quarter, args));
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches += 3;
     ctx->contract_launches++;

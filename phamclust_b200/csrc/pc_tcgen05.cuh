@@ -161,6 +161,19 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
         : "memory");
 }
 
+// the same, delivered to the smem of every CTA in `cta_mask` (same CTA-relative offset); each
+// destination's bytes complete on the barrier at the same offset in the leader of ITS CTA pair
+__device__ __forceinline__ void tma_load_2d_pair_multicast(void *smem_dst, const CUtensorMap *map,
+                                                           uint32_t leader_bar_cluster_addr, int32_t c0,
+                                                           int32_t c1, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar_cluster_addr),
+        "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+
 // D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] . B[smem, N/2 rows per CTA]^T, M = 256
 __device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                              uint32_t idesc, uint32_t accumulate)

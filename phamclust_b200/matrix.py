@@ -481,6 +481,91 @@ def matrix_de_novo(genomes, func, cpus=1, as_distance=True):
     return SymMatrix.from_micro(table.names, micro, is_distance=bool(as_distance))
 
 
+class ResidentMatrix:
+    """A distance / similarity matrix whose packed triangle STAYS in HBM (the ctx's resident
+    buffer, include/phamclust_b200.h "the triangle kept in HBM").  It offers what the pipeline's
+    first consumer needs -- thresholded clustering (scripts/phamclust.py:300-317) through
+    ``clustering.hierarchical_clustering`` -- without shipping N(N+1)/2 values to the host:
+    ``threshold_components`` asks the device for the pairs under the threshold (an edge list),
+    ``extract_submatrix`` gathers just a component's entries into an ordinary host ``SymMatrix``.
+    ``to_symmatrix()`` fetches everything after all.  Valid until the next matrix is made resident
+    or another table is loaded on that context (checked)."""
+
+    def __init__(self, names, ctx, is_distance, generation):
+        self._nodes = list(names)
+        self._index = {name: k for k, name in enumerate(self._nodes)}
+        self._ctx, self._is_distance, self._generation = ctx, bool(is_distance), generation
+        self._offsets = _tri_offsets(len(self._nodes))
+        self.d2h_bytes = 0                       # what the queries have shipped so far
+
+    def _check(self):
+        if getattr(self._ctx, "resident_generation", None) != self._generation or self._ctx.n != len(self._nodes):
+            raise RuntimeError("the resident matrix of this context has been replaced")
+
+    is_distance = property(lambda self: self._is_distance)
+    nodes = property(lambda self: self._nodes[:])
+
+    def __len__(self):
+        return len(self._nodes)
+
+    def __contains__(self, item):
+        return item in self._index
+
+    def threshold_components(self, max_micro):
+        """One component label per node (the graph of off-diagonal pairs with weight <=
+        ``max_micro`` micro-units), like ``SymMatrix.threshold_components`` -- the scan runs on
+        the device, only the edge list crosses PCIe."""
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        self._check()
+        n = len(self._nodes)
+        edges = self._ctx.resident_threshold_edges(int(max_micro))
+        self.d2h_bytes += edges.nbytes
+        graph = coo_matrix((np.ones(len(edges), dtype=np.int8), (edges[:, 0], edges[:, 1])), shape=(n, n))
+        _, label = connected_components(graph, directed=False)
+        return label
+
+    def extract_submatrix(self, nodes):
+        self._check()
+        for node in nodes:
+            if node not in self._index:
+                raise KeyError(f"node '{node}' not in matrix")
+        idx = np.fromiter((self._index[x] for x in nodes), dtype=np.int64, count=len(nodes))
+        iu, ju = np.triu_indices(len(nodes))
+        a, b = idx[iu], idx[ju]
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        micro = self._ctx.resident_gather(self._offsets[lo] + (hi - lo))
+        self.d2h_bytes += micro.nbytes
+        return SymMatrix(list(nodes), self._is_distance, _micro=micro)
+
+    def to_symmatrix(self):
+        self._check()
+        micro = self._ctx.resident_fetch()
+        self.d2h_bytes += micro.nbytes
+        return SymMatrix.from_micro(self._nodes, micro, self._is_distance)
+
+    def to_ndarray(self, condensed=False):
+        return self.to_symmatrix().to_ndarray(condensed)
+
+
+def matrix_de_novo_resident(genomes, func, cpus=1, as_distance=True, device=0):
+    """``matrix_de_novo`` that leaves the result in HBM and returns a ``ResidentMatrix``
+    (single GPU).  Same arguments and errors as ``matrix_de_novo``."""
+    if len(genomes) == 0:
+        raise ValueError("need at least 1 genome to construct matrix de novo")
+    key = _metric_key(func)
+    table = genomes if isinstance(genomes, PackedTable) else \
+        pack_genomes(genomes, with_sequences=key in ("aai", "peq"))
+    ctx = get_context(device)
+    ctx.load_table(table)
+    if key in ("aai", "peq"):
+        if table.seq_off is None:
+            raise ValueError(f"metric {key} needs translations")
+        ctx.load_sequences(table)
+    generation = ctx.matrix_resident(key, as_distance=as_distance)
+    return ResidentMatrix(table.names, ctx, as_distance, generation)
+
+
 # ---------------------------------------------------------------------------------------
 # file formats (matrix.py:500-670): adjacency, squareform, lower triangle; "%.6f"
 # ---------------------------------------------------------------------------------------

@@ -52,6 +52,57 @@ def test_device_round6_equals_cpython_round(gpu_ctx):
     assert gpu_ctx.debug_round6(xs).tolist() == expect
 
 
+def test_integer_epilogue_equals_cpython_arithmetic(gpu_ctx):
+    """The production epilogue of gcs/jc/pocp/af works in integers (exact rational, round half
+    even) and only asks fp64 on exact .5 ties; both it and the fp64 path must equal what the
+    reference's float arithmetic gives (metrics.py:45-53 etc. + matrix.py:323) -- on random
+    operands, on every small denominator exhaustively, and on the tie-prone ones (denominators
+    that are multiples of 128, where 10^6 p / q can end in .5)."""
+    rng = np.random.default_rng(99)
+    cases = []
+    for q in list(range(1, 260)) + [384, 512, 640, 768, 896, 1024, 1280, 2560, 12800, 65536, 10 ** 6, 2 ** 20, 2 ** 30 - 128]:
+        ps = range(0, q + 1) if q <= 260 else sorted({int(x) for x in rng.integers(0, q + 1, size=300)} | {0, 1, q // 2, q - 1, q})
+        cases += [(p, q) for p in ps]
+    big = rng.integers(1, 2 ** 31 - 2, size=20000)
+    cases += [(int(rng.integers(0, q + 1)), int(q)) for q in big]
+    p = np.array([c[0] for c in cases], dtype=np.int64)
+    q = np.array([c[1] for c in cases], dtype=np.int64)
+
+    def python_micro(sim, as_distance):
+        return int(round(round(1.0 - sim if as_distance else sim, 6) * 1e6))
+
+    for metric in ("gcs", "jc", "pocp", "af"):
+        # operands (numer, den_i, den_j) whose ratio is p / q for that metric
+        if metric == "gcs":                      # sim = 2 numer / den: use even p
+            keep = (p % 2 == 0)
+            numer, den = p[keep] // 2, q[keep]
+        elif metric == "jc":                     # sim = numer / (den - numer)
+            numer, den = p, q + p
+            keep = den < 2 ** 31
+            numer, den = numer[keep], den[keep]
+        else:
+            numer, den = p, q
+        den_i = den // 2
+        den_j = den - den_i
+        for as_distance in (True, False):
+            got, got64 = gpu_ctx.debug_metric_micro(metric, as_distance, numer, den_i, den_j)
+            want = []
+            for a, d in zip(numer.tolist(), den.tolist()):
+                if a == 0:
+                    sim = 0.0
+                elif metric == "gcs":
+                    sim = (2.0 * a) / d
+                elif metric == "jc":
+                    sim = a / (d - a)
+                else:
+                    sim = a / d
+                want.append(python_micro(sim, as_distance))
+            want = np.array(want, dtype=np.int32)
+            assert np.array_equal(got64, want), (metric, as_distance, "fp64 path")
+            bad = np.nonzero(got != want)[0]
+            assert bad.size == 0, (metric, as_distance, [(int(numer[k]), int(den[k]), int(got[k]), int(want[k])) for k in bad[:5]])
+
+
 # ----------------------------------------------------------------------------- golden matrices
 @pytest.mark.parametrize("dataset", sorted(testdata.DATASETS))
 def test_golden_matrices_from_the_verbatim_reference(gpu_ctx, dataset):

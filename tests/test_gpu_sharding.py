@@ -143,3 +143,32 @@ def test_two_nccl_ranks_equal_one_gpu(gpu_ctx):
             assert bounds[0] == 0 and bounds[-1] == table.n_genomes
         if metric == "peq":
             assert results[0][metric][2] + results[1][metric][2] > 0
+
+
+def test_resident_matrix_clusters_without_shipping_the_triangle(gpu_ctx, monkeypatch):
+    """The nr / clustering hand-off on the triangle kept in HBM: threshold edges and component
+    blocks come from the device (pc_resident_threshold_edges / pc_resident_gather); partitions,
+    sub-matrices and medoids equal those of the host SymMatrix path, for a fraction of the D2H."""
+    from phamclust_b200 import METRICS, clustering, matrix_de_novo, matrix_de_novo_resident
+    monkeypatch.setattr(clustering, "DECOMPOSE_MIN_NODES", 64)
+    table = synthetic.phage_table(900, seed=13, genomes_per_cluster=30, pool=100, with_sequences=False)
+    host = matrix_de_novo(table, METRICS["gcs"], 1)
+    res = matrix_de_novo_resident(table, METRICS["gcs"], 1)
+    assert len(res) == 900 and res.is_distance and res.nodes == host.nodes
+    for eps in (0.25, 0.6):
+        want_labels = host.threshold_components(int(round(eps * 1e6)) + 1)
+        got_labels = res.threshold_components(int(round(eps * 1e6)) + 1)
+        # same partition (label values may differ)
+        assert len(set(zip(want_labels.tolist(), got_labels.tolist()))) == len(set(want_labels.tolist()))
+        a = clustering.hierarchical_clustering(host, "average", eps=eps)
+        b = clustering.hierarchical_clustering(res, "average", eps=eps)
+        assert [sorted(m.nodes) for m in a] == [sorted(m.nodes) for m in b]
+        for x, y in zip(a, b):
+            assert np.array_equal(x.extract_submatrix(sorted(x.nodes)).micro, y.extract_submatrix(sorted(y.nodes)).micro)
+            assert x.extract_submatrix(sorted(x.nodes)).medoid == y.extract_submatrix(sorted(y.nodes)).medoid
+    assert 0 < res.d2h_bytes < host.micro.nbytes // 2
+    assert np.array_equal(res.to_symmatrix().micro, host.micro)
+    gpu_ctx_other = matrix_de_novo(table, METRICS["jc"], 1)          # reloads the table on the same ctx
+    with pytest.raises(RuntimeError):
+        res.threshold_components(250001)
+    assert len(gpu_ctx_other) == 900

@@ -47,5 +47,42 @@ def launches(path):
         print(f"{v / 1e6:10.3f} ms {c:5d} launches {100 * v / tot:6.2f} %  {k[:110]}")
 
 
+def traffic(path, key, out="profiles/ncu_traffic.json", pick=None):
+    """dram__bytes_read + dram__bytes_write per launch of the kernels in an .ncu-rep (mean over the
+    captured launches, or only those whose name contains ``pick``) -> profiles/ncu_traffic.json[key];
+    bench.py reports it as roofline.traffic together with the library build it belongs to."""
+    import json
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    from phamclust_b200 import build_native
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    vals, names = [], []
+    for row in rows[2:]:
+        name = row[hdr.index("Kernel Name")]
+        if pick and pick not in name:
+            continue
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            k = hdr.index(m)
+            tot += float(row[k].replace(",", "")) * scale[units[k]]
+        vals.append(tot)
+        names.append(name)
+    target = root / out
+    data = json.loads(target.read_text()) if target.exists() else {}
+    data[key] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
+                 "kernels": sorted(set(n.split("(")[0] for n in names))[:8],
+                 "source": f"ncu --set full --clock-control none, {pathlib.Path(path).name}; library sha256 "
+                           f"{build_native.library_sha256()[:16]}"}
+    target.write_text(json.dumps(data, indent=1) + "\n")
+    print(key, data[key])
+
+
 if __name__ == "__main__":
-    (rep if sys.argv[1].endswith(".ncu-rep") else launches)(sys.argv[1])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], pick=sys.argv[4] if len(sys.argv) > 4 else None)
+    else:
+        (rep if sys.argv[1].endswith(".ncu-rep") else launches)(sys.argv[1])
