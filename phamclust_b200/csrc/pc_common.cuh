@@ -400,7 +400,10 @@ PC_HD inline int pc_nw_choose_cfg(int m, int n, int mode, bool coarse)
         const int kmin = g == 0 ? 8 : 16;
         if (K < kmin) K = kmin;
         if (K > kmax) continue;
-        const long long cost = (long long)(m + G - 1) * (K * per_cell + per_step) * G;
+        long long cost = (long long)(m + G - 1) * (K * per_cell + per_step) * G;
+        // LEX configs with K >= 40 only fit two warps per SM sub-partition: ncu has their ALU
+        // pipe at 75-78 % against 84-86 % for the configs with three or more
+        if (lex && K >= 40) cost += cost / 10;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = lex ? PC_NW_LEX0 + g * PC_NW_LEX_NK + (K - 8) / 2 : g * PC_NW_NK + (K - 8) / 2;
