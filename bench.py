@@ -567,19 +567,26 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
             visited = (stats["i8_tile_steps"] / stats["i8_tile_steps_dense"]) if stats["i8_tile_steps_dense"] else 1.0
             dense_tops = ops / (per_launch_ms * 1e-3) / 1e12
             tops = dense_tops * visited
-            peak = 2.0 * peaks["bf16_tflops"]
+            # int8 peak: MEASURED_PEAKS.json has no int8 figure.  2 x the measured bf16 number (3349)
+            # is provably too low -- this engine sustains 4.1 POP/s executed on C5 -- so the NOMINAL
+            # dense int8 rate is the denominator (4500 TOP/s = 2 x nominal bf16) and the measured-bf16
+            # derivative is reported next to it
+            peak = 4500.0
+            derived = 2.0 * peaks["bf16_tflops"]
             traffic, traffic_src = ncu_traffic(f"i8_{workload}_{metric}") if world == 1 else (None, None)
             algo_bytes = n * k_eff * limbs + 4.0 * _native.tri_len(n, r0, r1)
-            roofline = {"bound": "tensor", "kernel": "i8 contraction (tcgen05 kind::i8, TMA, TMEM) + fused epilogue",
+            roofline = {"bound": "tensor", "kernel": "i8 contraction (tcgen05 cta_group::2 kind::i8, TMA, TMEM) + fused epilogue",
                         "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak,
+                        "frac_of_2x_measured_bf16": tops / derived, "two_x_measured_bf16": derived,
                         "k_blocks_visited_frac": visited, "dense_equivalent_tops": dense_tops,
                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": algo_bytes,
                         "kernel_ms_per_step": contract_ms / max(steps, 1),
                         "share_of_step": contract_ms / total_ms if total_ms else None,
                         "algorithmic_ops_per_launch": ops, "k_columns": k_eff * limbs,
-                        "peak_basis": (f"2 x MEASURED_PEAKS.json bf16_tflops ({peak_kind}; int8 dense is not "
-                                       "measured by the driver: derived, nominal 4500 TOP/s; r1 ncu: tensor pipe "
-                                       "73.5 % at 0.86 of this figure, so the true int8 peak is ~15 % above it)")}
+                        "peak_basis": ("NOMINAL dense int8 tensor rate of the B200 (4500 TOP/s); the driver's "
+                                       f"MEASURED_PEAKS.json ({peak_kind}) holds no int8 figure and 2 x its bf16 number "
+                                       f"({derived:.0f}) is below what this kernel sustains on C5 (4.1 POP/s executed); "
+                                       "ncu's sm__pipe_tensor_cycles_active is the independent check (profiles/)")}
         else:
             words = (table.n_phams + 1023) // 1024 * 32
             algo_bytes = n * words * 4 + tri * 4            # operand read once + result written
