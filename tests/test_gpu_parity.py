@@ -488,12 +488,19 @@ def test_checksums_at_benchmark_size_c3(gpu_ctx):
     assert shared.sum() == (members * (members - 1) // 2).sum()
     pocp = gpu_ctx.numerators("pocp").astype(np.int64)
     assert pocp.sum() == ((members - 1) * csum).sum()
-    # spot rows against the sparse-product oracle
-    sub = table.subset(300)
-    want = po.table_numerators(sub, "gcs")
-    offs = np.arange(300) * n - (np.arange(300) * (np.arange(300) - 1)) // 2
-    for i in (0, 17, 299):
-        assert np.array_equal(shared[offs[i] + 1: offs[i] + (300 - i)], want[i, i + 1:300])
+    # 50 random FULL rows (plus the first and last) of the shared counts and of the pocp numerators
+    # against the sparse-product oracle, entry for entry
+    from scipy.sparse import csr_matrix
+    ones = np.ones(len(table.pham_id), dtype=np.int64)
+    b = csr_matrix((ones, table.pham_id, table.genome_ptr), shape=(n, table.n_phams))
+    c = csr_matrix((table.copies.astype(np.int64), table.pham_id, table.genome_ptr), shape=(n, table.n_phams))
+    rows = sorted(set(np.random.default_rng(50).choice(n, size=50, replace=False).tolist()) | {0, n - 1})
+    want_shared = np.asarray((b[rows] @ b.T).todense())
+    want_pocp = np.asarray((c[rows] @ b.T).todense()) + np.asarray((b[rows] @ c.T).todense())
+    for k, i in enumerate(rows):
+        lo = i * n - (i * (i - 1)) // 2
+        assert np.array_equal(shared[lo + 1: lo + (n - i)], want_shared[k, i + 1:]), i
+        assert np.array_equal(pocp[lo + 1: lo + (n - i)], want_pocp[k, i + 1:]), i
     jc = gpu_ctx.matrix("jc").astype(np.int64)
     gcs = gpu_ctx.matrix("gcs").astype(np.int64)
     assert jc.min() >= 0 and jc.max() <= 1000000 and (jc >= gcs).all()   # jc sim <= gcs sim
@@ -534,6 +541,36 @@ def test_peq_properties_on_phage_table(gpu_ctx):
         j = rng.randrange(i + 1, n)
         k = i * n - (i * (i - 1)) // 2 + (j - i)
         assert (hit[k], length[k]) == po.aai_parts(genomes[i], genomes[j])
+
+
+def test_aai_sums_at_full_c2_size_against_the_oracle(gpu_ctx):
+    """The benchmark's own workload (BASELINE.json configs[1] stand-in: 2000 genomes, 3.1 M distinct
+    alignments through LEX, rebased LEX and classic kernels): the integer sums behind aai/peq --
+    (sum of identical columns, sum of alignment lengths) per genome pair -- for 200 pairs, half of
+    them inside a phage cluster (dozens of shared phams each), against the oracle's C traceback."""
+    table = synthetic.phage_table(2000, seed=42)
+    _load(gpu_ctx, table)
+    n = table.n_genomes
+    hit, length = gpu_ctx.numerators("aai")
+    stats = gpu_ctx.stats()
+    assert stats["lexr_cells"] > 0 and stats["lex_cells"] > 0
+    genomes = unpack_genomes(table)
+    rng = random.Random(2000)
+    pairs = []
+    for _ in range(100):
+        i = rng.randrange(n - 1)
+        pairs.append((i, rng.randrange(i + 1, n)))
+    for _ in range(100):                                  # same cluster of 50 consecutive genomes
+        c = rng.randrange(n // 50)
+        i, j = sorted(rng.sample(range(50 * c, 50 * c + 50), 2))
+        pairs.append((i, j))
+    shared_pairs = 0
+    for i, j in pairs:
+        k = i * n - (i * (i - 1)) // 2 + (j - i)
+        want = po.aai_parts(genomes[i], genomes[j])
+        assert (int(hit[k]), int(length[k])) == want, (i, j)
+        shared_pairs += want[1] > 0
+    assert shared_pairs >= 100
 
 
 # ----------------------------------------------------------------------------- sharding on one GPU
