@@ -489,12 +489,37 @@ __global__ void aai_epilogue_kernel(int metric, int as_distance, int raw, int64_
             continue;
         }
         // aai similarity: length-weighted mean identity = sum(hit) / sum(len)
-        // (statistics.py:22); no shared pham -> 0.0 (metrics.py:198-199)
-        const double aai = len ? (double)hit / (double)len : 0.0;
+        // (statistics.py:22); no shared pham -> 0.0 (metrics.py:198-199).
+        // Integers first (fp64 issues ~1 warp instruction per 26 cycles per SM on this part, and
+        // most pairs of a large table share nothing): the exact rational rounded half-even equals
+        // CPython's float result unless the quotient ends in .5 (see pc_cheap_metric_micro); those
+        // ties, and lengths beyond 2^31, take the fp64 path below.
+        if (len == 0 || hit == 0) {                 // similarity 0.0 exactly; peq = af * 0.0
+            out[k] = as_distance ? 1000000 : 0;
+            continue;
+        }
+        if (len < (1ull << 31) && hit <= len) {
+            bool tie;
+            if (metric == PC_AAI) {
+                const int micro = pc_ratio_micro_int((uint32_t)(as_distance ? len - hit : hit), (uint32_t)len, &tie);
+                if (!tie) { out[k] = micro; continue; }
+            } else {
+                // peq multiplies the two ROUNDED factors (metrics.py:247-248): a = af, b = aai, both in
+                // micro-units; round(1.0 - (a / 1e6) * (b / 1e6), 6) is the exact a * b / 1e6 rounded
+                // half-even (error of the double path < 5e-10 micro-units, boundary distance 5e-7)
+                const int b = pc_ratio_micro_int((uint32_t)hit, (uint32_t)len, &tie);
+                if (!tie) {
+                    const long long prod = (long long)out[k] * (long long)b;          // <= 1e12
+                    const long long num = as_distance ? 1000000000000ll - prod : prod;
+                    const long long q = num / 1000000ll, rem = num % 1000000ll;
+                    if (rem != 500000ll) { out[k] = (int32_t)(rem > 500000ll ? q + 1 : q); continue; }
+                }
+            }
+        }
+        const double aai = (double)hit / (double)len;
         if (metric == PC_AAI) {
             out[k] = pc_finish_micro(aai, as_distance);
         } else {
-            // peq multiplies the two ROUNDED factors (metrics.py:247-248)
             const double af_r = (double)out[k] / 1e6;
             const double aai_r = (double)pc_round6_micro(aai) / 1e6;
             out[k] = pc_finish_micro(af_r * aai_r, as_distance);
