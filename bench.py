@@ -346,14 +346,20 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
         builder = distributed.ShardedBuilder(table, metric)
         builder.load()
         r0, r1 = builder.r0, builder.r1
-        width = max(max(builder.sizes), 1)
-        gathered = torch.empty(world * width, dtype=torch.int32, device=dev)
+        fused = builder.enable_fused_gather()        # symmetric-memory triangle: gather fused into the kernels
         state = {}
+        if fused:
+            def step():
+                state["tri"] = builder.gathered_triangle()
+            local_view = lambda: state["tri"][_native.tri_len(n, 0, r0):]
+        else:
+            width = max(max(builder.sizes), 1)
+            gathered = torch.empty(world * width, dtype=torch.int32, device=dev)
 
-        def step():
-            state["local"] = builder.row_block()
-            builder.all_gather(state["local"], gathered)
-        local_view = lambda: state["local"]
+            def step():
+                state["local"] = builder.row_block()
+                builder.all_gather(state["local"], gathered)
+            local_view = lambda: state["local"]
 
     for _ in range(max(warmup, 0)):
         flush.zero_()
@@ -409,6 +415,10 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
     if world > 1:
         dist.all_reduce(local_sum, op=dist.ReduceOp.SUM)
     checksum = int(local_sum.item())          # sum of every entry of the packed triangle
+    if world > 1 and builder.fused is not None:
+        # every rank must hold the WHOLE triangle after the fused gather: its sum is the checksum
+        whole = int(state["tri"].to(torch.int64).sum().item())
+        assert whole == checksum, f"rank {rank}: gathered triangle sums to {whole}, row blocks to {checksum}"
 
     # ---- e2e: host buffers in, host buffer out, through the C ABI, every step ----
     host_table, pinned, h2d = host_buffers(torch, table, need_seqs)
@@ -599,15 +609,20 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
                         "note": "POPC-issue bound in practice (16 lanes/clk/SM), far from the HBM roof",
                         "peak_basis": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"}
 
+    gather_txt = ""
+    if world > 1:
+        gather_txt = ("gather FUSED into the producing kernels (every row segment stored into all ranks' symmetric-"
+                      "memory triangles over NVLink, one device-side barrier)" if builder.fused is not None else
+                      f"one NCCL all-gather of the row blocks (no symmetric memory: {builder.fused_error})")
     if world == 1:
         parallelism = "1 GPU"
     elif need_seqs:
         parallelism = (f"{world} ranks: phams dealt by cost, each rank ships only its genes; sparse contribution "
                        f"records exchanged by one NCCL all-to-all ({builder.exchange_records} records received by "
-                       "rank 0 per step); pair-balanced row-block epilogue + all-gather")
+                       "rank 0 per step); pair-balanced row-block epilogue; " + gather_txt)
     else:
         parallelism = (f"{world} ranks: row blocks cut by estimated contraction work "
-                       f"(rank 0 rows [{r0},{r1}) of {n}), no collective during compute, one all-gather")
+                       f"(rank 0 rows [{r0},{r1}) of {n}), no collective during compute; " + gather_txt)
     value = pairs * steps / (total_ms * 1e-3)
     record = {"metric": "genome_pairs_per_sec", "value": value, "unit": "pairs/s",
               "n_gpus": world, "steps": steps, "warmup": warmup,

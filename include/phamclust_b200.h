@@ -208,6 +208,20 @@ int pc_resident_gather(pc_ctx *ctx, int64_t n_idx, const int64_t *tri_index_host
                        int32_t *out_host);
 int pc_resident_fetch(pc_ctx *ctx, int32_t *out_host);
 
+/*
+ * pc_matrix_rows_owned with the gather of the row blocks FUSED into the kernel that produces them:
+ * every value is stored into out_dev (this rank's triangle, slice starting at idx(row_begin,
+ * row_begin)) and into the same slice of n_peers other triangles (peer_out_dev[k]: device
+ * addresses of the other ranks' buffers mapped into this process -- CUDA IPC / symmetric memory;
+ * the stores cross NVLink while the next tile is being multiplied).  After every rank's call and a
+ * barrier, every rank holds the whole triangle; no separate all-gather.  gcs/jc/pocp/af need the
+ * default tensor engine for this.
+ */
+int pc_matrix_rows_fused(pc_ctx *ctx, int metric, int as_distance, int ppos,
+                         int64_t row_begin, int64_t row_end,
+                         const uint64_t *acc_rows_dev, int32_t *out_dev,
+                         int n_peers, int32_t *const *peer_out_dev);
+
 /* -------- integer test hooks (bit-exact parity) ------------------------- */
 /*
  * Numerators the reference computes as Python ints, packed triangle, host:

@@ -22,7 +22,7 @@ STAGES = ("h2d", "pack", "contract", "align", "gather", "epilogue", "d2h",
 EXPORTS = ("pc_init", "pc_destroy", "pc_last_error", "pc_version", "pc_set_stream",
            "pc_set_engine", "pc_set_dp_mode", "pc_sync", "pc_load_table", "pc_load_sequences", "pc_matrix",
            "pc_matrix_rows", "pc_align_accumulate", "pc_numerators", "pc_load_sequences_part", "pc_align_units",
-           "pc_align_contributions", "pc_accumulate_records", "pc_matrix_rows_owned",
+           "pc_align_contributions", "pc_accumulate_records", "pc_matrix_rows_owned", "pc_matrix_rows_fused",
            "pc_matrix_resident", "pc_resident_threshold_edges", "pc_resident_gather", "pc_resident_fetch",
            "pc_alignment_identities", "pc_debug_round6", "pc_debug_metric_micro", "pc_timings", "pc_counters", "pc_reset_counters", "pc_stat",
            "pc_write_matrix", "pc_parse_squareform", "pc_scan_tsv", "pc_tsv_intern", "pc_gather_fields",
@@ -64,6 +64,7 @@ def load_library():
     lib.pc_align_contributions.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     lib.pc_accumulate_records.argtypes = [vp, i64, vp, i64, vp]
     lib.pc_matrix_rows_owned.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, i32]
+    lib.pc_matrix_rows_fused.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, i32, vp]
     lib.pc_matrix_resident.argtypes = [vp, i32, i32, i32]
     lib.pc_resident_threshold_edges.argtypes = [vp, i32, i64, vp, vp]
     lib.pc_resident_gather.argtypes = [vp, i64, vp, vp]
@@ -256,6 +257,15 @@ class Context:
             self._h, _metric_id(metric), int(bool(as_distance)), int(bool(ppos)), row_begin,
             row_end, ctypes.c_void_p(acc_rows_ptr or 0), out.ctypes.data, 0))
         return out
+
+    def matrix_rows_fused(self, metric, as_distance, row_begin, row_end, acc_rows_ptr, out_device_ptr,
+                          peer_ptrs, ppos=False):
+        """``matrix_rows_owned`` whose result is also stored into the same slice of the other ranks'
+        triangles (``peer_ptrs``: peer-mapped device addresses of those slices)."""
+        arr = (ctypes.c_void_p * max(len(peer_ptrs), 1))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+        self._check(self._lib.pc_matrix_rows_fused(
+            self._h, _metric_id(metric), int(bool(as_distance)), int(bool(ppos)), row_begin, row_end,
+            ctypes.c_void_p(acc_rows_ptr or 0), ctypes.c_void_p(out_device_ptr), len(peer_ptrs), arr))
 
     # ---- the triangle kept in HBM ---------------------------------------------------
     def matrix_resident(self, metric, as_distance=True, ppos=False):

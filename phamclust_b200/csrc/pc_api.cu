@@ -875,7 +875,7 @@ static const int32_t *den_of(pc_ctx *ctx, int metric)
 
 // cheap metric for rows [r0, r1) into out_dev (device)
 static int contract_rows(pc_ctx *ctx, int metric, int as_distance, int raw, int64_t r0,
-                         int64_t r1, int32_t *out_dev)
+                         int64_t r1, int32_t *out_dev, bool to_peers = false)
 {
     EpilogueArgs ep;
     ep.den = den_of(ctx, metric);
@@ -886,9 +886,17 @@ static int contract_rows(pc_ctx *ctx, int metric, int as_distance, int raw, int6
     ep.row_begin = r0;
     ep.row_end = r1;
     ep.out = out_dev;
+    ep.n_peer_out = 0;
     // AUTO: the tensor-core engine whenever the weights fit its limb layout
     int engine = ctx->engine;
     if (engine == PC_ENGINE_AUTO) engine = pc_i8_supported(ctx, metric) ? PC_ENGINE_I8MMA : PC_ENGINE_POPC;
+    if (to_peers && ctx->n_peer_out) {
+        if (engine != PC_ENGINE_I8MMA)
+            return pc_fail(ctx, PC_EINVAL, "the fused all-gather needs the CTA-pair tensor engine (metric %d, engine %d)",
+                           metric, engine);
+        ep.n_peer_out = ctx->n_peer_out;
+        for (int o = 0; o < ctx->n_peer_out; ++o) ep.peer_out[o] = ctx->peer_out[o];
+    }
     if (engine == PC_ENGINE_I8MMA || engine == PC_ENGINE_I8MMA_V1) {
         PC_TRY(pc_i8_contract(ctx, metric, ep));
         return PC_OK;
@@ -1363,15 +1371,18 @@ extern "C" int pc_matrix_rows(pc_ctx *ctx, int metric, int as_distance, int ppos
         return maybe_collect(ctx);
     }
     if (metric <= PC_AF) {
-        PC_TRY(contract_rows(ctx, metric, as_distance, 0, row_begin, row_end, out_dev));
+        PC_TRY(contract_rows(ctx, metric, as_distance, 0, row_begin, row_end, out_dev, true));
     } else {
         if (!acc_dev) return pc_fail(ctx, PC_EINVAL, "aai/peq rows need the accumulators");
         if (metric == PC_PEQ)   // alignment_fraction(source, target) as SIMILARITY, metrics.py:247
             PC_TRY(contract_rows(ctx, PC_AF, 0, 0, row_begin, row_end, out_dev));
+        PeerOuts peers;
+        peers.n = ctx->n_peer_out;
+        for (int o = 0; o < ctx->n_peer_out; ++o) peers.p[o] = ctx->peer_out[o];
         PC_TRY(pc_stage_begin(ctx, PC_T_EPILOGUE));
         PC_TRY(pc_launch_aai_epilogue(ctx, metric, as_distance, 0, row_begin, row_end,
                                       reinterpret_cast<const unsigned long long *>(acc_dev),
-                                      out_dev, nullptr));
+                                      out_dev, nullptr, &peers));
         PC_TRY(pc_stage_end(ctx));
     }
     if (!out_on_device) PC_TRY(download(ctx, out, out_dev, (size_t)count * sizeof(int32_t)));
@@ -1390,6 +1401,23 @@ extern "C" int pc_matrix_rows_owned(pc_ctx *ctx, int metric, int as_distance, in
     // entries of rows [row_begin, row_end) are ever read)
     const uint64_t *base = acc_rows_dev ? acc_rows_dev - pc_tri_index(ctx->N, row_begin, row_begin) : nullptr;
     return pc_matrix_rows(ctx, metric, as_distance, ppos, row_begin, row_end, base, out, out_on_device);
+}
+
+extern "C" int pc_matrix_rows_fused(pc_ctx *ctx, int metric, int as_distance, int ppos,
+                                    int64_t row_begin, int64_t row_end, const uint64_t *acc_rows_dev,
+                                    int32_t *out_dev, int n_peers, int32_t *const *peer_out_dev)
+{
+    PC_ENTER(ctx);
+    if (n_peers < 0 || n_peers > PC_MAX_PEER_OUT || (n_peers > 0 && !peer_out_dev) || !out_dev)
+        return pc_fail(ctx, PC_EINVAL, "pc_matrix_rows_fused: 0..%d peers", PC_MAX_PEER_OUT);
+    ctx->n_peer_out = n_peers;
+    for (int o = 0; o < n_peers; ++o) {
+        if (!peer_out_dev[o]) { ctx->n_peer_out = 0; return pc_fail(ctx, PC_EINVAL, "pc_matrix_rows_fused: peer %d is NULL", o); }
+        ctx->peer_out[o] = peer_out_dev[o];
+    }
+    const int rc = pc_matrix_rows_owned(ctx, metric, as_distance, ppos, row_begin, row_end, acc_rows_dev, out_dev, 1);
+    ctx->n_peer_out = 0;
+    return rc;
 }
 
 static int full_accumulate(pc_ctx *ctx, int ppos)

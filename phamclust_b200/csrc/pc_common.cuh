@@ -44,6 +44,8 @@ void devbuf_free(DevBuf &b);
 // ---------------------------------------------------------------------------
 // kernel argument blocks
 // ---------------------------------------------------------------------------
+#define PC_MAX_PEER_OUT 15        // other ranks of the node whose triangles receive the row block
+
 struct PopcTerm {
     const uint32_t *a;   // bit rows read for the tile's ROW genomes
     const uint32_t *b;   // bit rows read for the tile's COLUMN genomes
@@ -59,6 +61,10 @@ struct EpilogueArgs {
     int64_t row_begin;   // first genome row covered by `out`
     int64_t row_end;
     int32_t *out;        // packed triangle slice starting at idx(row_begin,row_begin)
+    // fused all-gather: the same slice in the triangles of the other ranks (peer-mapped
+    // addresses, stores travel over NVLink); honoured by the pair engine and the aai epilogue
+    int n_peer_out;
+    int32_t *peer_out[PC_MAX_PEER_OUT];
 };
 
 struct NwArgs {
@@ -211,6 +217,8 @@ struct pc_ctx {
     DevBuf d_dest;                                 // [2][PC_MAX_DEST] record counts / write cursors per destination
     DevBuf d_out;                                  // int32 result staging
     DevBuf d_resident, d_res_edges, d_res_idx, d_res_vals;   // the triangle kept in HBM + its query scratch
+    int n_peer_out = 0;                            // pc_matrix_rows_fused: peers' slices for the call in flight
+    int32_t *peer_out[PC_MAX_PEER_OUT] = {};
     int64_t resident_n = -1;                       // genomes of the resident triangle (-1: none)
 
     // ---- measurement ----
@@ -244,10 +252,14 @@ int pc_launch_emit_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen,
                          unsigned long long *dest_counts /*[2][PC_MAX_DEST]*/, unsigned long long *records);
 int pc_launch_accumulate_records(pc_ctx *ctx, int64_t n_records, const unsigned long long *records,
                                  int64_t n_acc, unsigned long long *acc);
+struct PeerOuts {
+    int n;
+    int32_t *p[PC_MAX_PEER_OUT];
+};
 int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
                            int64_t row_begin, int64_t row_end,
                            const unsigned long long *acc, int32_t *out,
-                           int32_t *out_aux);
+                           int32_t *out_aux, const PeerOuts *peers = nullptr);
 int pc_launch_encode(pc_ctx *ctx, const uint8_t *raw, const int64_t *raw_off,
                      const int64_t *gene_off, const int32_t *gene_len,
                      const uint8_t *code_lut, int64_t n_genes, uint8_t *codes);

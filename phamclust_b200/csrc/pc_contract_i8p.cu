@@ -417,7 +417,11 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
                 for (int r = 0; r < 32; ++r) {
                     const int64_t rb = __shfl_sync(0xffffffffu, row_base, r);
                     const int val = xp[r * 33 + lane];
-                    if (((rows_ok >> r) & 1u) && j < n && j >= row0 + r) ep.out[rb + j] = val;
+                    if (((rows_ok >> r) & 1u) && j < n && j >= row0 + r) {
+                        ep.out[rb + j] = val;
+                        // fused all-gather: the same 128-byte row segment into every peer's triangle
+                        for (int o = 0; o < ep.n_peer_out; ++o) ep.peer_out[o][rb + j] = val;
+                    }
                 }
                 __syncwarp();
             }

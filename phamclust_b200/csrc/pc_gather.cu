@@ -462,7 +462,7 @@ int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitle
 __global__ void aai_epilogue_kernel(int metric, int as_distance, int raw, int64_t n,
                                     int64_t row_begin, int64_t row_end,
                                     const unsigned long long *__restrict__ acc,
-                                    int32_t *__restrict__ out, int32_t *__restrict__ out_aux)
+                                    int32_t *__restrict__ out, int32_t *__restrict__ out_aux, const PeerOuts peers)
 {
     const int64_t base = pc_tri_index(n, row_begin, row_begin);
     const int64_t total = pc_tri_index(n, row_end, row_end) - base;   // row_end may equal n
@@ -484,8 +484,14 @@ __global__ void aai_epilogue_kernel(int metric, int as_distance, int raw, int64_
             if (out_aux) out_aux[k] = (i == j) ? 0 : (int32_t)len;
             continue;
         }
+#define PC_PUT(val_)                                                                  \
+    do {                                                                              \
+        const int32_t v_ = (val_);                                                    \
+        out[k] = v_;                                                                  \
+        for (int o_ = 0; o_ < peers.n; ++o_) peers.p[o_][k] = v_;                     \
+    } while (0)
         if (i == j) {                               // matrix.py:467-468
-            out[k] = as_distance ? 0 : 1000000;
+            PC_PUT(as_distance ? 0 : 1000000);
             continue;
         }
         // aai similarity: length-weighted mean identity = sum(hit) / sum(len)
@@ -495,14 +501,14 @@ __global__ void aai_epilogue_kernel(int metric, int as_distance, int raw, int64_
         // CPython's float result unless the quotient ends in .5 (see pc_cheap_metric_micro); those
         // ties, and lengths beyond 2^31, take the fp64 path below.
         if (len == 0 || hit == 0) {                 // similarity 0.0 exactly; peq = af * 0.0
-            out[k] = as_distance ? 1000000 : 0;
+            PC_PUT(as_distance ? 1000000 : 0);
             continue;
         }
         if (len < (1ull << 31) && hit <= len) {
             bool tie;
             if (metric == PC_AAI) {
                 const int micro = pc_ratio_micro_int((uint32_t)(as_distance ? len - hit : hit), (uint32_t)len, &tie);
-                if (!tie) { out[k] = micro; continue; }
+                if (!tie) { PC_PUT(micro); continue; }
             } else {
                 // peq multiplies the two ROUNDED factors (metrics.py:247-248): a = af, b = aai, both in
                 // micro-units; round(1.0 - (a / 1e6) * (b / 1e6), 6) is the exact a * b / 1e6 rounded
@@ -512,25 +518,29 @@ __global__ void aai_epilogue_kernel(int metric, int as_distance, int raw, int64_
                     const long long prod = (long long)out[k] * (long long)b;          // <= 1e12
                     const long long num = as_distance ? 1000000000000ll - prod : prod;
                     const long long q = num / 1000000ll, rem = num % 1000000ll;
-                    if (rem != 500000ll) { out[k] = (int32_t)(rem > 500000ll ? q + 1 : q); continue; }
+                    if (rem != 500000ll) { PC_PUT((int32_t)(rem > 500000ll ? q + 1 : q)); continue; }
                 }
             }
         }
         const double aai = (double)hit / (double)len;
         if (metric == PC_AAI) {
-            out[k] = pc_finish_micro(aai, as_distance);
+            PC_PUT(pc_finish_micro(aai, as_distance));
         } else {
             const double af_r = (double)out[k] / 1e6;
             const double aai_r = (double)pc_round6_micro(aai) / 1e6;
-            out[k] = pc_finish_micro(af_r * aai_r, as_distance);
+            PC_PUT(pc_finish_micro(af_r * aai_r, as_distance));
         }
     }
+#undef PC_PUT
 }
 
 int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
                            int64_t row_begin, int64_t row_end,
-                           const unsigned long long *acc, int32_t *out, int32_t *out_aux)
+                           const unsigned long long *acc, int32_t *out, int32_t *out_aux, const PeerOuts *peers)
 {
+    PeerOuts po;
+    po.n = 0;
+    if (peers) po = *peers;
     const int64_t total = pc_tri_index(ctx->N, row_end, row_end) -
                           pc_tri_index(ctx->N, row_begin, row_begin);
     if (total <= 0) return PC_OK;
@@ -538,7 +548,7 @@ int pc_launch_aai_epilogue(pc_ctx *ctx, int metric, int as_distance, int raw,
     int64_t cap = (int64_t)ctx->sm_count * 16;
     int grid = (int)(blocks < cap ? blocks : cap);
     aai_epilogue_kernel<<<grid, 256, 0, ctx->stream>>>(metric, as_distance, raw, ctx->N,
-                                                      row_begin, row_end, acc, out, out_aux);
+                                                      row_begin, row_end, acc, out, out_aux, po);
     PC_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return PC_OK;

@@ -19,7 +19,13 @@ genome pairs (/root/reference/src/phamclust/matrix.py:471-491):
 
 Assembly of the row blocks, two consumers:
 
-* device (``sharded_matrix``): one all-gather over NVLink, every rank ends up with the triangle;
+* device (``sharded_matrix``): every rank ends up with the triangle.  On GPUs the gather is FUSED
+  into the kernels that produce the row block (``FusedTriangle`` + ``pc_matrix_rows_fused``): the
+  triangle lives in symmetric memory, and the contraction's epilogue (gcs/jc/pocp/af) or the aai/peq
+  epilogue stores every 128-byte row segment into its own triangle AND into the same place of every
+  peer's triangle over NVLink while the next tile is multiplied -- no separate collective, one
+  device-side barrier at the end.  Where symmetric memory is not available (and in the CPU tests)
+  the row blocks are exchanged with one NCCL / gloo all-gather;
 * host (``sharded_matrix_to_host``; what the reference does next is host clustering): every rank
   copies its finished block from its own GPU over its own PCIe link into ONE triangle in POSIX
   shared memory (``SharedTriangle``) -- no device-side assembly, no single-link D2H.
@@ -130,6 +136,34 @@ def assemble(n, bounds, shards):
     return out
 
 
+class FusedTriangle:
+    """The packed int32 triangle of every rank in symmetric memory (torch.distributed
+    ._symmetric_memory: CUDA IPC mappings of every rank's buffer into every process), so that a
+    kernel of one rank can store straight into the others' triangles."""
+
+    def __init__(self, n, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.n = n
+        count = max(n * (n + 1) // 2, 1)
+        group = dist.group.WORLD
+        self.tensor = symm_mem.empty(count, dtype=torch.int32, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(self.ptrs) == self.world and self.ptrs[self.rank] == self.tensor.data_ptr()
+
+    def slice_ptrs(self, r0):
+        """(own, [peers]) addresses of the slice that starts at row r0."""
+        off = 4 * tri_offset(self.n, r0)
+        return self.ptrs[self.rank] + off, [p + off for k, p in enumerate(self.ptrs) if k != self.rank]
+
+    def barrier(self):
+        """Device-side barrier on the current stream: every rank's stores have landed after it."""
+        self.handle.barrier()
+
+
 class ShardedBuilder:
     """This rank's share of one matrix build (the default process group's world).
 
@@ -160,6 +194,8 @@ class ShardedBuilder:
         self.sizes = [tri_offset(self.n, self.bounds[r + 1]) - tri_offset(self.n, self.bounds[r])
                       for r in range(self.world)]
         self.exchange_records = 0           # records this rank received in the last exchange
+        self.fused = None                   # FusedTriangle once the fused gather has been set up
+        self.fused_error = None
 
     def load(self, table=None):
         """Host buffers -> this rank's device: the table, and for aai/peq only the genes of the
@@ -196,6 +232,41 @@ class ShardedBuilder:
         if self.r1 > self.r0:
             self.ops.rows_to_host(self.r0, self.r1, acc, out)
 
+    def enable_fused_gather(self):
+        """Set up the symmetric-memory triangle for ``gathered_triangle``; returns False (and keeps
+        the all-gather path) where that is not possible.  Collective: every rank calls it."""
+        if self.fused is not None:
+            return True
+        if self.world == 1 or not hasattr(self.ops, "rows_fused"):
+            return False
+        import torch
+        ok = torch.ones(1, dtype=torch.int32, device=self.ops.device)
+        try:
+            fused = FusedTriangle(self.n, self.ops.device)
+        except Exception as exc:              # no symmetric memory here: say why, fall back
+            self.fused_error = f"{type(exc).__name__}: {exc}"
+            fused = None
+            ok.zero_()
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            return False
+        self.fused = fused
+        return True
+
+    def gathered_triangle(self):
+        """Device consumer: the whole packed triangle on this rank's device after every rank has
+        computed its row block.  Fused path: the row block is stored into every rank's triangle by
+        the kernel that computes it; else row blocks + one all-gather (returned padded per rank:
+        use ``assemble_host``)."""
+        if self.fused is None:
+            return self.all_gather(self.row_block())
+        own, peers = self.fused.slice_ptrs(self.r0)
+        acc = self.accumulators()
+        if self.r1 > self.r0:
+            self.ops.rows_fused(self.r0, self.r1, acc, own, peers)
+        self.fused.barrier()
+        return self.fused.tensor
+
     def all_gather(self, local, gathered=None):
         """Device consumer: every rank receives every row block (padded to the widest)."""
         import torch
@@ -217,11 +288,13 @@ class ShardedBuilder:
         return assemble(self.n, self.bounds, [host[r] for r in range(self.world)])
 
 
-def sharded_matrix(table, metric, as_distance=True, ppos=False, backend_ops=None):
+def sharded_matrix(table, metric, as_distance=True, ppos=False, backend_ops=None, fused=True):
     """Packed int32 micro-unit triangle computed by all ranks of the default process group;
     every rank returns the full triangle (host numpy)."""
     builder = ShardedBuilder(table, metric, as_distance, ppos, backend_ops)
     builder.load()
+    if fused and builder.enable_fused_gather():
+        return builder.gathered_triangle().cpu().numpy()
     return builder.assemble_host(builder.all_gather(builder.row_block()))
 
 
@@ -362,6 +435,12 @@ class _GpuOps:
                                        acc_rows.data_ptr() if acc_rows is not None else None,
                                        out_device_ptr=out.data_ptr(), ppos=self.ppos)
         return out[:count]
+
+    def rows_fused(self, r0, r1, acc_rows, out_ptr, peer_ptrs):
+        """Row block stored into this rank's triangle and, by the same kernel, into the peers'."""
+        self.ctx.matrix_rows_fused(self.metric, self.as_distance, r0, r1,
+                                   acc_rows.data_ptr() if acc_rows is not None else None, out_ptr, peer_ptrs,
+                                   ppos=self.ppos)
 
     def rows_to_host(self, r0, r1, acc_rows, out):
         """Row block computed on this GPU, D2H by the library into ``out`` (page-locked

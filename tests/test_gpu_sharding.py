@@ -102,9 +102,16 @@ def _nccl_worker(rank, world, port, queue):
         for metric, table in (("peq", synthetic.phage_table(300, seed=5)),
                               ("jc", synthetic.sparse_table(1500, 9000, seed=6))):
             n = table.n_genomes
-            got = distributed.sharded_matrix(table, metric)
+            got = distributed.sharded_matrix(table, metric, fused=False)        # row blocks + NCCL all-gather
             builder = distributed.ShardedBuilder(table, metric)
             builder.load()
+            # the gather fused into the producing kernels (peer stores over NVLink, symmetric memory)
+            fused_ok = builder.enable_fused_gather()
+            if fused_ok:
+                for _ in range(2):                                              # reuse of the triangle too
+                    tri = builder.gathered_triangle()
+                    torch.cuda.synchronize()
+                    assert np.array_equal(tri.cpu().numpy(), got), (metric, "fused gather")
             shared = distributed.SharedTriangle(n, pin_rows=(builder.r0, builder.r1))
             try:
                 host = distributed.sharded_matrix_to_host(table, metric, shared, builder=builder).copy()
@@ -112,7 +119,7 @@ def _nccl_worker(rank, world, port, queue):
             finally:
                 shared.close()
             assert np.array_equal(host, got)
-            out[metric] = (got, builder.bounds, builder.exchange_records)
+            out[metric] = (got, builder.bounds, builder.exchange_records, fused_ok, builder.fused_error)
         queue.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -138,7 +145,8 @@ def test_two_nccl_ranks_equal_one_gpu(gpu_ctx):
                           ("jc", synthetic.sparse_table(1500, 9000, seed=6))):
         single = packed_matrix(table, metric)
         for rank in (0, 1):
-            got, bounds, records = results[rank][metric]
+            got, bounds, records, fused_ok, fused_error = results[rank][metric]
+            assert fused_ok, fused_error                 # a B200 box has NVLink peer access: the fused path must run
             assert np.array_equal(got, single), (metric, rank)
             assert bounds[0] == 0 and bounds[-1] == table.n_genomes
         if metric == "peq":
