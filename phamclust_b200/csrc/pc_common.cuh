@@ -475,7 +475,16 @@ __device__ __forceinline__ int pc_ratio_micro_int(uint32_t p, uint32_t q, bool *
     while (rem < 0) { rem += q; --est; }
     while (rem >= (long long)q) { rem -= q; ++est; }
     const long long twice = 2 * rem;
-    *tie = twice == (long long)q;
+    *tie = false;
+    if (twice == (long long)q) {
+        // the exact quotient ends in .5.  If p / q in lowest terms has a power-of-two denominator
+        // (the odd part of q divides p) every double on CPython's path is exact and round() sees a
+        // true tie: half to even.  Otherwise the direction is that of the division's rounding
+        // error: the caller asks the fp64 path.
+        const uint32_t odd = q >> (__ffs((int)q) - 1);
+        if (p % odd == 0) return (int)(est + (est & 1u));
+        *tie = true;
+    }
     return (int)(twice > (long long)q ? est + 1 : est);
 }
 
@@ -501,9 +510,10 @@ static __device__ __noinline__ int pc_cheap_metric_micro_f64(int metric, int as_
 // computed in integers instead: the exact rational (q - p) * 10^6 / q rounded half-even.  The two
 // agree unless the exact quotient ends in .5: the double path's total error is below 1.2e-10
 // micro-units (two roundings of relative size 2^-53, times 10^6) while a non-tie quotient stays at
-// least 1 / (2 q) > 2.3e-10 away from the rounding boundary for q < 2^31.  Exact ties (q a multiple
-// of 128, about 1 % of pairs) and out-of-range operands take the fp64 path, which is CPython's
-// arithmetic verbatim.
+// least 1 / (2 q) > 2.3e-10 away from the rounding boundary for q < 2^31.  Exact ties need q to be a
+// multiple of 128 (about 1 % of pairs); when the reduced fraction has a power-of-two denominator the
+// doubles are exact and the tie goes to even, in integers; the remaining ties (q a multiple of 640)
+// and out-of-range operands take the fp64 path, which is CPython's arithmetic verbatim.
 __device__ __forceinline__ int pc_cheap_metric_micro(int metric, int as_distance, int numer,
                                                      int den_i, int den_j)
 {

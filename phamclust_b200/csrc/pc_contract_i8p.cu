@@ -48,7 +48,6 @@
 #define P2_THREADS (32 * (P2_FIRST_EPI_WARP + P2_EPI_WARPS))
 #define P2_ORDER_ROWS 8           // tile-queue locality blocks: 8 row tiles x 9 column tiles ~ one round of 74 pairs
 #define P2_ORDER_COLS 9
-#define P2_ORDER_SHIFT 3          // work resolution inside a block: 8 K blocks
 #define P2_BAR_BYTES 256
 #define P2_DEN_BYTES (P2_BN * 4)
 #define P2_XPOSE_BYTES (P2_EPI_WARPS * 32 * 33 * 4)
@@ -69,8 +68,8 @@ struct P2Args {
     const uint32_t *masks;
     int n_tiles;
     unsigned long long *tile_steps;
-    // rounds in lock step (L2 reuse): sync[0] = sum of n_steps over the queue (written by the
-    // build kernel), sync[1 + r] = producers that have reached round r
+    // rounds in lock step (L2 reuse): sync[0] = sum of n_steps over the queue, sync[1] = the longest
+    // tile (both written by the build kernel), sync[2 + r] = producers that have reached round r
     unsigned int *sync;
     int lock_mode;         // 0: lock step when the launch is tensor-heavy, 1: always, 2: never
     EpilogueArgs ep;
@@ -90,7 +89,7 @@ __global__ void p2_build_tiles_kernel(const uint32_t *__restrict__ occ, int occ_
                                       int n_row_tiles, int n_col_tiles, P2Tile *__restrict__ tiles,
                                       uint32_t *__restrict__ masks,
                                       uint32_t *__restrict__ keys, int32_t *__restrict__ ids, int *__restrict__ counter,
-                                      unsigned int *__restrict__ total_steps, int order_by_work)
+                                      unsigned int *__restrict__ total_steps)
 {
     // one warp per candidate tile (bi, bj) of 256 * pairs rows x 256 columns; tiles strictly below
     // the diagonal do not exist
@@ -124,18 +123,33 @@ __global__ void p2_build_tiles_kernel(const uint32_t *__restrict__ occ, int occ_
         P2Tile t;
         t.bi = bi; t.bj = bj; t.n_steps = (int32_t)(steps * n_pass); t.mask_slot = slot;
         tiles[slot] = t;
-        // queue order (descending key): tiles that run at the same time -- one round of the
-        // static schedule is a window of #clusters consecutive entries -- should form a compact
-        // block of the tile grid so that they share operand strips in L2 (a 256-genome strip is
-        // 15 MB at C3; sorted by work alone every tile pulled its own two strips from DRAM: 4.0 GB
-        // read for 0.6 GB of operand).  Blocks of 8 row tiles x 9 column tiles, late rows first
-        // (their genomes occupy the most K blocks: the long tiles), longest first inside a block.
-        const uint32_t blk = (uint32_t)(bi * pairs / P2_ORDER_ROWS) * 4096u + (uint32_t)(4095 - min(bj / P2_ORDER_COLS, 4095));
-        const uint32_t w = (uint32_t)min(t.n_steps >> P2_ORDER_SHIFT, 1023);
-        keys[slot] = order_by_work ? (uint32_t)t.n_steps : ((blk << 10) | w);
         ids[slot] = slot;
+        if (t.n_steps) atomicMax(total_steps + 1, (unsigned int)t.n_steps);    // longest tile of the launch
         if (t.n_steps) atomicAdd(total_steps, (unsigned int)min(t.n_steps, 1 << 16));
     }
+}
+
+// Queue order (descending key).  One round of the static schedule is a window of #clusters
+// consecutive entries that run in lock step, so a round lasts as long as its LONGEST tile, and its
+// tiles share operand strips in L2 only if they sit close together in the tile grid (a 256-genome
+// strip is 15 MB at C3, 51 MB at C5).  Primary key: work bucket (visited K blocks in ~16-32 coarse
+// classes) -- rounds of equal tiles; inside a bucket: locality blocks of 8 row tiles x 9 column
+// tiles, late rows first; inside a block: longest first.  Simulated on the C3 / C5 occupancy
+// (round-max efficiency, distinct strips per round): pure locality order 0.85 / 22 and 0.94 / 24,
+// pure work order 0.94 / 29 and 0.99 / 64 (DRAM-bound at C5), this order 0.94 / 30 and 0.98 / 36.
+__global__ void p2_keys_kernel(const P2Tile *__restrict__ tiles, int n_tiles, int pairs,
+                               const unsigned int *__restrict__ stats, uint32_t *__restrict__ keys)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tiles) return;
+    const P2Tile t = tiles[k];
+    int shift = 0;
+    while ((stats[1] >> shift) > 31u) ++shift;                 // <= 32 buckets over the launch's range
+    const uint32_t bucket = (uint32_t)t.n_steps >> shift;
+    const uint32_t blk = (uint32_t)(t.bi * pairs / P2_ORDER_ROWS) * 4096u + (uint32_t)(4095 - min(t.bj / P2_ORDER_COLS, 4095));
+    const uint32_t fine = shift >= 8 ? ((uint32_t)t.n_steps >> (shift - 8)) & 255u
+                                     : ((uint32_t)t.n_steps << (8 - shift)) & 255u;
+    keys[k] = (bucket << 26) | ((blk & 0x3ffffu) << 8) | fine;
 }
 
 // K schedule of one tile, identical for producer and MMA issuer: n_limbs == 0 -> one pass over
@@ -257,7 +271,7 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
             const unsigned int n_producers = 2u * PAIRS * (unsigned int)n_clusters;
             for (int round = 0; round * n_clusters < a.n_tiles; ++round) {
                 if (lock_step) {
-                    unsigned int *ctr = a.sync + 1 + round;
+                    unsigned int *ctr = a.sync + 2 + round;
                     atomicAdd(ctr, 1u);
                     unsigned int seen;
                     do {
@@ -555,8 +569,10 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
                                                             n_col_tiles,
                                                             ctx->d_p2_tiles.as<P2Tile>(), ctx->d_p2_masks.as<uint32_t>(),
                                                             keys_in, ids_in, counter,
-                                                            ctx->d_p2_sync.as<unsigned int>(),
-                                                            getenv("PC_I8_ORDER") && atoi(getenv("PC_I8_ORDER")) == 1);
+                                                            ctx->d_p2_sync.as<unsigned int>());
+        PC_CUDA(ctx, cudaGetLastError());
+        p2_keys_kernel<<<(int)((max_tiles + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_p2_tiles.as<P2Tile>(), (int)max_tiles, pairs, ctx->d_p2_sync.as<unsigned int>(), keys_in);
         PC_CUDA(ctx, cudaGetLastError());
     }
     PC_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->d_p2_temp.p, temp_bytes, keys_in, keys_out, ids_in,
@@ -592,7 +608,7 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
     else
         PC_CUDA(ctx, cudaLaunchKernelEx(&cfg, i8_pair_kernel<2>, map, map_quarter, args));
     PC_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 4;
     ctx->contract_launches++;
     PC_TRY(pc_stage_end(ctx));
     return PC_OK;
