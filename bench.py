@@ -611,8 +611,11 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
 
     gather_txt = ""
     if world > 1:
-        gather_txt = ("gather FUSED into the producing kernels (every row segment stored into all ranks' symmetric-"
-                      "memory triangles over NVLink, one device-side barrier)" if builder.fused is not None else
+        gather_txt = ((f"no collective: symmetric-memory triangles, {builder.push_blocks} row sub-blocks pushed to the peers "
+                       "by copy engines while the next one is computed, one device-side barrier"
+                       if builder.gather_mode == "push" else
+                       "gather FUSED into the producing kernels (every row segment stored into all ranks' symmetric-"
+                       "memory triangles over NVLink, one device-side barrier)") if builder.fused is not None else
                       f"one NCCL all-gather of the row blocks (no symmetric memory: {builder.fused_error})")
     if world == 1:
         parallelism = "1 GPU"

@@ -19,13 +19,12 @@ genome pairs (/root/reference/src/phamclust/matrix.py:471-491):
 
 Assembly of the row blocks, two consumers:
 
-* device (``sharded_matrix``): every rank ends up with the triangle.  On GPUs the gather is FUSED
-  into the kernels that produce the row block (``FusedTriangle`` + ``pc_matrix_rows_fused``): the
-  triangle lives in symmetric memory, and the contraction's epilogue (gcs/jc/pocp/af) or the aai/peq
-  epilogue stores every 128-byte row segment into its own triangle AND into the same place of every
-  peer's triangle over NVLink while the next tile is multiplied -- no separate collective, one
-  device-side barrier at the end.  Where symmetric memory is not available (and in the CPU tests)
-  the row blocks are exchanged with one NCCL / gloo all-gather;
+* device (``sharded_matrix``): every rank ends up with the triangle.  On GPUs the triangle lives in
+  symmetric memory (``FusedTriangle``) and no collective is called: either copy engines push each
+  finished row sub-block into the peers' triangles while the next sub-block is computed (default),
+  or the producing kernel's epilogue itself stores every row segment into all triangles over NVLink
+  (``pc_matrix_rows_fused``); one device-side barrier ends the step.  Where symmetric memory is not
+  available (and in the CPU tests) the row blocks are exchanged with one NCCL / gloo all-gather;
 * host (``sharded_matrix_to_host``; what the reference does next is host clustering): every rank
   copies its finished block from its own GPU over its own PCIe link into ONE triangle in POSIX
   shared memory (``SharedTriangle``) -- no device-side assembly, no single-link D2H.
@@ -185,17 +184,27 @@ class ShardedBuilder:
         self.n = len(table.genome_ptr) - 1
         self.align = metric in ALIGN_METRICS
         self.ops = backend_ops or _GpuOps(metric, as_distance, ppos)
+        self._row_weight = None
         if self.align or balance != "work" or self.world == 1:
             # aai/peq: the row-block stage is the dense epilogue, whose cost is the pair count
             self.bounds = row_partition(self.n, self.world)
         else:
-            self.bounds = row_partition(self.n, self.world, contraction_row_weights(table))
+            self._row_weight = contraction_row_weights(table)
+            bounds = row_partition(self.n, self.world, self._row_weight)
+            # whole 256-row tiles per rank (a tile cut by a boundary would be multiplied twice)
+            if self.n >= 512 * self.world:
+                for r in range(1, self.world):
+                    bounds[r] = min(max((bounds[r] + 128) // 256 * 256, bounds[r - 1]), self.n)
+            self.bounds = bounds
         self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.sizes = [tri_offset(self.n, self.bounds[r + 1]) - tri_offset(self.n, self.bounds[r])
                       for r in range(self.world)]
         self.exchange_records = 0           # records this rank received in the last exchange
         self.fused = None                   # FusedTriangle once the fused gather has been set up
         self.fused_error = None
+        self.gather_mode = os.environ.get("PC_GATHER", "push")     # "push" (copy engines) | "stores" (kernel)
+        self.push_blocks = int(os.environ.get("PC_PUSH_BLOCKS", "4"))
+        self._push_streams = None
 
     def load(self, table=None):
         """Host buffers -> this rank's device: the table, and for aai/peq only the genes of the
@@ -253,19 +262,77 @@ class ShardedBuilder:
         self.fused = fused
         return True
 
-    def gathered_triangle(self):
+    def gathered_triangle(self, mode=None):
         """Device consumer: the whole packed triangle on this rank's device after every rank has
-        computed its row block.  Fused path: the row block is stored into every rank's triangle by
-        the kernel that computes it; else row blocks + one all-gather (returned padded per rank:
-        use ``assemble_host``)."""
+        computed its row block.  With the symmetric-memory triangle set up, two ways to get a row
+        block into the peers' triangles (``mode``, default ``self.gather_mode``):
+
+        * ``"push"``: the kernels write this rank's triangle only; the block is cut into a few
+          row sub-blocks and, as soon as a sub-block is done, copy engines push it to every peer
+          (one stream per peer, ``cudaMemcpyAsync`` between peer-mapped buffers) while the next
+          sub-block is being computed -- no SM takes part in the transfer;
+        * ``"stores"``: the producing kernel itself stores every row segment into all triangles
+          (``pc_matrix_rows_fused``).  Measured: free at 2 GPUs, but an SM sustains well under
+          1 GB/s of peer stores, so from 4 GPUs on the epilogue becomes the bottleneck.
+
+        Without symmetric memory: row blocks + one all-gather (returned padded per rank: use
+        ``assemble_host``)."""
         if self.fused is None:
             return self.all_gather(self.row_block())
-        own, peers = self.fused.slice_ptrs(self.r0)
+        mode = mode or self.gather_mode
         acc = self.accumulators()
-        if self.r1 > self.r0:
-            self.ops.rows_fused(self.r0, self.r1, acc, own, peers)
-        self.fused.barrier()
-        return self.fused.tensor
+        if mode == "stores":
+            own, peers = self.fused.slice_ptrs(self.r0)
+            if self.r1 > self.r0:
+                self.ops.rows_fused(self.r0, self.r1, acc, own, peers)
+            self.fused.barrier()
+            return self.fused.tensor
+        import torch
+        fused = self.fused
+        peers = [p for p in range(self.world) if p != self.rank]
+        if self._push_streams is None:
+            self._push_streams = [torch.cuda.Stream(device=self.ops.device) for _ in peers]
+        main = torch.cuda.current_stream(self.ops.device)
+        cuts = self._push_cuts()
+        for a, b in zip(cuts, cuts[1:]):
+            if b <= a:
+                continue
+            lo, hi = tri_offset(self.n, a), tri_offset(self.n, b)
+            block = fused.tensor[lo:hi]
+            if self.align:
+                off = tri_offset(self.n, a) - tri_offset(self.n, self.r0)
+                self.ops.rows(a, b, acc[off:], out=block)
+            else:
+                self.ops.rows(a, b, None, out=block)
+            done = torch.cuda.Event()
+            done.record(main)
+            for stream, peer in zip(self._push_streams, peers):
+                with torch.cuda.stream(stream):
+                    stream.wait_event(done)
+                    fused.handle.get_buffer(peer, (hi - lo,), torch.int32, lo).copy_(block, non_blocking=True)
+        for stream in self._push_streams:
+            main.wait_stream(stream)
+        fused.barrier()
+        return fused.tensor
+
+    def _push_cuts(self):
+        """Row boundaries of the sub-blocks of this rank's block (about equal work each)."""
+        k = max(1, min(self.push_blocks, self.r1 - self.r0))
+        if k == 1 or self.align:
+            sub = row_partition(self.r1 - self.r0, k) if k > 1 else [0, self.r1 - self.r0]
+            # (pair-balanced cut of a block that starts at row r0 of an n-row triangle: good enough)
+            return [self.r0 + x for x in sub]
+        w = self._row_weight[self.r0:self.r1] if self._row_weight is not None else None
+        if w is None:
+            return [self.r0 + (self.r1 - self.r0) * i // k for i in range(k + 1)]
+        cum = np.concatenate(([0.0], np.cumsum(w)))
+        cuts = [self.r0]
+        for i in range(1, k):
+            c = int(np.searchsorted(cum, cum[-1] * i / k, side="left"))
+            cut = (self.r0 + c) // 256 * 256               # whole 256-row tiles of the contraction
+            cuts.append(min(max(cut, cuts[-1]), self.r1))
+        cuts.append(self.r1)
+        return cuts
 
     def all_gather(self, local, gathered=None):
         """Device consumer: every rank receives every row block (padded to the widest)."""

@@ -108,10 +108,13 @@ def _nccl_worker(rank, world, port, queue):
             # the gather fused into the producing kernels (peer stores over NVLink, symmetric memory)
             fused_ok = builder.enable_fused_gather()
             if fused_ok:
-                for _ in range(2):                                              # reuse of the triangle too
-                    tri = builder.gathered_triangle()
+                for mode in ("push", "stores", "push"):                         # reuse of the triangle too
+                    tri = builder.gathered_triangle(mode)
                     torch.cuda.synchronize()
-                    assert np.array_equal(tri.cpu().numpy(), got), (metric, "fused gather")
+                    assert np.array_equal(tri.cpu().numpy(), got), (metric, mode)
+                    tri.zero_()
+                    torch.cuda.synchronize()
+                    dist.barrier()
             shared = distributed.SharedTriangle(n, pin_rows=(builder.r0, builder.r1))
             try:
                 host = distributed.sharded_matrix_to_host(table, metric, shared, builder=builder).copy()
