@@ -318,6 +318,8 @@ class ShardedBuilder:
     def _push_cuts(self):
         """Row boundaries of the sub-blocks of this rank's block (about equal work each)."""
         k = max(1, min(self.push_blocks, self.r1 - self.r0))
+        if 4 * (tri_offset(self.n, self.r1) - tri_offset(self.n, self.r0)) < (64 << 20):
+            k = 1                                          # a small block: one launch, one push
         if k == 1 or self.align:
             sub = row_partition(self.r1 - self.r0, k) if k > 1 else [0, self.r1 - self.r0]
             # (pair-balanced cut of a block that starts at row r0 of an n-row triangle: good enough)
