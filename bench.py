@@ -563,7 +563,8 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
     else:
         contract_ms = timings["contract"]
         launches = max(counters["contract_launches"], 1)
-        per_launch_ms = contract_ms / launches
+        # one step may take several launches (row sub-blocks of the push gather): rates are per STEP
+        per_launch_ms = contract_ms / max(steps, 1)
         af_limbs = 1 if int(table.len_sum.max(initial=0)) <= 255 else 2
         limbs = {"gcs": 1, "jc": 1, "pocp": 2, "af": 2 * af_limbs}[metric]     # K multiplier of the operand
         if (engine or "auto") in ("i8mma", "i8mma_v1", "auto"):
@@ -589,10 +590,11 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
                         "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak,
                         "frac_of_2x_measured_bf16": tops / derived, "two_x_measured_bf16": derived,
                         "k_blocks_visited_frac": visited, "dense_equivalent_tops": dense_tops,
-                        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": algo_bytes,
+                        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_step": algo_bytes,
                         "kernel_ms_per_step": contract_ms / max(steps, 1),
                         "share_of_step": contract_ms / total_ms if total_ms else None,
-                        "algorithmic_ops_per_launch": ops, "k_columns": k_eff * limbs,
+                        "algorithmic_ops_per_step": ops, "launches_per_step": launches / max(steps, 1),
+                        "k_columns": k_eff * limbs,
                         "peak_basis": ("NOMINAL dense int8 tensor rate of the B200 (4500 TOP/s); the driver's "
                                        f"MEASURED_PEAKS.json ({peak_kind}) holds no int8 figure and 2 x its bf16 number "
                                        f"({derived:.0f}) is below what this kernel sustains on C5 (4.1 POP/s executed); "
