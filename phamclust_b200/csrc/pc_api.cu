@@ -1172,8 +1172,13 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
     // the configs are independent: fork them over a few streams (long ones first) so
     // that one config's tail (its last, longest alignments) overlaps the next config
     PC_TRY(pc_stage_begin(ctx, PC_T_ALIGN));
-    constexpr int N_DP_STREAMS = 4;
-    cudaEvent_t fork = nullptr, join[N_DP_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    constexpr int MAX_DP_STREAMS = 8;
+    static const int N_DP_STREAMS = [] {
+        const char *env = getenv("PC_DP_STREAMS");
+        const int v = env ? atoi(env) : 4;
+        return v >= 1 && v <= MAX_DP_STREAMS ? v : 4;
+    }();
+    cudaEvent_t fork = nullptr, join[MAX_DP_STREAMS] = {};
     PC_TRY(take_event(ctx, &fork));
     PC_CUDA(ctx, cudaEventRecord(fork, ctx->stream));
     for (int k = 0; k < N_DP_STREAMS; ++k) {
@@ -1184,10 +1189,27 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
     }
     for (int c = PC_NW_MULTI0; c < PC_NW_LEX0; ++c)       // size the shared spill buffer once
         if (cfg_info[c]) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
+    // launch order: the configs whose single alignments take longest go first (their tail -- a few
+    // warps finishing their last alignment -- is then covered by the kernels behind them), the
+    // configs of short alignments last (the step ends with a short tail).  Time of one alignment
+    // ~ rows x columns per lane x instructions per cell; rows ~ columns for members of one pham.
+    std::vector<std::pair<double, int>> order;
+    for (int c = 0; c < PC_NW_NCFG; ++c) {
+        if (cfg_info[c] == 0) continue;
+        int G, K;
+        pc_nw_cfg(c, G, K);
+        const bool multi = c >= PC_NW_MULTI0 && c < PC_NW_LEX0;
+        const double cols = (double)G * K * (multi ? 2.0 : 1.0);
+        const double per_cell = c >= PC_NW_LEX0 ? 1.0 : 1.7;
+        order.push_back({cols * K * (multi ? 2.0 : 1.0) * per_cell, c});
+    }
+    std::sort(order.begin(), order.end(), [](const std::pair<double, int> &x, const std::pair<double, int> &y) {
+        return x.first != y.first ? x.first > y.first : x.second > y.second;
+    });
     int next = 0;
-    for (int c = PC_NW_NCFG - 1; c >= 0; --c) {
+    for (const auto &entry : order) {
+        const int c = entry.second;
         const int64_t count = (int64_t)cfg_info[c];
-        if (count == 0) continue;
         a.task_base = (int64_t)cfg_info[PC_NW_NCFG + c];
         a.n_tasks = count;
         a.work_counter = ctx->d_counters.as<unsigned long long>() + c;

@@ -142,7 +142,7 @@ struct pc_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // D2H of finished row blocks, overlapped with compute
-    cudaStream_t dp_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // DP configs run side by side
+    cudaStream_t dp_streams[8] = {};             // DP configs run side by side
     cudaStream_t stream = nullptr;
     std::string err;
     int engine = PC_ENGINE_AUTO;
