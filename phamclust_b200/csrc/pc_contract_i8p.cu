@@ -269,14 +269,18 @@ i8_pair_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ 
             // most tiles are empty) skip it -- there a round lasts microseconds.
             const bool lock_step = a.lock_mode == 1 || (a.lock_mode == 0 && a.sync[0] >= (unsigned int)a.n_tiles * 64u);
             const unsigned int n_producers = 2u * PAIRS * (unsigned int)n_clusters;
+            bool in_step = lock_step;
             for (int round = 0; round * n_clusters < a.n_tiles; ++round) {
-                if (lock_step) {
+                if (in_step) {
                     unsigned int *ctr = a.sync + 2 + round;
                     atomicAdd(ctr, 1u);
-                    unsigned int seen;
+                    unsigned int seen, spins = 0;
                     do {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
                         if (seen < n_producers) __nanosleep(200);
+                        // lock step is an optimisation, never a dependency: if the grid is not
+                        // co-resident after all (a foreign kernel holds SMs) stop waiting for it
+                        if (++spins > (1u << 21)) { in_step = false; break; }
                     } while (seen < n_producers);
                 }
                 const int q = p2_queue_slot(round, cluster, n_clusters);
