@@ -518,8 +518,8 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
     if need_seqs:
         alu, instr, counts_state = dp_instruction_counts()
         cells = counters["dp_cells"]
-        lex_cells, lexr_cells = stats["lex_cells"], stats["lexr_cells"]
-        cls_cells = cells - lex_cells - lexr_cells
+        lex_cells, lexr_cells, lexc_cells = stats["lex_cells"], stats["lexr_cells"], stats.get("lexc_cells", 0)
+        cls_cells = cells - lex_cells - lexr_cells - lexc_cells
         align_ms = timings["align"]
         launches = max(counters["align_launches"], 1)
         gcups = cells / (align_ms * 1e-3) / 1e9 if align_ms > 0 else 0.0
@@ -528,14 +528,17 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
         # instructions per cell / the pipe's (resp. the issue ports') lanes per second
         alu_lanes = SM_COUNT * 64 * sm_mhz * 1e6
         issue_lanes = SM_COUNT * 128 * sm_mhz * 1e6
-        alu_work = lex_cells * alu["lex"] + lexr_cells * alu["lexr"] + cls_cells * alu["classic"]
-        issue_work = lex_cells * instr["lex"] + lexr_cells * instr["lexr"] + cls_cells * instr["classic"]
+        alu_work = (lex_cells * alu["lex"] + lexr_cells * alu["lexr"] + lexc_cells * alu["lexc"]
+                    + cls_cells * alu["classic"])
+        issue_work = (lex_cells * instr["lex"] + lexr_cells * instr["lexr"] + lexc_cells * instr["lexc"]
+                      + cls_cells * instr["classic"])
         peak = cells / (alu_work / alu_lanes) / 1e9 if alu_work else 0.0
         issue_peak = cells / (issue_work / issue_lanes) / 1e9 if issue_work else 0.0
         all_lex_peak = alu_lanes / alu["lex"] / 1e9
         traffic, traffic_src = ncu_traffic("dp")
         roofline = {"bound": "int-alu-pipe",
-                    "kernel": "nw_lex_kernel<G,K,B,REBASE> + nw_kernel<G,K> (global-alignment DP, one launch per config)",
+                    "kernel": "nw_lex_kernel<G,K,B,REBASE> + nw_lexc_kernel<K> + nw_kernel<G,K> (global-alignment DP, "
+                              "one launch per config)",
                     "achieved": gcups, "peak": peak, "unit": "GCUPS", "frac": gcups / peak if peak else None,
                     "frac_of_all_lex_bound": gcups / all_lex_peak if all_lex_peak else None,
                     "all_lex_peak": all_lex_peak,
@@ -543,7 +546,9 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
                     "cells_per_step": cells / max(steps, 1),
                     "cell_fractions": {"lex": lex_cells / cells if cells else None,
                                        "lexr": lexr_cells / cells if cells else None,
+                                       "lexc": lexc_cells / cells if cells else None,
                                        "classic": cls_cells / cells if cells else None},
+                    "lexc_fallbacks_per_step": stats.get("lexc_fallbacks", 0) / max(steps, 1),
                     "alu_instr_per_cell": alu, "instr_per_cell": instr, "instr_counts": counts_state,
                     "kernel_ms_per_step": align_ms / max(steps, 1),
                     "launches_per_step": launches / max(steps, 1),

@@ -80,6 +80,8 @@ __device__ __forceinline__ void load_ref_codes(const uint8_t *p, int (&rc)[K])
     }
 }
 
+int pc_nw_multichunk_warps(pc_ctx *ctx);
+
 template <int G, int K, bool MULTI, bool REPL, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
 {
@@ -114,15 +116,17 @@ __global__ void __launch_bounds__(THREADS, 1) nw_kernel(const NwArgs a)
     const int64_t warp_id = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
     int4 *spill = MULTI ? a.spill + warp_id * a.spill_stride : nullptr;
     const int2 *tab_lane = REPL ? s_tab + lane : s_tab;
+    // the LEXC fallback launch learns its task count from the device
+    const int64_t n_tasks = a.n_tasks_dev ? (int64_t)*a.n_tasks_dev : a.n_tasks;
 
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)SUBS);
         base = __shfl_sync(FULL, base, 0);
-        if ((int64_t)base >= a.n_tasks) break;
+        if ((int64_t)base >= n_tasks) break;
 
         const int64_t t = (int64_t)base + sub;
-        const bool valid = t < a.n_tasks;
+        const bool valid = t < n_tasks;
         int m = 0, n = 0;
         int64_t slot = 0;
         const uint8_t *q = a.codes, *r = a.codes;
@@ -469,6 +473,231 @@ static int launch_lex(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
     return PC_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// LEXC kernel: the rebased LEX word with the two COUNTERS rebased as well, in column chunks --
+// any length, any score range (pc_common.cuh, PC_NW_LEXC_*; executable model with the soundness
+// argument: oracle/lexc_model.c).  One warp per alignment.
+//
+//   word  = score << 22 | prio << 20 | (diagonal steps - base_d) << 10 | (matches - base_m)
+//   frame = (score base rb, base_d, base_m) per lane; rbU is the packed frame (mod 2^32) used to
+//           convert words between lanes, rbDM = (base_d + 512) << 16 | (base_m + 512) the centre
+//           column's true counters at the last re-centring
+// Every R = 8 row-steps a lane subtracts (centre word - C0) from all of its state, C0 = both
+// counter fields at 512, and CHECKS that every counter field then lies in [384, 640): one IMAD
+// (FMA pipe) + one LOP3 per word.  Every row-step the word pair received from the left lane (or
+// from the spilled boundary column of the previous chunk) is converted by the difference of the
+// two frames, the two lanes' counter bases are checked to be within 255 of each other and the
+// converted words to be inside the band.  While no check has failed no field has borrowed from
+// or carried into another, so every comparison and every counter is exact; a failed check lists
+// the alignment for the classic kernel (a.fallback_slots) instead of writing a result.
+// ---------------------------------------------------------------------------
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) nw_lexc_kernel(const NwArgs a)
+{
+    extern __shared__ __align__(16) int s_lex[];
+    const int lane = threadIdx.x & 31;
+    constexpr int open = PC_GAP_OPEN_DEFAULT, ext = PC_GAP_EXTEND_DEFAULT;
+    constexpr int G = 32, B = PC_NW_LEXC_BITS, R = PC_NW_LEXC_REBASE, BAND = PC_NW_LEXC_BAND;
+    constexpr int SH = 2 * B + 2;
+    constexpr int U = 1 << SH;
+    constexpr int CMASK = (1 << B) - 1;
+    constexpr int PRIO_E = (PC_H_PRIORITY_DIAG_DEL_INS ? 1 : 2) << (2 * B);
+    constexpr int PRIO_F = (PC_H_PRIORITY_DIAG_DEL_INS ? 2 : 1) << (2 * B);
+    constexpr int PRIO_D = 3 << (2 * B);
+    constexpr int PMASK = 3 << (2 * B);
+    constexpr int c0 = 1 << (B - 1);
+    constexpr int C0 = (c0 << B) | c0;                       // both counter fields centred
+    constexpr int LO = ((c0 - BAND) << B) | (c0 - BAND);     // lower edge of the band, both fields
+    constexpr int FTOP = CMASK & ~(2 * BAND - 1);            // bits a field inside the band never has (after - LO)
+    constexpr int TOPMASK = (FTOP << B) | FTOP;
+    constexpr int DBIAS = (PC_NW_LEXC_FRAME << 16) | PC_NW_LEXC_FRAME;
+    constexpr unsigned DMASK = 0xFE00FE00u;                  // frame difference outside [-255, 256]
+    constexpr int CU = (ext - open) * U;                     // opening a gap, drifted
+    constexpr int EDGE = (ext - open) * U + C0;              // boundary cells but (0, 0), initial frame
+    constexpr int ORIGIN = C0;                               // H^[0][0]
+    constexpr int NEG = EDGE + CU - 4 * U;                   // just under any opening from a boundary cell
+    constexpr int CAP = G * K;
+    static_assert(PC_GAP_TIE_EXTENDS, "the LEX priorities encode 'ties extend'");
+    static_assert((R & (R - 1)) == 0 && PC_NW_LEXR_WINDOW_OK(K, R), "LEXC: the score window of LEXR");
+    static_assert(2 * BAND == 256 && PC_NW_LEXC_FRAME == 255, "LEXC: the masks above");
+    const int one = a.gap_extend;                            // == 1 at run time, opaque to ptxas
+
+    for (int x = threadIdx.x; x < NW_TAB_CODES * NW_TAB_CODES * 32; x += THREADS) {
+        const int e = x >> 5;
+        const int2 v = a.subtab[(e / NW_TAB_CODES) * 32 + (e % NW_TAB_CODES)];
+        s_lex[x] = (v.x + 2 * ext) * U + PRIO_D + (1 << B) + (v.y >> 16);
+    }
+    __syncthreads();
+
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int QSTRIDE = NW_TAB_CODES * 32;
+    const int64_t warp_id = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    int4 *spill = a.spill + warp_id * a.spill_stride;
+    const int *tab_lane = s_lex + lane;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.work_counter, 1ull);
+        base = __shfl_sync(FULL, base, 0);
+        if ((int64_t)base >= a.n_tasks) break;
+
+        int64_t slot = a.task_base + (int64_t)base;
+        if (a.perm) slot = a.perm[slot];
+        const int qg = a.task_q[slot], rg = a.task_r[slot];
+        const int m = a.gene_len[qg], n = a.gene_len[rg];
+        const uint8_t *q = a.codes + a.gene_off[qg], *r = a.codes + a.gene_off[rg];
+        const int nchunks = (n + CAP - 1) / CAP;
+        const int steps = m + G - 1;
+
+        unsigned chk_all = 0;
+        bool flagged = false;
+        int res_word = 0, res_rb = 0, res_dm = 0;
+        for (int chunk = 0; chunk < nchunks && !flagged; ++chunk) {
+            const int col0 = chunk * CAP + lane * K;
+            int Hp[K], Fp[K], rc[K];
+            load_ref_codes<K, 5, true>(r + col0, rc);
+#pragma unroll
+            for (int x = 0; x < K; ++x) {
+                Hp[x] = EDGE;
+                Fp[x] = NEG;
+            }
+            int diagH = (col0 == 0) ? ORIGIN : EDGE;
+            int outH = C0, outE = NEG;
+            int rb = 0, rbDM = 0;
+            unsigned rbU = 0u - (unsigned)C0;
+            unsigned chk = 0;
+            int4 pre = make_int4(0, 0, 0, 0);
+            if (chunk > 0 && lane == 0 && m >= 1) pre = __ldcg(spill + 1);
+
+            for (int s = 1; s <= steps; ++s) {
+                if ((s & (R - 1)) == 0) {
+                    // re-centre on the middle column, then check the band (warp-uniform branch)
+                    const int wc = Hp[K / 2];
+                    const int nd = C0 - wc;                  // minus the shift of the frame
+                    const int ndl = nd - LO;
+                    rb += wc >> SH;
+                    rbU -= (unsigned)nd;
+                    rbDM += ((wc >> B) & CMASK) * 65536 + (wc & CMASK) - (c0 * 65536 + c0);
+#pragma unroll
+                    for (int x = 0; x < K; ++x) {
+                        chk |= (unsigned)(fma_add(Hp[x], one, ndl) & TOPMASK);
+                        Hp[x] = fma_add(Hp[x], one, nd);
+                        chk |= (unsigned)(fma_add(Fp[x], one, ndl) & TOPMASK);
+                        Fp[x] = fma_add(Fp[x], one, nd);
+                    }
+                    chk |= (unsigned)(fma_add(diagH, one, ndl) & TOPMASK);
+                    diagH = fma_add(diagH, one, nd);
+                    chk |= (unsigned)(fma_add(outH, one, ndl) & TOPMASK);
+                    outH = fma_add(outH, one, nd);
+                    chk |= (unsigned)(fma_add(outE, one, ndl) & TOPMASK);
+                    outE = fma_add(outE, one, nd);
+                    // lanes that hold padding columns only do not count; give up early
+                    if (__any_sync(FULL, chk != 0 && col0 < n)) { flagged = true; break; }
+                }
+                int inH = __shfl_up_sync(FULL, outH, 1);
+                int inE = __shfl_up_sync(FULL, outE, 1);
+                unsigned inB = __shfl_up_sync(FULL, rbU, 1);
+                int inDM = __shfl_up_sync(FULL, rbDM, 1);
+                const int i = s - lane;
+                const bool active = (i >= 1) && (i <= m);
+                if (lane == 0) {
+                    if (chunk == 0 || !active) {
+                        inH = EDGE; inE = NEG; inB = 0u - (unsigned)C0; inDM = 0;
+                    } else {
+                        inH = pre.x; inE = pre.y; inB = (unsigned)pre.z; inDM = pre.w;
+                        if (i < m) pre = __ldcg(spill + i + 1);
+                    }
+                }
+                const int conv = (int)(inB - rbU);           // sender's frame -> this lane's (mod 2^32)
+                inH += conv;
+                inE += conv;
+                if (active) {
+                    chk |= (unsigned)(inDM - rbDM + DBIAS) & DMASK;
+                    chk |= (unsigned)((inH - LO) & TOPMASK);
+                    chk |= (unsigned)((inE - LO) & TOPMASK);
+                    int qc = (int)(__ldg(q + (i - 1)) & 31u);
+                    if (qc >= NW_TAB_CODES) qc = 0;
+                    const int *trow = tab_lane + qc * QSTRIDE;
+                    int hl = inH, el = inE;
+                    int hd = diagH;
+                    diagH = inH;
+#pragma unroll
+                    for (int x = 0; x < K; ++x) {
+                        const int tw = trow[rc[x]];
+                        const int f = __viaddmax_s32(Hp[x], CU, Fp[x]) | PRIO_F;
+                        const int e = __viaddmax_s32(hl, CU, el) | PRIO_E;
+                        const int hdg = fma_add(hd, one, tw);
+                        const int h = __vimax3_s32(hdg, f, e) & ~PMASK;
+                        hd = Hp[x];
+                        hl = h;
+                        Hp[x] = h; Fp[x] = f;
+                        el = e;
+                    }
+                    outH = hl; outE = el;
+                    if (lane == G - 1 && chunk + 1 < nchunks)
+                        __stcg(spill + i, make_int4(outH, outE, (int)rbU, rbDM));
+                }
+            }
+            __syncwarp();
+            if (col0 < n) chk_all |= chk;
+            if (chunk == nchunks - 1) {
+                const int last = n - 1 - chunk * CAP;        // column index inside the chunk
+                if (lane == last / K) {
+                    const int xs = last % K;
+#pragma unroll
+                    for (int x = 0; x < K; ++x)
+                        if (x == xs) res_word = Hp[x];
+                    res_rb = rb;
+                    res_dm = rbDM;
+                }
+            }
+        }
+        flagged = flagged || __any_sync(FULL, chk_all != 0);
+        if (flagged) {
+            if (lane == 0) a.fallback_slots[atomicAdd(a.fallback_count, 1ull)] = slot;
+        } else {
+            if (lane == 0 && a.cell_counter)
+                atomicAdd(a.cell_counter + 3, (unsigned long long)m * (unsigned long long)n);
+            if (n == 0) {            // no DP columns: the answer is a boundary cell
+                if (lane == 0) {
+                    a.out_hitlen[slot] = (uint32_t)m;
+                    if (a.out_score) a.out_score[slot] = (m == 0) ? 0 : -open - (m - 1) * ext;
+                }
+            } else if (lane == ((n - 1) % CAP) / K) {
+                const int matched = (res_word & CMASK) + (res_dm & 0xffff) - c0;
+                const int columns = m + n - (((res_word >> B) & CMASK) + (res_dm >> 16) - c0);
+                a.out_hitlen[slot] = ((uint32_t)matched << 16) | (uint32_t)columns;
+                if (a.out_score) a.out_score[slot] = (res_word >> SH) + res_rb - (m + n) * ext;
+            }
+        }
+    }
+}
+
+template <int K>
+static int launch_lexc(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
+{
+    // a few registers more than the LEXR variant of the same K (frame, check word, prefetch)
+    constexpr int THREADS = K <= 16 ? 640 : K <= 22 ? 512 : 384;
+    const size_t smem = (size_t)NW_TAB_CODES * NW_TAB_CODES * 32 * sizeof(int);
+    auto kern = nw_lexc_kernel<K, THREADS>;
+    PC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 0;
+    PC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const int64_t want = (args.n_tasks + (THREADS / 32) - 1) / (THREADS / 32);
+    const int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    if ((int64_t)grid * (THREADS / 32) > pc_nw_multichunk_warps(ctx))
+        return pc_fail(ctx, PC_EINVAL, "LEXC launch of %d warps exceeds the spill region", grid * (THREADS / 32));
+    kern<<<grid, THREADS, smem, stream>>>(args);
+    PC_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->align_launches++;
+    return PC_OK;
+}
+
 // the G x K grid the chooser can pick (pc_nw_choose_cfg): K >= 16 for G >= 8
 #define PC_K_CASE(K_, CALL) case K_: if constexpr (G == 4 || K_ >= 16) { return CALL; } break;
 
@@ -548,6 +777,23 @@ static int launch_k(pc_ctx *ctx, const NwArgs &args, bool repl, int K, cudaStrea
     return pc_fail(ctx, PC_EINVAL, "no DP kernel for G=%d K=%d", G, K);
 }
 
+// the launch that re-runs what LEXC gave up on: classic <32, 20, multi-chunk> takes any length
+int pc_launch_nw_fallback(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream)
+{
+    if (args.n_tasks <= 0) return PC_OK;
+    return launch_gk<32, 20, true>(ctx, args, ctx->n_codes <= NW_TAB_CODES, stream);
+}
+
+__global__ void add_counter_kernel(unsigned long long *total, const unsigned long long *value)
+{
+    *total += *value;
+}
+
+void pc_launch_add_counter(unsigned long long *total, const unsigned long long *value, cudaStream_t stream)
+{
+    add_counter_kernel<<<1, 1, 0, stream>>>(total, value);
+}
+
 int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream)
 {
     if (args.n_tasks <= 0) return PC_OK;
@@ -556,6 +802,19 @@ int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream)
     const bool repl = ctx->n_codes <= NW_TAB_CODES;
     int G, K;
     pc_nw_cfg(cfg, G, K);
+    if (cfg >= PC_NW_LEXC0) {
+        if (!repl) return pc_fail(ctx, PC_EINVAL, "LEX DP config %d needs the 24-code table", cfg);
+        if (!args.spill || !args.fallback_count || !args.fallback_slots)
+            return pc_fail(ctx, PC_EINVAL, "LEXC DP config %d needs a spill region and a fallback list", cfg);
+        switch (K) {
+        case 16: return launch_lexc<16>(ctx, args, stream);
+        case 18: return launch_lexc<18>(ctx, args, stream);
+        case 20: return launch_lexc<20>(ctx, args, stream);
+        case 22: return launch_lexc<22>(ctx, args, stream);
+        case 24: return launch_lexc<24>(ctx, args, stream);
+        }
+        return pc_fail(ctx, PC_EINVAL, "no LEXC DP kernel for K=%d", K);
+    }
     if (cfg >= PC_NW_LEXR0) {
         if (!repl) return pc_fail(ctx, PC_EINVAL, "LEX DP config %d needs the 24-code table", cfg);
 #define PC_LEXR_CASE(K_) case K_: return launch_lex<32, K_, PC_NW_LEXR_BITS, PC_NW_LEXR_REBASE(K_)>(ctx, args, stream);

@@ -791,6 +791,8 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
     PC_TRY(pc_stage_end(ctx));
     dbg_mark("seqs: canonical ids");
     ctx->plan.part = ctx->plan.n_parts = -1;
+    ctx->lexc_off = false;
+    ctx->lexc_last_tasks = 0;
     ctx->seq_part = my_part;
     ctx->seq_parts = n_parts;
     ctx->have_seqs = true;
@@ -1071,7 +1073,7 @@ static void fill_nw_common(pc_ctx *ctx, NwArgs &a, int ppos)
     a.subtab = ctx->d_subtab[ppos ? 1 : 0].as<int2>();
     a.gap_open = PC_GAP_OPEN_DEFAULT;
     a.gap_extend = PC_GAP_EXTEND_DEFAULT;
-    a.cell_counter = ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG;
+    a.cell_counter = ctx->d_counters.as<unsigned long long>() + PC_CTR_CELLS;
 }
 
 // the LEX DP kernel needs the 24-code replicated table and the per-gene bounds
@@ -1080,25 +1082,63 @@ static bool lex_allowed(const pc_ctx *ctx)
     return PC_NW_LEX_ENABLED && ctx->dp_mode == PC_DP_AUTO && ctx->n_codes <= 24 && ctx->d_gene_hi.p;
 }
 
-// counters layout: [0..PC_NW_NCFG) work counters, [PC_NW_NCFG] cumulative cells of the classic
-// DP kernel, [PC_NW_NCFG + 1] of the LEX kernel, [PC_NW_NCFG + 2] of the rebased LEX kernel
+// counters layout: [0..PC_NW_NCFG) work counters, then cumulative cells of the classic DP kernel,
+// the LEX kernel, the rebased LEX kernel and the LEXC kernel, then the LEXC fallback: number of
+// listed alignments and the work counter of the launch that re-runs them, then the cumulative
+// number of alignments that fell back
 static int ensure_counters(pc_ctx *ctx)
 {
     if (!ctx->d_counters.p) {
-        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * (PC_NW_NCFG + 3)));
-        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * (PC_NW_NCFG + 3), ctx->stream));
+        PC_TRY(devbuf_reserve(ctx, ctx->d_counters, sizeof(unsigned long long) * PC_CTR_COUNT));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_CTR_COUNT, ctx->stream));
     }
     return PC_OK;
 }
 
-// every multi-chunk config gets its own spill region (they may run side by side)
-static int ensure_spill(pc_ctx *ctx, int max_qlen, NwArgs &a, int cfg)
+// every chunked config gets its own spill region (they may run side by side): the 4 classic
+// multi-chunk configs, the LEXC configs, and the launch that re-runs what LEXC gave up on
+#define PC_SPILL_REGIONS ((PC_NW_LEX0 - PC_NW_MULTI0) + PC_NW_LEXC_NK + 1)
+static int ensure_spill(pc_ctx *ctx, int max_qlen, NwArgs &a, int region)
 {
     a.spill_stride = (int64_t)max_qlen + 2;
     const int64_t warps = pc_nw_multichunk_warps(ctx);
-    const int n_multi = PC_NW_LEX0 - PC_NW_MULTI0;
-    PC_TRY(devbuf_reserve(ctx, ctx->d_spill, (size_t)n_multi * warps * a.spill_stride * sizeof(int4)));
-    a.spill = ctx->d_spill.as<int4>() + (size_t)(cfg - PC_NW_MULTI0) * warps * a.spill_stride;
+    PC_TRY(devbuf_reserve(ctx, ctx->d_spill, (size_t)PC_SPILL_REGIONS * warps * a.spill_stride * sizeof(int4)));
+    a.spill = ctx->d_spill.as<int4>() + (size_t)region * warps * a.spill_stride;
+    return PC_OK;
+}
+
+static bool cfg_spills(int cfg) { return (cfg >= PC_NW_MULTI0 && cfg < PC_NW_LEX0) || cfg >= PC_NW_LEXC0; }
+static int spill_region(int cfg)
+{
+    return cfg >= PC_NW_LEXC0 ? (PC_NW_LEX0 - PC_NW_MULTI0) + (cfg - PC_NW_LEXC0) : cfg - PC_NW_MULTI0;
+}
+
+// LEXC launches list the alignments whose band checks failed; `n_lexc` bounds the list
+static int prepare_fallback(pc_ctx *ctx, NwArgs &a, int64_t n_lexc)
+{
+    PC_TRY(devbuf_reserve(ctx, ctx->d_fallback, sizeof(int64_t) * (size_t)std::max<int64_t>(n_lexc, 1)));
+    unsigned long long *ctr = ctx->d_counters.as<unsigned long long>();
+    PC_CUDA(ctx, cudaMemsetAsync(ctr + PC_CTR_FALLBACK, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    a.fallback_count = ctr + PC_CTR_FALLBACK;
+    a.fallback_slots = ctx->d_fallback.as<int64_t>();
+    return PC_OK;
+}
+
+// ... and the classic multi-chunk kernel re-runs them (task count read on the device; an empty
+// list costs one launch of blocks that exit at once).  `stream` must be ordered after every LEXC launch.
+static int launch_fallback(pc_ctx *ctx, NwArgs a, int max_qlen, int64_t n_lexc, cudaStream_t stream)
+{
+    unsigned long long *ctr = ctx->d_counters.as<unsigned long long>();
+    PC_TRY(ensure_spill(ctx, max_qlen, a, PC_SPILL_REGIONS - 1));
+    a.perm = ctx->d_fallback.as<int64_t>();
+    a.task_base = 0;
+    a.n_tasks = n_lexc;
+    a.n_tasks_dev = ctr + PC_CTR_FALLBACK;
+    a.work_counter = ctr + PC_CTR_FALLBACK_WORK;
+    a.fallback_count = nullptr;
+    a.fallback_slots = nullptr;
+    PC_TRY(pc_launch_nw_fallback(ctx, a, stream));
+    pc_launch_add_counter(ctr + PC_CTR_FALLBACK_TOTAL, ctr + PC_CTR_FALLBACK, stream);
     return PC_OK;
 }
 
@@ -1131,6 +1171,7 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
     u.gene_len = ctx->d_gene_len.as<int32_t>();
     u.gene_hi = lex_allowed(ctx) ? ctx->d_gene_hi.as<int32_t>() : nullptr;
     u.coarse_k = ctx->n_codes > 24;
+    u.no_lexc = ctx->lexc_off ? 1 : 0;
     u.n_genomes = ctx->N;
     {
         int64_t blocks = (pl.n_units + 255) / 256;
@@ -1157,9 +1198,17 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
     PC_TRY(pc_launch_classify_units(ctx, u));
     unsigned long long cfg_info[2 * PC_NW_NCFG];
     PC_CUDA(ctx, cudaMemcpyAsync(cfg_info, pl.cfg_info.p, sizeof cfg_info, cudaMemcpyDeviceToHost, ctx->stream));
+    // how the previous call's LEXC launches fared on this data (read at the sync that is needed anyway)
+    unsigned long long prev_fallbacks = 0;
+    if (ctx->lexc_last_tasks > 0)
+        PC_CUDA(ctx, cudaMemcpyAsync(&prev_fallbacks, ctx->d_counters.as<unsigned long long>() + PC_CTR_FALLBACK,
+                                     sizeof prev_fallbacks, cudaMemcpyDeviceToHost, ctx->stream));
     PC_TRY(pc_launch_scatter_units(ctx, u, ctx->d_task_q.as<int32_t>(), ctx->d_task_r.as<int32_t>()));
     PC_TRY(pc_stage_end(ctx));
     PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // per-config task counts size the launches
+    // more than a third of the LEXC alignments went to the classic kernel as well: this data has
+    // long gaps, stop trying (takes effect at the next call; reset by pc_load_sequences)
+    if (ctx->lexc_last_tasks >= 64 && 3 * (int64_t)prev_fallbacks > ctx->lexc_last_tasks) ctx->lexc_off = true;
 
     NwArgs a;
     memset(&a, 0, sizeof a);
@@ -1178,6 +1227,10 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
         const int v = env ? atoi(env) : 4;
         return v >= 1 && v <= MAX_DP_STREAMS ? v : 4;
     }();
+    int64_t n_lexc = 0;
+    for (int c = PC_NW_LEXC0; c < PC_NW_NCFG; ++c) n_lexc += (int64_t)cfg_info[c];
+    ctx->lexc_last_tasks = n_lexc;
+    if (n_lexc) PC_TRY(prepare_fallback(ctx, a, n_lexc));   // zeroes its counters on ctx->stream: before the fork
     cudaEvent_t fork = nullptr, join[MAX_DP_STREAMS] = {};
     PC_TRY(take_event(ctx, &fork));
     PC_CUDA(ctx, cudaEventRecord(fork, ctx->stream));
@@ -1187,8 +1240,8 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
         PC_TRY(take_event(ctx, &join[k]));
         PC_CUDA(ctx, cudaStreamWaitEvent(ctx->dp_streams[k], fork, 0));
     }
-    for (int c = PC_NW_MULTI0; c < PC_NW_LEX0; ++c)       // size the shared spill buffer once
-        if (cfg_info[c]) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
+    for (int c = 0; c < PC_NW_NCFG; ++c)                  // size the shared spill buffer once
+        if (cfg_info[c] && cfg_spills(c)) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, spill_region(c)));
     // launch order: the configs whose single alignments take longest go first (their tail -- a few
     // warps finishing their last alignment -- is then covered by the kernels behind them), the
     // configs of short alignments last (the step ends with a short tail).  Time of one alignment
@@ -1198,7 +1251,7 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
         if (cfg_info[c] == 0) continue;
         int G, K;
         pc_nw_cfg(c, G, K);
-        const bool multi = c >= PC_NW_MULTI0 && c < PC_NW_LEX0;
+        const bool multi = cfg_spills(c);
         const double cols = (double)G * K * (multi ? 2.0 : 1.0);
         const double per_cell = c >= PC_NW_LEX0 ? 1.0 : 1.7;
         order.push_back({cols * K * (multi ? 2.0 : 1.0) * per_cell, c});
@@ -1207,14 +1260,30 @@ static int align_tasks(pc_ctx *ctx, int ppos, int part, int n_parts, UnitArgs &u
         return x.first != y.first ? x.first > y.first : x.second > y.second;
     });
     int next = 0;
+    std::vector<cudaEvent_t> lexc_done;
     for (const auto &entry : order) {
         const int c = entry.second;
         const int64_t count = (int64_t)cfg_info[c];
         a.task_base = (int64_t)cfg_info[PC_NW_NCFG + c];
         a.n_tasks = count;
         a.work_counter = ctx->d_counters.as<unsigned long long>() + c;
-        if (c >= PC_NW_MULTI0 && c < PC_NW_LEX0) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, c));
-        PC_TRY(pc_launch_nw(ctx, a, c, ctx->dp_streams[next++ % N_DP_STREAMS]));
+        if (cfg_spills(c)) PC_TRY(ensure_spill(ctx, pl.max_gene_len, a, spill_region(c)));
+        cudaStream_t st = ctx->dp_streams[next++ % N_DP_STREAMS];
+        PC_TRY(pc_launch_nw(ctx, a, c, st));
+        if (c >= PC_NW_LEXC0) {
+            cudaEvent_t ev = nullptr;
+            PC_TRY(take_event(ctx, &ev));
+            PC_CUDA(ctx, cudaEventRecord(ev, st));
+            lexc_done.push_back(ev);
+        }
+    }
+    if (n_lexc) {
+        // what LEXC gave up on, behind every LEXC launch (the stream that got the first -- longest --
+        // config: the LEXC configs are at the head of the order)
+        cudaStream_t st = ctx->dp_streams[0];
+        for (cudaEvent_t ev : lexc_done) PC_CUDA(ctx, cudaStreamWaitEvent(st, ev, 0));
+        PC_TRY(launch_fallback(ctx, a, pl.max_gene_len, n_lexc, st));
+        for (cudaEvent_t ev : lexc_done) ctx->deferred_events.push_back(ev);
     }
     for (int k = 0; k < N_DP_STREAMS; ++k) {
         PC_CUDA(ctx, cudaEventRecord(join[k], ctx->dp_streams[k]));
@@ -1590,7 +1659,7 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
                                  : PC_NW_MODE_CLASSIC;
         bucket[t] = pc_nw_choose_cfg(lq, lr, mode, ctx->n_codes > 24);
         bucket_count[bucket[t]]++;
-        if (bucket[t] >= PC_NW_MULTI0 && bucket[t] < PC_NW_LEX0)
+        if (cfg_spills(bucket[t]))
             max_q_multi = std::max(max_q_multi, ctx->h_gene_len[query_gene[t]]);
     }
     std::vector<int64_t> bucket_off(PC_NW_NCFG + 1, 0);
@@ -1617,14 +1686,22 @@ extern "C" int pc_alignment_identities(pc_ctx *ctx, int64_t n_tasks, const int32
         fill_nw_common(ctx, a, ppos);
         a.out_hitlen = ctx->d_hitlen.as<uint32_t>() + (size_t)ppos * n_tasks;
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * PC_NW_NCFG, ctx->stream));
+        int64_t n_lexc = 0;
+        for (int b = PC_NW_LEXC0; b < PC_NW_NCFG; ++b) n_lexc += bucket_count[b];
+        if (n_lexc) PC_TRY(prepare_fallback(ctx, a, n_lexc));
+        ctx->lexc_last_tasks = 0;             // the fallback counter no longer describes an align_tasks call
         PC_TRY(pc_stage_begin(ctx, PC_T_ALIGN));
         for (int b = PC_NW_NCFG - 1; b >= 0; --b) {
             if (bucket_count[b] == 0) continue;
             a.task_base = bucket_off[b];
             a.n_tasks = bucket_count[b];
             a.work_counter = ctx->d_counters.as<unsigned long long>() + b;
-            if (b >= PC_NW_MULTI0 && b < PC_NW_LEX0) PC_TRY(ensure_spill(ctx, max_q_multi, a, b));
+            if (cfg_spills(b)) PC_TRY(ensure_spill(ctx, max_q_multi, a, spill_region(b)));
             PC_TRY(pc_launch_nw(ctx, a, b, ctx->stream));
+        }
+        if (n_lexc) {
+            NwArgs fb = a;
+            PC_TRY(launch_fallback(ctx, fb, max_q_multi, n_lexc, ctx->stream));
         }
         PC_TRY(pc_stage_end(ctx));
         ctx->alignments += n_tasks;
@@ -1731,11 +1808,11 @@ extern "C" int pc_counters(pc_ctx *ctx, int64_t *launches, int64_t *dp_cells,
     PC_ENTER(ctx);
     unsigned long long cells = 0;
     if (ctx->d_counters.p) {
-        unsigned long long all[3] = {0, 0, 0};        // classic, LEX, rebased LEX
+        unsigned long long all[4] = {0, 0, 0, 0};     // classic, LEX, rebased LEX, LEXC
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PC_CUDA(ctx, cudaMemcpy(all, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG,
+        PC_CUDA(ctx, cudaMemcpy(all, ctx->d_counters.as<unsigned long long>() + PC_CTR_CELLS,
                                 sizeof all, cudaMemcpyDeviceToHost));
-        cells = all[0] + all[1] + all[2];
+        cells = all[0] + all[1] + all[2] + all[3];
     }
     if (launches) *launches = ctx->launches;
     if (dp_cells) *dp_cells = (int64_t)cells;
@@ -1756,12 +1833,15 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
     case PC_STAT_GENES: *out = ctx->n_genes; break;
     case PC_STAT_LEX_ALIGNMENTS: *out = ctx->lex_alignments; break;
     case PC_STAT_LEX_CELLS:
-    case PC_STAT_LEXR_CELLS: {
+    case PC_STAT_LEXR_CELLS:
+    case PC_STAT_LEXC_CELLS:
+    case PC_STAT_LEXC_FALLBACKS: {
         unsigned long long cells = 0;
         if (ctx->d_counters.p) {
+            const int at = which == PC_STAT_LEX_CELLS ? PC_CTR_CELLS + 1 : which == PC_STAT_LEXR_CELLS ? PC_CTR_CELLS + 2
+                         : which == PC_STAT_LEXC_CELLS ? PC_CTR_CELLS + 3 : PC_CTR_FALLBACK_TOTAL;
             PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG +
-                                                (which == PC_STAT_LEX_CELLS ? 1 : 2),
+            PC_CUDA(ctx, cudaMemcpy(&cells, ctx->d_counters.as<unsigned long long>() + at,
                                     sizeof cells, cudaMemcpyDeviceToHost));
         }
         *out = (int64_t)cells;
@@ -1789,12 +1869,15 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
         // cannot take for ANY residues (score bound of an all-W sequence: 11 per residue)
         const bool coarse = ctx->n_codes > 24, lex = lex_allowed(ctx);
         std::vector<char> reach(PC_NW_NCFG, 0);
-        for (int n = 1; n <= 4200; ++n)
+        for (int n = 1; n <= 4200; ++n) {
             for (int m = 1; m <= 4096; m *= 4) {
                 // cheapest and dearest residues (score bounds 0 and 11 per residue) span the modes
                 reach[pc_nw_choose_cfg(m, n, pc_nw_mode(m, n, 0, 0, lex), coarse)] = 1;
                 reach[pc_nw_choose_cfg(m, n, pc_nw_mode(m, n, 11 * m, 11 * n, lex), coarse)] = 1;
             }
+            // queries about as long as the ref (LEXC only takes those)
+            reach[pc_nw_choose_cfg(n, n, pc_nw_mode(n, n, 11 * n, 11 * n, lex), coarse)] = 1;
+        }
         int64_t count = 0;
         for (char c : reach) count += c;
         *out = count;
@@ -1819,8 +1902,8 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
     if (ctx->d_i8_steps.p)
         PC_CUDA(ctx, cudaMemsetAsync(ctx->d_i8_steps.p, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->d_counters.p) {
-        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_NW_NCFG, 0,
-                                     3 * sizeof(unsigned long long), ctx->stream));
+        PC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + PC_CTR_CELLS, 0,
+                                     (PC_CTR_COUNT - PC_CTR_CELLS) * sizeof(unsigned long long), ctx->stream));
         PC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return PC_OK;

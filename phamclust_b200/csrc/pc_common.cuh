@@ -84,6 +84,11 @@ struct NwArgs {
     unsigned long long *cell_counter;
     const int2 *subtab;          // [32*32] {score, 1 + (hit << 16)}
     int gap_open, gap_extend;
+    // LEXC: alignments whose band checks failed are listed here (slots) and re-run by the classic
+    // multi-chunk kernel, which then takes its task count from the device (n_tasks_dev)
+    unsigned long long *fallback_count;
+    int64_t *fallback_slots;
+    const unsigned long long *n_tasks_dev;   // nullable; overrides n_tasks (n_tasks still sizes the grid)
 };
 
 struct UnitArgs {
@@ -99,6 +104,7 @@ struct UnitArgs {
     const int32_t *gene_len;
     const int32_t *gene_hi;      // per-gene score bound; NULL = never use the LEX DP kernel
     int coarse_k;                // 1: the 32-code table is in use (K in multiples of 4 only)
+    int no_lexc;                 // 1: LEXC gave up on too many alignments of this data before
     int64_t n_genomes;
     // device-side bucketing of the units by DP kernel config
     int64_t units_per_block;     // contiguous units owned by one classify/scatter block
@@ -212,7 +218,9 @@ struct pc_ctx {
 
     // ---- aai work buffers ----
     AlignPlan plan;
-    DevBuf d_task_q, d_task_r, d_hitlen, d_score, d_spill, d_counters, d_perm;
+    DevBuf d_task_q, d_task_r, d_hitlen, d_score, d_spill, d_counters, d_perm, d_fallback;
+    bool lexc_off = false;           // LEXC fell back too often on the loaded sequences
+    int64_t lexc_last_tasks = 0;     // LEXC alignments of the previous align_tasks call
     DevBuf d_acc;                                  // uint64 accumulators (single-GPU path)
     DevBuf d_dest;                                 // [2][PC_MAX_DEST] record counts / write cursors per destination
     DevBuf d_out;                                  // int32 result staging
@@ -244,6 +252,14 @@ int pc_launch_pack_bits(pc_ctx *ctx, int source /*0 presence,1 copies,2 len*/,
 int pc_launch_popc_contract(pc_ctx *ctx, const PopcTerm *d_terms, int n_terms,
                             const EpilogueArgs &ep);
 int pc_launch_nw(pc_ctx *ctx, const NwArgs &args, int cfg, cudaStream_t stream);
+int pc_launch_nw_fallback(pc_ctx *ctx, const NwArgs &args, cudaStream_t stream);   // classic multi-chunk, any length
+void pc_launch_add_counter(unsigned long long *total, const unsigned long long *value, cudaStream_t stream);
+// ctx->d_counters: [0..PC_NW_NCFG) work counters of the DP launches, then
+#define PC_CTR_CELLS PC_NW_NCFG                  // cumulative DP cells: classic, LEX, LEXR, LEXC
+#define PC_CTR_FALLBACK (PC_NW_NCFG + 4)         // alignments LEXC listed for the classic kernel (this step)
+#define PC_CTR_FALLBACK_WORK (PC_NW_NCFG + 5)    // work counter of the launch that re-runs them
+#define PC_CTR_FALLBACK_TOTAL (PC_NW_NCFG + 6)   // cumulative
+#define PC_CTR_COUNT (PC_NW_NCFG + 8)
 int pc_launch_classify_units(pc_ctx *ctx, const UnitArgs &u);
 int pc_launch_scatter_units(pc_ctx *ctx, const UnitArgs &u, int32_t *task_q, int32_t *task_r);
 int pc_launch_gather_units(pc_ctx *ctx, const UnitArgs &u, const uint32_t *hitlen,
@@ -283,6 +299,9 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 //   LEXR (rebased LEX)   c = 140 + (K-16)/2, G = 32,  K in 16..32: 10-bit counters and a 10-bit
 //                        score field that every lane re-centres every few rows (pc_nw_lexr_ok:
 //                        min length < 1024, ref <= 1024 columns, any score range)
+//   LEXC (rebased LEX with rebased counters)  c = 149 + (K-16)/2, G = 32, K in 16..24, column
+//                        chunks: any length with |m - n| <= PC_NW_LEXC_MAXDIFF; an alignment whose
+//                        counters leave the band is re-run by the classic multi-chunk kernel
 // The chooser only ever picks K >= 16 for G >= 8 (a smaller G covers the same columns with less
 // pipeline fill), and multiples of 4 up to 32 when the 32-code table is in use; only those
 // combinations are instantiated (pc_align.cu).
@@ -292,7 +311,9 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #define PC_NW_LEX0 (PC_NW_MULTI0 + 4)
 #define PC_NW_LEXR0 (PC_NW_LEX0 + 4 * PC_NW_LEX_NK)
 #define PC_NW_LEXR_NK 9             // G = 32, K = 16, 18 .. 32
-#define PC_NW_NCFG (PC_NW_LEXR0 + PC_NW_LEXR_NK)
+#define PC_NW_LEXC0 (PC_NW_LEXR0 + PC_NW_LEXR_NK)
+#define PC_NW_LEXC_NK 5             // G = 32, K = 16, 18 .. 24, ceil(n / 32K) column chunks
+#define PC_NW_NCFG (PC_NW_LEXC0 + PC_NW_LEXC_NK)
 #define PC_NW_KMAX 32
 #define PC_NW_LEX_KMAX 48
 #define PC_NW_COST_PER_CELL 18      // relative cost model (the kernels are ALU-pipe bound)
@@ -317,10 +338,31 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #define PC_NW_LEXR_WINDOW_OK(K, R) \
     (PC_NW_LEXR_LIP * ((K) / 2 + (R)) + PC_GAP_OPEN_DEFAULT + PC_NW_LEXR_LIP + 8 < (1 << (32 - (2 * PC_NW_LEXR_BITS + 2) - 1)))
 #define PC_NW_LEXR_REBASE(K) ((K) <= 24 ? 8 : 4)   // row-steps between two re-centrings
+// LEXC word: the LEXR layout with the two counters stored relative to a per-lane base as well
+// (re-centred together with the score every R row-steps), so neither the length nor the score
+// range is bounded.  Unlike scores, counters of neighbouring cells have no proven bound on their
+// difference (two near-optimal routes may differ in their number of diagonal steps), so the kernel
+// CHECKS: after every re-centring all counter fields of a lane must lie within BAND of the centre
+// column's, neighbouring lanes' bases within FRAME of each other, every word received from the
+// neighbour within BAND after conversion.  While no check has failed no field has borrowed from or
+// carried into its neighbour (2 BAND + R < 2^(B-1) and BAND + R + FRAME + 1 <= 2^(B-1), see
+// oracle/lexc_model.c for the induction), so the result is exact; a failed check sends the
+// alignment to the classic kernel.  Long gaps are what breaks the band, hence MAXDIFF.
+#define PC_NW_LEXC_BITS 10
+#define PC_NW_LEXC_REBASE 8
+#define PC_NW_LEXC_BAND 128
+#define PC_NW_LEXC_FRAME 255
+#define PC_NW_LEXC_MAXDIFF 128
+#define PC_NW_LEXC_FALLBACK_CFG PC_NW_MULTI0    // classic <32, 20, multi-chunk>: any length
+static_assert(2 * PC_NW_LEXC_BAND + PC_NW_LEXC_REBASE < (1 << (PC_NW_LEXC_BITS - 1)) &&
+              PC_NW_LEXC_BAND + PC_NW_LEXC_REBASE + PC_NW_LEXC_FRAME + 1 <= (1 << (PC_NW_LEXC_BITS - 1)) &&
+              PC_NW_LEXC_BITS == PC_NW_LEXR_BITS,
+              "LEXC: the counter fields cannot borrow or carry while the checks hold");
 // which DP kernel family runs an alignment
 #define PC_NW_MODE_CLASSIC 0
 #define PC_NW_MODE_LEX 1
 #define PC_NW_MODE_LEXR 2
+#define PC_NW_MODE_LEXC 3
 
 #ifdef __CUDACC__
 #define PC_HD __host__ __device__
@@ -329,7 +371,10 @@ int pc_build_canonical_genes(pc_ctx *ctx);
 #endif
 PC_HD inline void pc_nw_cfg(int c, int &G, int &K)
 {
-    if (c >= PC_NW_LEXR0) {
+    if (c >= PC_NW_LEXC0) {
+        G = 32;
+        K = 16 + 2 * (c - PC_NW_LEXC0);
+    } else if (c >= PC_NW_LEXR0) {
         G = 32;
         K = 16 + 2 * (c - PC_NW_LEXR0);
     } else if (c >= PC_NW_LEX0) {
@@ -375,13 +420,26 @@ PC_HD inline bool pc_nw_lexr_ok(int m, int n)
 #endif
 }
 
+// LEXC takes what is left when the two lengths are close (a global alignment of sequences whose
+// lengths differ by d holds gaps of d columns at least, and long gaps break the counter band).
+PC_HD inline bool pc_nw_lexc_ok(int m, int n)
+{
+#if PC_NW_LEX_ENABLED
+    const int d = m < n ? n - m : m - n;
+    return d <= PC_NW_LEXC_MAXDIFF && n >= 1;
+#else
+    return false;
+#endif
+}
+
 // kernel family of an (m-row query, n-column ref) alignment; `allowed`: the 24-code table and
 // the per-gene bounds are available and the caller did not ask for the classic kernel only
-PC_HD inline int pc_nw_mode(int m, int n, int hi_q, int hi_r, bool allowed)
+PC_HD inline int pc_nw_mode(int m, int n, int hi_q, int hi_r, bool allowed, bool lexc = true)
 {
     if (!allowed) return PC_NW_MODE_CLASSIC;
     if (n <= 32 * PC_NW_LEX_KMAX && pc_nw_lex_ok(m, n, hi_q, hi_r)) return PC_NW_MODE_LEX;
     if (pc_nw_lexr_ok(m, n)) return PC_NW_MODE_LEXR;
+    if (lexc && pc_nw_lexc_ok(m, n)) return PC_NW_MODE_LEXC;
     return PC_NW_MODE_CLASSIC;
 }
 
@@ -398,6 +456,17 @@ PC_HD inline int pc_nw_choose_cfg(int m, int n, int mode, bool coarse)
         K = (K + 1) & ~1;
         if (K < 16) K = 16;
         return PC_NW_LEXR0 + (K - 16) / 2;
+    }
+    if (mode == PC_NW_MODE_LEXC) {
+        int best_c = PC_NW_LEXC0;
+        long long best_cost = -1;
+        for (int c = PC_NW_LEXC0; c < PC_NW_LEXC0 + PC_NW_LEXC_NK; ++c) {
+            const int K = 16 + 2 * (c - PC_NW_LEXC0);
+            const long long chunks = (n + 32 * K - 1) / (32 * K);
+            const long long cost = chunks * (long long)(m + 31) * (K * (long long)PC_NW_LEX_COST_PER_CELL + 22);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+        }
+        return best_c;
     }
     const bool lex = mode == PC_NW_MODE_LEX;
     int best = PC_NW_LEX0 - 1;

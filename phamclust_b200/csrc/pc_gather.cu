@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(UNIT_THREADS) classify_units_kernel(const Unit
                 const uint64_t h = ht_insert(u.ht_keys, u.ht_mask, ((uint64_t)cq << 32) | cr, &inserted);
                 if (inserted) {
                     const int lq = u.gene_len[cq], lr = u.gene_len[cr];
-                    const int mode = u.gene_hi ? pc_nw_mode(lq, lr, u.gene_hi[cq], u.gene_hi[cr], true)
+                    const int mode = u.gene_hi ? pc_nw_mode(lq, lr, u.gene_hi[cq], u.gene_hi[cr], true, !u.no_lexc)
                                                : PC_NW_MODE_CLASSIC;
                     const int cfg = pc_nw_choose_cfg(lq, lr, mode, u.coarse_k != 0);
                     const unsigned int rank = atomicAdd(&s_cnt[cfg], 1u);

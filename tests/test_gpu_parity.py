@@ -243,7 +243,9 @@ def test_every_reachable_dp_config_is_launched_and_bit_exact(gpu_ctx, dp_mode):
     seqs = list(short)
     q, r = [], []
     lengths = sorted({g * k - d for g in (4, 8, 16, 32) for k in range(8, 50, 2) for d in (0, 1)}
-                     | {1537, 1700, 2049, 2300, 2561, 2700, 3000})
+                     | {1537, 1700, 2049, 2300, 2561, 2700, 3000}
+                     # twins of these lengths land in every LEXC config (K = 16 .. 24, 2 column chunks)
+                     | {1030, 1100, 1270, 1400, 1530})
     for n in lengths:
         ref = testdata.random_protein(rng, n, n, testdata.AA if n % 3 else "AG")
         twin = testdata.mutate(rng, ref, 0.3, testdata.AA)
@@ -331,6 +333,99 @@ def test_rebased_lex_kernel_long_alignments(gpu_ctx):
     assert stats["lexr_cells"] > 0, stats
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, [(len(seqs[q[k]]), len(seqs[r[k]]), got[k].tolist(), want[k].tolist()) for k in bad[:5]]
+
+
+def test_lexc_kernel_any_length(gpu_ctx):
+    """LEXC: what neither LEX nor LEXR can take (min length >= 1024, or a ref of more than 1024
+    columns) and whose two lengths differ by at most 128 runs on the rebased LEX word with REBASED
+    COUNTERS, in column chunks.  The kernel checks its counter band and hands an alignment to the
+    classic kernel when a check fails, so every result must equal the explicit-traceback oracle
+    whichever way it went: homologs with small indels (stay on LEXC), lengths at every chunk edge
+    (32 x K columns, K = 16 .. 24), all-W / single-letter / tie-rich inputs, and pairs built to
+    break the band (a + b against b + a, a 300-residue block moved, unrelated sequences)."""
+    rng = random.Random(1536)
+    seqs, q, r = [], [], []
+
+    def pair(a, b):
+        seqs.extend([a, b])
+        q.extend([len(seqs) - 2, len(seqs) - 1])
+        r.extend([len(seqs) - 1, len(seqs) - 2])
+
+    for n in (1024, 1025, 1030, 1087, 1088, 1151, 1152, 1153, 1279, 1280, 1281, 1407, 1408, 1409, 1500, 1535, 1536,
+              1537, 1600, 1727, 1728, 1900, 2047, 2048, 2049, 2111, 2112, 2303, 2304, 2305, 2600, 3071, 3072, 3300):
+        for alpha, rate in ((testdata.AA, 0.05), (testdata.AA, 0.3), ("AG", 0.1)):
+            a = testdata.random_protein(rng, n, n, alpha)
+            pair(a, testdata.mutate(rng, a, rate, alpha))
+    # short query / long ref inside the length window: m < 1024 <= n
+    for m, n in ((960, 1060), (1000, 1128), (1023, 1025), (950, 1078)):
+        a = testdata.random_protein(rng, n, n, testdata.AA)
+        pair(testdata.mutate(rng, a, 0.2, testdata.AA)[:m], a)
+    for k in (1024, 1100, 1536, 2000):
+        pair("W" * k, "W" * (k + 7))
+        pair("A" * k, "A" * (k - 3))
+        pair("AG" * (k // 2), "GA" * (k // 2) + "A")
+    n_band_ok = len(q)
+    # built to leave the band: the checks must catch all of them
+    for k in (600, 800, 1100):
+        a, b = testdata.random_protein(rng, k, k, testdata.AA), testdata.random_protein(rng, k, k, testdata.AA)
+        pair(a + b, b + a)
+    for k in (1300, 1800):
+        a = testdata.random_protein(rng, k, k, testdata.AA)
+        pair(a, a[:200] + a[500:] + a[200:500])
+        pair(a, testdata.random_protein(rng, k + 40, k + 40, testdata.AA))
+        pair(a, testdata.mutate(rng, a, 0.7, testdata.AA))
+    _load(gpu_ctx, _genes_table(seqs))
+    off, res = _arena(seqs)
+    want = nw_c.batch(res, off, q, r, mode=0)
+    gpu_ctx.set_dp_mode("auto")
+    gpu_ctx.reset_counters()
+    got = gpu_ctx.alignment_identities(q, r)
+    stats = gpu_ctx.stats()
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, [(len(seqs[q[k]]), len(seqs[r[k]]), got[k].tolist(), want[k].tolist()) for k in bad[:5]]
+    assert stats["lexc_cells"] > 0, stats
+    # the hook runs every task twice (identity and ppos tables); the band-breaking pairs fall back,
+    # the homologs do not (a handful may, where a mutated copy happens to open a long gap)
+    assert 2 * 6 <= stats["lexc_fallbacks"] <= 2 * (len(q) - n_band_ok) + n_band_ok // 4, stats
+    # and the classic kernel alone gives the same
+    gpu_ctx.set_dp_mode("classic")
+    try:
+        assert np.array_equal(gpu_ctx.alignment_identities(q, r), want)
+    finally:
+        gpu_ctx.set_dp_mode("auto")
+
+
+def test_lexc_gives_up_on_data_with_long_gaps(gpu_ctx):
+    """One pham of twelve 1300-residue genes that are rearrangements of each other (a + b, b + a,
+    a block moved): every alignment breaks LEXC's counter band and is re-run by the classic kernel
+    -- the matrix must equal the oracle's -- and since more than a third fell back, the next call
+    on the same sequences does not try LEXC again."""
+    rng = random.Random(77)
+    a, b, c = (testdata.random_protein(rng, k, k, testdata.AA) for k in (650, 650, 300))
+    variants = [a + b, b + a, a[:300] + b + a[300:], b[:200] + a + b[200:], c + a + b[:350], a + b[:350] + c,
+                b + c + a[:350], a[350:] + b + c + a[:50], b[:325] + a + b[325:], a[:500] + c + b + a[500:550],
+                c + b + a[:350], b[300:] + a + b[:300]]
+    variants = [v[:1300] for v in variants]
+    genomes = [Genome(f"g{k}") for k in range(len(variants))]
+    for k, (g, v) in enumerate(zip(genomes, variants)):
+        g.add("pham1", testdata.mutate(rng, v, 0.05))
+        g.add(f"own{k}", testdata.random_protein(rng, 50, 50, testdata.AA))
+    table = pack_genomes(genomes)
+    _load(gpu_ctx, table)
+    gpu_ctx.reset_counters()
+    first = gpu_ctx.matrix("peq", as_distance=True).astype(np.int64)
+    s1 = gpu_ctx.stats()
+    second = gpu_ctx.matrix("aai", as_distance=True).astype(np.int64)
+    s2 = gpu_ctx.stats()
+    third = gpu_ctx.matrix("peq", as_distance=True).astype(np.int64)
+    s3 = gpu_ctx.stats()
+    assert s1["lexc_fallbacks"] > 22, s1                      # 66 alignments, more than a third gave up
+    assert s2["lexc_fallbacks"] >= s1["lexc_fallbacks"]       # the second call learns it at its sync ...
+    assert s3["lexc_fallbacks"] == s2["lexc_fallbacks"] and s3["lexc_cells"] == s2["lexc_cells"], (s2, s3)   # ... the third skips LEXC
+    ref_genomes = unpack_genomes(table)
+    assert np.abs(first - _oracle_triangle(ref_genomes, "peq", True)).max() <= FLOAT_TOL_MICRO
+    assert np.abs(second - _oracle_triangle(ref_genomes, "aai", True)).max() <= FLOAT_TOL_MICRO
+    assert np.array_equal(first, third)
 
 
 def test_non_standard_residues_and_case(gpu_ctx, dp_mode):

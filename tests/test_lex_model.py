@@ -85,3 +85,60 @@ def test_rebased_lex_word_equals_the_traceback_oracle():
     got, _ = lex_model.lexr_stats(long_a[:200], long_a[5:190], 32, 16, 8, bits=10, ppos=True)
     ident, similar, length, score = nw_c.forward_stats(long_a[:200], long_a[5:190])
     assert got == (ident + similar, length, score)
+
+
+def test_lexc_model_equals_the_oracle_or_raises_its_flag():
+    """LEXC (nw_lexc_kernel): score AND counters re-centred per lane, column chunks, band checks.
+    oracle/lexc_model.c executes the kernel's arithmetic word for word.  Whatever the input, the
+    model either reports the oracle's (identical, length, score) or raises the fallback flag --
+    and it never sees a counter field borrow or carry while the flag is still clear (``broke``),
+    which is the induction the kernel's exactness rests on."""
+    from oracle import lexc_c
+    rng = random.Random(1536)
+    cases = []
+    for n in (1024, 1025, 1100, 1279, 1280, 1281, 1536, 1537, 2049, 2305):
+        a = testdata.random_protein(rng, n, n, testdata.AA)
+        cases.append((a, testdata.mutate(rng, a, 0.05), False))
+        cases.append((testdata.mutate(rng, a, 0.3), a, False))
+    ag = testdata.random_protein(rng, 1200, 1200, "AG")
+    cases += [(ag, testdata.mutate(rng, ag, 0.1, "AG"), False), ("W" * 1100, "W" * 1107, False),
+              ("A" * 1030, "A" * 1027, False), ("AG" * 550, "GA" * 550 + "A", False)]
+    a, b = testdata.random_protein(rng, 700, 700, testdata.AA), testdata.random_protein(rng, 700, 700, testdata.AA)
+    c = testdata.random_protein(rng, 1400, 1400, testdata.AA)
+    cases += [(a + b, b + a, True), (c, c[:200] + c[500:] + c[200:500], True),
+              (c, testdata.random_protein(rng, 1440, 1440, testdata.AA), None),
+              (c[:300], c, None), (c, c[:300], None)]            # far outside MAXDIFF: flagged or exact
+    flagged = 0
+    for q, r, expect_flag in cases:
+        ident, similar, length, score = nw_c.forward_stats(q, r)
+        for ppos in (False, True):
+            for K in (lexc_c.choose_k(len(q), len(r)), 16, 24):
+                got = lexc_c.align(q, r, K=K, ppos=ppos)
+                assert not (got["broke"] and not got["flagged"]), (len(q), len(r), K, got)
+                if expect_flag is not None:
+                    assert bool(got["flagged"]) == expect_flag, (len(q), len(r), K, got)
+                if got["flagged"]:
+                    flagged += 1
+                    continue
+                assert (got["matched"], got["columns"], got["score"]) == (
+                    ident + (similar if ppos else 0), length, score), (len(q), len(r), K, got)
+                assert got["field_dev"] <= lexc_c.BAND + lexc_c.REBASE and got["frame_dev"] <= 256
+                assert got["score_field"] < 512
+    assert flagged >= 12
+
+
+def test_lexc_model_small_and_degenerate_inputs():
+    """Short sequences run through the same code (one chunk, most lanes padding only)."""
+    from oracle import lexc_c
+    rng = random.Random(5)
+    for t in range(60):
+        alpha = ["AG", "WC", testdata.AA][t % 3]
+        a = testdata.random_protein(rng, 1, 90, alpha)
+        b = testdata.mutate(rng, a, 0.3, alpha) if t % 2 else testdata.random_protein(rng, 1, 90, alpha)
+        ident, similar, length, score = nw_c.forward_stats(a, b)
+        got = lexc_c.align(a, b, K=16)
+        if not got["flagged"]:
+            assert (got["matched"], got["columns"], got["score"]) == (ident, length, score), (a, b, got)
+        assert not (got["broke"] and not got["flagged"])
+    got = lexc_c.align("MKT", "", K=16)
+    assert (got["matched"], got["columns"], got["score"], got["flagged"]) == (0, 3, -13, 0)

@@ -4,7 +4,7 @@ library that is actually shipped, instead of hand-counted literals.
 
     python tools/sass_roofline.py            # writes profiles/sass_dp_instr.json + SASS excerpts
 
-For one representative config of each DP kernel family (plain LEX, rebased LEX, classic) the
+For one representative config of each DP kernel family (plain LEX, rebased LEX, LEXC, classic) the
 script disassembles the function with ``cuobjdump -sass``, finds the row-step loop (the
 backward branch whose body holds the VIMNMX3 cell chain), and counts its instructions by issue
 pipe (B300_MICROARCH.md "fma vs alu split": IMAD/FFMA on the FMA pipe; IADD3/LOP3/SHF/PRMT/
@@ -31,6 +31,9 @@ FAMILIES = {
     "lex": (r"_Z13nw_lex_kernelILi8ELi32ELi\d+ELi9ELi0EEv6NwArgs", 32, 0),
     "lexr": (r"_Z13nw_lex_kernelILi32ELi24ELi\d+ELi10ELi8EEv6NwArgs", 24, 8),
     "classic": (r"_Z9nw_kernelILi32ELi24ELb0ELb1ELi\d+EEv6NwArgs", 24, 0),
+    # LEXC: per row-step the conversion and band checks of the received words, every 8 row-steps the
+    # re-centring with its checks (2 IMAD + 1 LOP3 per state word)
+    "lexc": (r"_Z14nw_lexc_kernelILi20ELi\d+EEv6NwArgs", 20, 8),
 }
 FMA_PIPE = ("IMAD", "FFMA", "FMUL", "FADD", "HFMA2", "HADD2", "HMUL2")
 LSU = ("LDS", "LDG", "STG", "STS", "SHFL", "ATOM", "RED", "LDC", "LDCU", "LDL", "STL", "LD", "ST")
