@@ -592,11 +592,15 @@ int pc_i8_pair_contract(pc_ctx *ctx, int n_limbs, int64_t p_pad, int64_t row_byt
     args.n_tiles = (int)max_tiles;
     args.tile_steps = ctx->d_i8_steps.as<unsigned long long>();
     args.sync = ctx->d_p2_sync.as<unsigned int>();
-    args.lock_mode = getenv("PC_I8_LOCK") ? atoi(getenv("PC_I8_LOCK")) : 0;
     args.ep = ep;
     // one cluster (CTA pair, or two pairs) per TPC group that can host it; fewer when there are fewer tiles
     int clusters = clusters_of[pairs];
     if ((int64_t)clusters > max_tiles) clusters = (int)max_tiles;
+    // Lock step pays once the pairs have rounds enough to drift apart: measured on one GPU
+    // (tools/probe_lock_threshold.py, profiles/r2_lock_probe.txt) 10 000 genomes x 58k-95k columns
+    // (11 rounds) run 3-4 % FASTER without it, 16 000 x 93k (27 rounds) 7 % slower, 20 000 x 154k
+    // (43 rounds) 35 % slower.  PC_I8_LOCK = 1 / 2 forces it on / off.
+    args.lock_mode = getenv("PC_I8_LOCK") ? atoi(getenv("PC_I8_LOCK")) : (max_tiles > 16 * (int64_t)clusters ? 0 : 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs * clusters));
     cfg.blockDim = dim3(P2_THREADS);
