@@ -11,6 +11,10 @@
 #include <chrono>
 #include <climits>
 #include <thread>
+#include <unistd.h>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 
 #include "pc_common.cuh"
 
@@ -283,6 +287,81 @@ static int host_threads(int64_t work)
     return (int)std::max(1u, std::min(8u, hw / 2));
 }
 
+// A small persistent pool: the host passes over the table are short (fractions of a millisecond),
+// and a step runs a dozen of them -- spawning and joining T threads for each cost more than the
+// passes themselves (about 0.1 ms per pass).  One job at a time; a second caller (another context
+// on another host thread) simply spawns its own threads as before.
+namespace {
+class HostPool {
+public:
+    static HostPool &get() { static HostPool pool; return pool; }
+
+    template <typename F>
+    bool run(int T, F &&body)
+    {
+        if (getpid() != pid_) return false;          // a forked child has no workers
+        std::unique_lock<std::mutex> job_lock(job_mutex_, std::try_to_lock);
+        if (!job_lock.owns_lock()) return false;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            while ((int)workers_->size() < T - 1) {
+                const int id = (int)workers_->size();
+                workers_->emplace_back([this, id] { work(id); });
+            }
+            fn_ = [&body](int t) { body(t); };
+            active_ = T - 1;
+            pending_ = T - 1;
+            ++generation_;
+        }
+        cv_.notify_all();
+        body(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+        return true;
+    }
+
+private:
+    HostPool() : pid_(getpid()) {}
+    ~HostPool()
+    {
+        if (getpid() != pid_) return;               // forked child: the thread objects are not ours, leak them
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &w : *workers_) w.join();
+        delete workers_;
+    }
+
+    void work(int id)
+    {
+        unsigned long long seen = 0;
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_.wait(lk, [&] { return stop_ || (generation_ != seen && id < active_); });
+            if (stop_) return;
+            seen = generation_;
+            auto fn = fn_;
+            lk.unlock();
+            fn(id + 1);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+
+    std::mutex job_mutex_, m_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> *workers_ = new std::vector<std::thread>();
+    std::function<void(int)> fn_;
+    unsigned long long generation_ = 0;
+    int active_ = 0, pending_ = 0;
+    bool stop_ = false;
+    const pid_t pid_;
+};
+}  // namespace
+
 template <typename F>
 static void run_threads(int T, F &&body)
 {
@@ -290,6 +369,8 @@ static void run_threads(int T, F &&body)
         body(0);
         return;
     }
+    static const bool use_pool = getenv("PC_HOST_POOL") == nullptr || atoi(getenv("PC_HOST_POOL")) != 0;
+    if (use_pool && HostPool::get().run(T, body)) return;
     std::vector<std::thread> pool;
     pool.reserve(T - 1);
     for (int t = 1; t < T; ++t) pool.emplace_back([&body, t] { body(t); });
