@@ -532,7 +532,6 @@ extern "C" int pc_load_table(pc_ctx *ctx, int64_t n_genomes, int64_t n_phams,
     for (int64_t p = 0; p < n_phams; ++p) pham_count[p + 1] += pham_count[p];
 
     ctx->N = n_genomes; ctx->P = n_phams; ctx->nnz = nnz;
-    ctx->h_pham_members.clear();
     ctx->deal_parts = -1;
     ctx->resident_n = -1;
     ctx->bits_ready = false;
@@ -622,115 +621,180 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
     if (total > 0 && !residues) return pc_fail(ctx, PC_EINVAL, "residues is NULL");
 
     dbg_mark("seqs: enter");
-    // which genes this rank needs: those of the entries whose pham it aligns
-    std::vector<uint8_t> owned;              // per gene (partial loads only)
+    std::vector<int32_t> &gene_len = ctx->h_gene_len;
+    std::vector<int64_t> &gene_off = ctx->h_gene_off;
+    ctx->have_seqs = false;
+    gene_len.resize(n_genes);
+    gene_off.resize(n_genes + 1);
+    struct SeqPart {
+        int64_t padded = 0, err_at = INT64_MAX, raw = 0, sum_err_at = INT64_MAX;
+        int32_t max_len = 0;
+        std::string err, sum_err;
+    };
+    // a gene's length, or -1 with the reason in `me`
+    auto checked_len = [&](int64_t g, SeqPart &me) -> int64_t {
+        const int64_t len = seq_off[g + 1] - seq_off[g];
+        char buf[200];
+        if (len < 0) {
+            snprintf(buf, sizeof buf, "seq_off is not monotone at gene %lld", (long long)g);
+            me.err_at = g; me.err = buf;
+            return -1;
+        }
+        if (len > 32767) {
+            snprintf(buf, sizeof buf,
+                     "gene %lld has %lld residues; the alignment counters hold at most 32767 "
+                     "(parasail's 16-bit scores are undefined there anyway)", (long long)g, (long long)len);
+            me.err_at = g; me.err = buf;
+            return -1;
+        }
+        return len;
+    };
+    auto len_sum_error = [&](int64_t e, int64_t sum, SeqPart &me) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "len_sum[%lld]=%u but its genes sum to %lld", (long long)e, ctx->h_len_sum[e], (long long)sum);
+        me.sum_err_at = e; me.sum_err = buf;
+    };
+    // the error a serial scan would meet first: a bad offset / length before any len_sum mismatch
+    auto first_error = [&](const std::vector<SeqPart> &parts) -> const std::string * {
+        const SeqPart *bad = nullptr;
+        for (const SeqPart &sp : parts)
+            if (sp.err_at != INT64_MAX && (!bad || sp.err_at < bad->err_at)) bad = &sp;
+        if (bad) return &bad->err;
+        for (const SeqPart &sp : parts)
+            if (sp.sum_err_at != INT64_MAX && (!bad || sp.sum_err_at < bad->sum_err_at)) bad = &sp;
+        return bad ? &bad->sum_err : nullptr;
+    };
+    int64_t cursor = 0;
     if (partial) {
+        // This rank needs the genes of the entries whose pham it aligns (deal_phams).  Two passes
+        // over the ENTRIES (an entry's genes are consecutive): lengths, checks and sizes, then --
+        // with every thread's share of the arena and of the staging known -- offsets and the
+        // gather of the owned residues into page-locked staging (1 / n_parts of the arena); the
+        // device sees length 0 for every other gene.
         deal_phams(ctx, n_parts);
         dbg_mark("seqs: phams dealt");
-        owned.assign((size_t)n_genes, 0);
-        const int To = host_threads(ctx->nnz);
-        run_threads(To, [&](int t) {
-            for (int64_t e = ctx->nnz * t / To; e < ctx->nnz * (t + 1) / To; ++e)
-                if (ctx->h_pham_part[ctx->h_pham_id[e]] == my_part)
-                    for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g) owned[g] = 1;
+        const int T = host_threads(ctx->nnz);
+        std::vector<SeqPart> part(T);
+        auto elo_of = [&](int t) { return ctx->nnz * t / T; };
+        ctx->h_gene_len_dev.resize((size_t)n_genes);       // every element is written below
+        ctx->h_raw_off.resize((size_t)n_genes + 1);
+        run_threads(T, [&](int t) {
+            SeqPart &me = part[t];
+            for (int64_t e = elo_of(t); e < elo_of(t + 1); ++e) {
+                const bool own = ctx->h_pham_part[ctx->h_pham_id[e]] == my_part;
+                int64_t sum = 0;
+                for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g) {
+                    const int64_t len = checked_len(g, me);
+                    if (len < 0) return;
+                    gene_len[g] = (int32_t)len;
+                    sum += len;
+                    if (!own) continue;
+                    me.max_len = std::max(me.max_len, (int32_t)len);
+                    me.padded += (len + 15) / 16 * 16;
+                    me.raw += len;
+                }
+                // the table's len_sum must describe these genes (metrics.py:136-147 sums them)
+                if (sum != (int64_t)ctx->h_len_sum[e] && me.sum_err_at == INT64_MAX) len_sum_error(e, sum, me);
+            }
         });
+        dbg_mark("seqs: lengths");
+        if (const std::string *msg = first_error(part)) return pc_fail(ctx, PC_EINVAL, "%s", msg->c_str());
+        std::vector<int64_t> base(T + 1, 0), raw_base(T + 1, 0);
+        int32_t max_len = 0;
+        for (int t = 0; t < T; ++t) {
+            base[t + 1] = base[t] + part[t].padded;
+            raw_base[t + 1] = raw_base[t] + part[t].raw;
+            max_len = std::max(max_len, part[t].max_len);
+        }
+        cursor = base[T];
+        ctx->max_gene_len = max_len;
+        const size_t need = (size_t)raw_base[T] + 16;
+        if (ctx->h_stage_cap < need) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr;
+            ctx->h_stage_cap = 0;
+            const size_t cap = need + need / 4;
+            if (cudaHostAlloc(&ctx->h_stage, cap, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return pc_fail(ctx, PC_ENOMEM, "no page-locked staging for %zu residue bytes", cap);
+            }
+            ctx->h_stage_cap = cap;
+        }
+        run_threads(T, [&](int t) {
+            int64_t at = base[t], raw_at = raw_base[t];
+            uint8_t *stage = (uint8_t *)ctx->h_stage;
+            const int64_t e_end = elo_of(t + 1);
+            constexpr int64_t AHEAD = 12;                  // entries; one in n_parts is owned
+            for (int64_t e = elo_of(t); e < e_end; ++e) {
+                // the owned genes sit ~n_parts genes apart in the caller's arena: every copy would
+                // start with a cache miss, so ask for the lines of an owned entry a few entries early
+                if (e + AHEAD < e_end && ctx->h_pham_part[ctx->h_pham_id[e + AHEAD]] == my_part) {
+                    const uint8_t *src = residues + seq_off[ctx->h_entry_first_gene[e + AHEAD]];
+                    for (int64_t o = 0; o < (int64_t)ctx->h_len_sum[e + AHEAD]; o += 64) __builtin_prefetch(src + o, 0, 0);
+                }
+                const bool own = ctx->h_pham_part[ctx->h_pham_id[e]] == my_part;
+                for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g) {
+                    gene_off[g] = at;
+                    ctx->h_raw_off[g] = raw_at;
+                    if (!own) {
+                        ctx->h_gene_len_dev[g] = 0;
+                        continue;
+                    }
+                    const int32_t len = gene_len[g];
+                    ctx->h_gene_len_dev[g] = len;
+                    memcpy(stage + raw_at, residues + seq_off[g], (size_t)len);
+                    raw_at += len;
+                    at += ((int64_t)len + 15) / 16 * 16;
+                }
+            }
+        });
+        gene_off[n_genes] = cursor;
+        ctx->h_raw_off[n_genes] = raw_base[T];
+        dbg_mark("seqs: offsets + staging");
+        PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+        PC_TRY(upload(ctx, ctx->d_raw, (const uint8_t *)ctx->h_stage, (size_t)raw_base[T]));
+        PC_TRY(upload(ctx, ctx->d_raw_off, ctx->h_raw_off.data(), (size_t)n_genes + 1));
+        PC_TRY(pc_stage_end(ctx));
     } else {
         // the residues go first: the copy runs while the host validates the offsets
         PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
         PC_TRY(upload(ctx, ctx->d_raw, residues, (size_t)total));
         PC_TRY(upload(ctx, ctx->d_raw_off, seq_off, (size_t)n_genes + 1));
         PC_TRY(pc_stage_end(ctx));
-    }
-
-    // gene lengths and their 16 B aligned offsets in the code arena, on a few host threads
-    std::vector<int32_t> &gene_len = ctx->h_gene_len;
-    std::vector<int64_t> &gene_off = ctx->h_gene_off;
-    ctx->have_seqs = false;
-    gene_len.resize(n_genes);
-    gene_off.resize(n_genes + 1);
-    const int T = host_threads(n_genes);
-    struct SeqPart {
-        int64_t padded = 0, err_at = INT64_MAX, raw = 0;
-        int32_t max_len = 0;
-        std::string err;
-    };
-    std::vector<SeqPart> part(T);
-    auto lo_of = [&](int t) { return n_genes * t / T; };
-    run_threads(T, [&](int t) {
-        SeqPart &me = part[t];
-        for (int64_t g = lo_of(t); g < lo_of(t + 1); ++g) {
-            const int64_t len = seq_off[g + 1] - seq_off[g];
-            char buf[200];
-            if (len < 0) {
-                snprintf(buf, sizeof buf, "seq_off is not monotone at gene %lld", (long long)g);
-                me.err_at = g; me.err = buf;
-                return;
+        // gene lengths and their 16 B aligned offsets in the code arena, on a few host threads
+        const int T = host_threads(n_genes);
+        std::vector<SeqPart> part(T);
+        auto lo_of = [&](int t) { return n_genes * t / T; };
+        auto elo_of = [&](int t) { return ctx->nnz * t / T; };
+        run_threads(T, [&](int t) {
+            SeqPart &me = part[t];
+            for (int64_t g = lo_of(t); g < lo_of(t + 1); ++g) {
+                const int64_t len = checked_len(g, me);
+                if (len < 0) return;
+                gene_len[g] = (int32_t)len;
+                me.max_len = std::max(me.max_len, (int32_t)len);
+                me.padded += (len + 15) / 16 * 16;
             }
-            if (len > 32767) {
-                snprintf(buf, sizeof buf,
-                         "gene %lld has %lld residues; the alignment counters hold at most 32767 "
-                         "(parasail's 16-bit scores are undefined there anyway)", (long long)g, (long long)len);
-                me.err_at = g; me.err = buf;
-                return;
-            }
-            gene_len[g] = (int32_t)len;
-            if (partial && !owned[g]) continue;
-            me.max_len = std::max(me.max_len, (int32_t)len);
-            me.padded += (len + 15) / 16 * 16;
-            me.raw += len;
+        });
+        dbg_mark("seqs: lengths");
+        if (const std::string *msg = first_error(part)) {
+            cudaStreamSynchronize(ctx->stream);        // the uploads read the caller's buffers
+            return pc_fail(ctx, PC_EINVAL, "%s", msg->c_str());
         }
-    });
-    int64_t cursor = 0;
-    {
-        const SeqPart *bad = nullptr;
         std::vector<int64_t> base(T + 1, 0);
         int32_t max_len = 0;
         for (int t = 0; t < T; ++t) {
-            if (part[t].err_at != INT64_MAX && (!bad || part[t].err_at < bad->err_at)) bad = &part[t];
             base[t + 1] = base[t] + part[t].padded;
             max_len = std::max(max_len, part[t].max_len);
-        }
-        if (bad) {
-            cudaStreamSynchronize(ctx->stream);        // the uploads read the caller's buffers
-            return pc_fail(ctx, PC_EINVAL, "%s", bad->err.c_str());
         }
         cursor = base[T];
         ctx->max_gene_len = max_len;
         // second pass: arena offsets; and the table's len_sum must describe these genes
         // (metrics.py:136-147 sums them)
-        std::vector<SeqPart> chk(T);
-        auto elo_of = [&](int t) { return ctx->nnz * t / T; };
-        // partial loads: the owned residues are gathered into page-locked staging (1 / n_parts of
-        // the arena), the device sees length 0 for every other gene
-        std::vector<int64_t> raw_base(T + 1, 0);
-        for (int t = 0; t < T; ++t) raw_base[t + 1] = raw_base[t] + part[t].raw;
-        if (partial) {
-            const size_t need = (size_t)raw_base[T] + 16;
-            if (ctx->h_stage_cap < need) {
-                if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-                ctx->h_stage = nullptr;
-                ctx->h_stage_cap = 0;
-                const size_t cap = need + need / 4;
-                if (cudaHostAlloc(&ctx->h_stage, cap, cudaHostAllocDefault) != cudaSuccess) {
-                    cudaGetLastError();
-                    return pc_fail(ctx, PC_ENOMEM, "no page-locked staging for %zu residue bytes", cap);
-                }
-                ctx->h_stage_cap = cap;
-            }
-            ctx->h_gene_len_dev.assign((size_t)n_genes, 0);
-            ctx->h_raw_off.assign((size_t)n_genes + 1, 0);
-        }
         run_threads(T, [&](int t) {
-            int64_t at = base[t], raw_at = raw_base[t];
+            int64_t at = base[t];
             for (int64_t g = lo_of(t); g < lo_of(t + 1); ++g) {
                 gene_off[g] = at;
-                if (partial) {
-                    ctx->h_raw_off[g] = raw_at;
-                    if (!owned[g]) continue;
-                    ctx->h_gene_len_dev[g] = gene_len[g];
-                    memcpy((uint8_t *)ctx->h_stage + raw_at, residues + seq_off[g], (size_t)gene_len[g]);
-                    raw_at += gene_len[g];
-                }
                 at += ((int64_t)gene_len[g] + 15) / 16 * 16;
             }
             for (int64_t e = elo_of(t); e < elo_of(t + 1); ++e) {
@@ -738,28 +802,16 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
                 for (int64_t g = ctx->h_entry_first_gene[e]; g < ctx->h_entry_first_gene[e + 1]; ++g)
                     sum += gene_len[g];
                 if (sum != (int64_t)ctx->h_len_sum[e]) {
-                    char buf[160];
-                    snprintf(buf, sizeof buf, "len_sum[%lld]=%u but its genes sum to %lld", (long long)e,
-                             ctx->h_len_sum[e], (long long)sum);
-                    chk[t].err_at = e; chk[t].err = buf;
+                    len_sum_error(e, sum, part[t]);
                     return;
                 }
             }
         });
         gene_off[n_genes] = cursor;
-        dbg_mark("seqs: offsets + staging");
-        for (int t = 0; t < T; ++t)
-            if (chk[t].err_at != INT64_MAX && (!bad || chk[t].err_at < bad->err_at)) bad = &chk[t];
-        if (bad) {
+        dbg_mark("seqs: offsets");
+        if (const std::string *msg = first_error(part)) {
             cudaStreamSynchronize(ctx->stream);
-            return pc_fail(ctx, PC_EINVAL, "%s", bad->err.c_str());
-        }
-        if (partial) {
-            ctx->h_raw_off[n_genes] = raw_base[T];
-            PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
-            PC_TRY(upload(ctx, ctx->d_raw, (const uint8_t *)ctx->h_stage, (size_t)raw_base[T]));
-            PC_TRY(upload(ctx, ctx->d_raw_off, ctx->h_raw_off.data(), (size_t)n_genes + 1));
-            PC_TRY(pc_stage_end(ctx));
+            return pc_fail(ctx, PC_EINVAL, "%s", msg->c_str());
         }
     }
     const int64_t raw_total = partial ? ctx->h_raw_off[n_genes] : total;
@@ -995,95 +1047,79 @@ static int contract_rows(pc_ctx *ctx, int metric, int as_distance, int raw, int6
 // ---------------------------------------------------------------------------
 // alignment planning (host) -- which member pairs exist, in which order
 // ---------------------------------------------------------------------------
-// CSC member lists (entries grouped by pham, ascending genome order) by a stable counting sort
-// over T entry ranges; built on demand, dropped by pc_load_table.
-static void ensure_pham_members(pc_ctx *ctx)
+// ascending LSD radix sort of 64-bit keys, bytes that are the same in every key skipped
+static void radix_sort_u64(std::vector<uint64_t> &keys)
 {
-    if (ctx->h_pham_members.size() == (size_t)ctx->nnz) return;
+    if (keys.size() < 2) return;
+    uint64_t all_or = 0, all_and = ~0ull;
+    for (const uint64_t k : keys) { all_or |= k; all_and &= k; }
+    const uint64_t varying = all_or ^ all_and;
+    std::vector<uint64_t> tmp(keys.size());
+    for (int byte = 0; byte < 8; ++byte) {
+        if (((varying >> (8 * byte)) & 0xff) == 0) continue;
+        size_t hist[257] = {0};
+        for (const uint64_t k : keys) hist[((k >> (8 * byte)) & 0xff) + 1]++;
+        for (int d = 0; d < 256; ++d) hist[d + 1] += hist[d];
+        for (const uint64_t k : keys) tmp[hist[(k >> (8 * byte)) & 0xff]++] = k;
+        keys.swap(tmp);
+    }
+}
+
+// Which partition aligns which pham: phams held by >= 2 genomes in descending cost order
+// (LPT; cost ~ (summed translation length of the members)^2, i.e. ordered by that sum; ties: lower
+// pham first), dealt in snake order (0..n-1, n-1..0, ...) -- plain round-robin would hand
+// partition 0 the largest pham of every lap.  A function of the TABLE only, so
+// pc_load_sequences_part can decide which genes a rank needs before any plan exists.  One pass
+// over the entries for the sums (no member lists), one radix sort.  ctx->h_deal_order: the phams
+// in deal order; ctx->h_pham_part[p]: owner of pham p or -1.
+static void deal_phams(pc_ctx *ctx, int n_parts)
+{
+    if (ctx->deal_parts == n_parts && ctx->h_pham_part.size() == (size_t)std::max<int64_t>(ctx->P, 1)) return;
     const int T = host_threads(ctx->nnz);
     const int64_t P = ctx->P;
     auto entries_of = [&](int t) { return ctx->nnz * t / T; };
     auto phams_of = [&](int t) { return P * t / T; };
-    // cnt[t][p] = entries of pham p in range t, then their rank offset
-    ctx->h_pham_members.resize(ctx->nnz);
-    std::vector<std::vector<int32_t>> cnt(T);
+    std::vector<std::vector<uint64_t>> tot(T);
     run_threads(T, [&](int t) {
-        cnt[t].assign(P, 0);
-        for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) cnt[t][ctx->h_pham_id[k]]++;
+        tot[t].assign((size_t)P, 0);
+        for (int64_t e = entries_of(t); e < entries_of(t + 1); ++e) tot[t][ctx->h_pham_id[e]] += ctx->h_len_sum[e];
     });
+    constexpr uint64_t TOT_MAX = (1ull << 40) - 1;
+    std::vector<std::vector<uint64_t>> local(T);
+    std::vector<char> wide(T, 0);
     run_threads(T, [&](int t) {
         for (int64_t p = phams_of(t); p < phams_of(t + 1); ++p) {
-            int32_t run = 0;
-            for (int u = 0; u < T; ++u) {
-                const int32_t c = cnt[u][p];
-                cnt[u][p] = run;
-                run += c;
-            }
+            uint64_t sum = 0;
+            for (int u = 0; u < T; ++u) sum += tot[u][p];
+            tot[0][p] = sum;
+            if (ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p] < 2) continue;   // cannot be shared by two genomes
+            if (sum > TOT_MAX) wide[t] = 1;
+            local[t].push_back(((TOT_MAX - std::min(sum, TOT_MAX)) << 24) | (uint64_t)(p & 0xffffff));
         }
     });
-    run_threads(T, [&](int t) {
-        for (int64_t k = entries_of(t); k < entries_of(t + 1); ++k) {
-            const int32_t p = ctx->h_pham_id[k];
-            ctx->h_pham_members[ctx->h_pham_ptr[p] + cnt[t][p]++] = k;
-        }
-    });
-}
-
-// Which partition aligns which pham: phams held by >= 2 genomes in descending cost order
-// (LPT; cost ~ (summed translation length of the members)^2), dealt in snake order
-// (0..n-1, n-1..0, ...) -- plain round-robin would hand partition 0 the largest pham of every
-// lap.  A function of the TABLE only, so pc_load_sequences_part can decide which genes a rank
-// needs before any plan exists.  ctx->h_deal_order: the phams in deal order; ctx->h_pham_part[p]:
-// owner of pham p or -1.
-static void deal_phams(pc_ctx *ctx, int n_parts)
-{
-    if (ctx->deal_parts == n_parts && ctx->h_pham_part.size() == (size_t)std::max<int64_t>(ctx->P, 1)) return;
-    ensure_pham_members(ctx);
-    const int T = host_threads(ctx->nnz);
-    const int64_t P = ctx->P;
-    auto phams_of = [&](int t) { return P * t / T; };
-    struct PhamInfo { int64_t pham; double cost; };
-    std::vector<PhamInfo> infos;
-    {
-        std::vector<std::vector<PhamInfo>> local(T);
-        run_threads(T, [&](int t) {
-            for (int64_t p = phams_of(t); p < phams_of(t + 1); ++p) {
-                const int64_t b = ctx->h_pham_ptr[p], e = ctx->h_pham_ptr[p + 1];
-                if (e - b < 2) continue;              // cannot be shared by two genomes
-                double tot = 0;
-                for (int64_t k = b; k < e; ++k) tot += ctx->h_len_sum[ctx->h_pham_members[k]];
-                local[t].push_back({p, tot * tot});   // ~ sum of len_a * len_b over its member pairs
-            }
-        });
-        size_t n = 0;
-        for (auto &v : local) n += v.size();
-        infos.reserve(n);
-        for (auto &v : local) infos.insert(infos.end(), v.begin(), v.end());
-    }
-    auto by_cost = [](const PhamInfo &x, const PhamInfo &y) {
-        if (x.cost != y.cost) return x.cost > y.cost;
-        return x.pham < y.pham;
-    };
-    {
-        // chunk sort + pairwise merges (the order is total, so the result does not depend on T)
-        const int chunks = infos.size() < 20000 ? 1 : T;
-        auto cut = [&](int c) { return infos.size() * (size_t)c / (size_t)chunks; };
-        run_threads(chunks, [&](int c) { std::sort(infos.begin() + cut(c), infos.begin() + cut(c + 1), by_cost); });
-        for (int width = 1; width < chunks; width *= 2) {
-            const int pairs = (chunks + 2 * width - 1) / (2 * width);
-            run_threads(pairs, [&](int q) {
-                const int lo = q * 2 * width, mid = std::min(lo + width, chunks), hi = std::min(lo + 2 * width, chunks);
-                if (mid < hi)
-                    std::inplace_merge(infos.begin() + cut(lo), infos.begin() + cut(mid), infos.begin() + cut(hi), by_cost);
-            });
-        }
-    }
+    size_t n = 0;
+    bool packed = P < (1ll << 24);
+    for (int t = 0; t < T; ++t) { n += local[t].size(); packed = packed && !wide[t]; }
     ctx->h_pham_part.assign(std::max<int64_t>(P, 1), -1);
-    ctx->h_deal_order.resize(infos.size());
-    for (size_t pos = 0; pos < infos.size(); ++pos) {
+    ctx->h_deal_order.resize(n);
+    if (packed) {
+        std::vector<uint64_t> keys;
+        keys.reserve(n);
+        for (auto &v : local) keys.insert(keys.end(), v.begin(), v.end());
+        radix_sort_u64(keys);                  // (TOT_MAX - sum, pham) ascending = sum descending, pham ascending
+        for (size_t pos = 0; pos < n; ++pos) ctx->h_deal_order[pos] = (int64_t)(keys[pos] & 0xffffff);
+    } else {                                   // more than 16 M phams or sums beyond 40 bits: comparison sort
+        size_t pos = 0;
+        for (int64_t p = 0; p < P; ++p)
+            if (ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p] >= 2) ctx->h_deal_order[pos++] = p;
+        const std::vector<uint64_t> &sum = tot[0];
+        std::sort(ctx->h_deal_order.begin(), ctx->h_deal_order.end(), [&](int64_t x, int64_t y) {
+            return sum[x] != sum[y] ? sum[x] > sum[y] : x < y;
+        });
+    }
+    for (size_t pos = 0; pos < n; ++pos) {
         const size_t lap = pos / (size_t)n_parts, in_lap = pos % (size_t)n_parts;
-        ctx->h_deal_order[pos] = infos[pos].pham;
-        ctx->h_pham_part[infos[pos].pham] = (int32_t)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap);
+        ctx->h_pham_part[ctx->h_deal_order[pos]] = (int32_t)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap);
     }
     ctx->deal_parts = n_parts;
 }
@@ -1109,18 +1145,47 @@ static int build_plan(pc_ctx *ctx, int part, int n_parts)
         ph_unit_off[x + 1] = ph_unit_off[x] + m * (m - 1) / 2;
     }
     std::vector<int32_t> mem_genome(ph_mem_off.back()), mem_first_gene(ph_mem_off.back()), mem_copies(ph_mem_off.back());
+    // member lists of THIS partition's phams (ascending genome order) by a stable counting sort
+    // over T entry ranges -- the other partitions' entries are only looked at
+    const size_t nm = mine.size();
+    std::vector<int32_t> slot_of((size_t)std::max<int64_t>(ctx->P, 1), -1);
+    for (size_t x = 0; x < nm; ++x) slot_of[mine[x]] = (int32_t)x;
+    auto entries_of = [&](int t) { return ctx->nnz * t / T; };
+    std::vector<std::vector<int32_t>> cnt(T);
+    run_threads(T, [&](int t) {
+        cnt[t].assign(nm, 0);
+        for (int64_t e = entries_of(t); e < entries_of(t + 1); ++e) {
+            const int32_t x = slot_of[ctx->h_pham_id[e]];
+            if (x >= 0) cnt[t][x]++;
+        }
+    });
     std::vector<int64_t> tasks_of(T, 0);
     run_threads(T, [&](int t) {
+        for (size_t x = nm * (size_t)t / (size_t)T; x < nm * (size_t)(t + 1) / (size_t)T; ++x) {
+            int32_t run = 0;
+            for (int u = 0; u < T; ++u) {
+                const int32_t c = cnt[u][x];
+                cnt[u][x] = run;
+                run += c;
+            }
+        }
+    });
+    run_threads(T, [&](int t) {
+        for (int64_t e = entries_of(t); e < entries_of(t + 1); ++e) {
+            const int32_t x = slot_of[ctx->h_pham_id[e]];
+            if (x < 0) continue;
+            const int64_t at = ph_mem_off[x] + cnt[t][x]++;
+            mem_genome[at] = ctx->h_entry_genome[e];
+            mem_first_gene[at] = (int32_t)ctx->h_entry_first_gene[e];
+            mem_copies[at] = (int32_t)ctx->h_copies[e];
+        }
+    });
+    run_threads(T, [&](int t) {
         int64_t tasks = 0;
-        for (size_t x = mine.size() * (size_t)t / (size_t)T; x < mine.size() * (size_t)(t + 1) / (size_t)T; ++x) {
-            const int64_t b = ctx->h_pham_ptr[mine[x]], e = ctx->h_pham_ptr[mine[x] + 1];
-            int64_t sum_c = 0, sum_c2 = 0, at = ph_mem_off[x];
-            for (int64_t k = b; k < e; ++k, ++at) {
-                const int64_t ent = ctx->h_pham_members[k];
-                const int64_t c = ctx->h_copies[ent];
-                mem_genome[at] = ctx->h_entry_genome[ent];
-                mem_first_gene[at] = (int32_t)ctx->h_entry_first_gene[ent];
-                mem_copies[at] = (int32_t)c;
+        for (size_t x = nm * (size_t)t / (size_t)T; x < nm * (size_t)(t + 1) / (size_t)T; ++x) {
+            int64_t sum_c = 0, sum_c2 = 0;
+            for (int64_t at = ph_mem_off[x]; at < ph_mem_off[x + 1]; ++at) {
+                const int64_t c = mem_copies[at];
                 sum_c += c;
                 sum_c2 += c * c;
             }

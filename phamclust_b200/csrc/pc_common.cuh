@@ -168,7 +168,6 @@ struct pc_ctx {
     std::vector<int32_t> h_den[3], h_pham_col;
     std::vector<std::vector<int32_t>> h_stamp;   // per host thread: epoch + genome that last listed the pham
     int32_t stamp_epoch = 0;
-    std::vector<int64_t> h_pham_members;  // entry ids grouped by pham, genome ascending
     std::vector<int32_t> h_pham_part;     // pham -> partition that aligns it (-1: held by < 2 genomes)
     std::vector<int64_t> h_deal_order;    // phams held by >= 2 genomes, descending cost
     int deal_parts = -1;                  // n_parts the deal above was made for
