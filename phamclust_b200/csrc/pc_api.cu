@@ -1065,13 +1065,15 @@ static void radix_sort_u64(std::vector<uint64_t> &keys)
     }
 }
 
-// Which partition aligns which pham: phams held by >= 2 genomes in descending cost order
-// (LPT; cost ~ (summed translation length of the members)^2, i.e. ordered by that sum; ties: lower
-// pham first), dealt in snake order (0..n-1, n-1..0, ...) -- plain round-robin would hand
-// partition 0 the largest pham of every lap.  A function of the TABLE only, so
-// pc_load_sequences_part can decide which genes a rank needs before any plan exists.  One pass
-// over the entries for the sums (no member lists), one radix sort.  ctx->h_deal_order: the phams
-// in deal order; ctx->h_pham_part[p]: owner of pham p or -1.
+// Which partition aligns which pham.  The DP cells of a pham are the sum over its member pairs of
+// len_a x len_b = (S^2 - Q) / 2 with S, Q the sum and the sum of squares of the members' summed
+// translation lengths -- one pass over the entries, no member lists.  Phams held by >= 2 genomes
+// are taken in descending order of S (ties: lower pham first; one radix sort) and each goes to the
+// partition with the least cells so far (greedy LPT; r2 first dealt them in snake order of S^2,
+// which overrates small phams up to 2x and left the ranks 10 % apart on C2).  A function of the
+// TABLE only -- every rank computes the same deal, and pc_load_sequences_part can decide which
+// genes a rank needs before any plan exists.  ctx->h_deal_order: the phams in deal order;
+// ctx->h_pham_part[p]: owner of pham p or -1.
 static void deal_phams(pc_ctx *ctx, int n_parts)
 {
     if (ctx->deal_parts == n_parts && ctx->h_pham_part.size() == (size_t)std::max<int64_t>(ctx->P, 1)) return;
@@ -1079,19 +1081,25 @@ static void deal_phams(pc_ctx *ctx, int n_parts)
     const int64_t P = ctx->P;
     auto entries_of = [&](int t) { return ctx->nnz * t / T; };
     auto phams_of = [&](int t) { return P * t / T; };
-    std::vector<std::vector<uint64_t>> tot(T);
+    std::vector<std::vector<uint64_t>> tot(T), sq(T);
     run_threads(T, [&](int t) {
         tot[t].assign((size_t)P, 0);
-        for (int64_t e = entries_of(t); e < entries_of(t + 1); ++e) tot[t][ctx->h_pham_id[e]] += ctx->h_len_sum[e];
+        sq[t].assign((size_t)P, 0);
+        for (int64_t e = entries_of(t); e < entries_of(t + 1); ++e) {
+            const uint64_t len = ctx->h_len_sum[e];
+            tot[t][ctx->h_pham_id[e]] += len;
+            sq[t][ctx->h_pham_id[e]] += len * len;
+        }
     });
     constexpr uint64_t TOT_MAX = (1ull << 40) - 1;
     std::vector<std::vector<uint64_t>> local(T);
     std::vector<char> wide(T, 0);
     run_threads(T, [&](int t) {
         for (int64_t p = phams_of(t); p < phams_of(t + 1); ++p) {
-            uint64_t sum = 0;
-            for (int u = 0; u < T; ++u) sum += tot[u][p];
+            uint64_t sum = 0, sum_sq = 0;
+            for (int u = 0; u < T; ++u) { sum += tot[u][p]; sum_sq += sq[u][p]; }
             tot[0][p] = sum;
+            sq[0][p] = sum_sq;
             if (ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p] < 2) continue;   // cannot be shared by two genomes
             if (sum > TOT_MAX) wide[t] = 1;
             local[t].push_back(((TOT_MAX - std::min(sum, TOT_MAX)) << 24) | (uint64_t)(p & 0xffffff));
@@ -1117,9 +1125,17 @@ static void deal_phams(pc_ctx *ctx, int n_parts)
             return sum[x] != sum[y] ? sum[x] > sum[y] : x < y;
         });
     }
+    std::vector<double> load((size_t)n_parts, 0.0);
     for (size_t pos = 0; pos < n; ++pos) {
-        const size_t lap = pos / (size_t)n_parts, in_lap = pos % (size_t)n_parts;
-        ctx->h_pham_part[ctx->h_deal_order[pos]] = (int32_t)((lap & 1) ? (size_t)n_parts - 1 - in_lap : in_lap);
+        const int64_t p = ctx->h_deal_order[pos];
+        int best = 0;
+        for (int k = 1; k < n_parts; ++k)
+            if (load[k] < load[best]) best = k;
+        const double s1 = (double)tot[0][p], s2 = (double)sq[0][p];
+        // + one row-step's worth per member pair: short alignments are not free
+        const double members = (double)(ctx->h_pham_ptr[p + 1] - ctx->h_pham_ptr[p]);
+        load[best] += 0.5 * (s1 * s1 - s2) + 2000.0 * 0.5 * members * (members - 1.0);
+        ctx->h_pham_part[p] = (int32_t)best;
     }
     ctx->deal_parts = n_parts;
 }
