@@ -468,13 +468,15 @@ def measure(env, workload, metric, genomes, phams, steps, warmup, engine=None, a
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         if rank == 0:
             assert int(shared.array.sum(dtype=np.int64)) == checksum, "e2e and resident results differ"
-        table_bytes = int(sum(a.nbytes for a in (table.genome_ptr, table.pham_id, table.copies, table.len_sum)))
-        seq_bytes = int(table.residues.nbytes) if need_seqs else 0
+        # what the ranks actually handed to their H2D copies (counted inside the library)
+        shipped = torch.tensor([ctx.stats()["h2d_bytes"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(shipped, op=dist.ReduceOp.SUM)
         e2e = {"value": pairs / float(worst.item()), "unit": "pairs/s",
-               "h2d_bytes_per_step": table_bytes * world + seq_bytes + (int(table.seq_off.nbytes) * world if need_seqs else 0),
+               "h2d_bytes_per_step": int(shipped.item()) // max(steps, 1),
                "d2h_bytes_per_step": int(tri * 4), "ms_per_step": 1e3 * float(worst.item()),
                "stage_ms_per_step_rank0": {k: v / max(steps, 1) for k, v in ctx.timings().items()},
-               "api": "per rank: pc_load_table + pc_load_sequences_part (its phams' genes only) + "
+               "api": "per rank: pc_load_table + pc_load_sequences_part (its phams' genes: gathered on the host at 8+ ranks, "
+                      "the whole page-locked arena shipped and filtered on the device below that) + "
                       "pc_align_contributions + NCCL all-to-all of the records + pc_accumulate_records + "
                       "pc_matrix_rows_owned into the node's shared page-locked host triangle "
                       "(distributed.SharedTriangle), every GPU over its own PCIe link"}

@@ -297,7 +297,8 @@ enum {
     PC_STAT_I8_TILE_STEPS_DENSE = 9,/* ... and what a dense K schedule would have issued          */
     PC_STAT_LEXR_CELLS = 10,        /* DP cells run by the rebased LEX kernel (10-bit counters)   */
     PC_STAT_LEXC_CELLS = 11,        /* DP cells run by the LEXC kernel (rebased counters, chunks)  */
-    PC_STAT_LEXC_FALLBACKS = 12     /* alignments LEXC handed to the classic kernel (band check)  */
+    PC_STAT_LEXC_FALLBACKS = 12,    /* alignments LEXC handed to the classic kernel (band check)  */
+    PC_STAT_H2D_BYTES = 13          /* bytes of the table / sequence loads shipped host -> device  */
 };
 int pc_stat(pc_ctx *ctx, int which, int64_t *out);
 

@@ -348,7 +348,7 @@ class Context:
         out = {}
         for which, key in enumerate(("logical_alignments", "unique_genes", "operand_columns", "genes",
                                      "lex_alignments", "lex_cells", "dp_configs_used", "dp_configs", "i8_tile_steps",
-                                     "i8_tile_steps_dense", "lexr_cells", "lexc_cells", "lexc_fallbacks")):
+                                     "i8_tile_steps_dense", "lexr_cells", "lexc_cells", "lexc_fallbacks", "h2d_bytes")):
             v = ctypes.c_int64()
             self._check(self._lib.pc_stat(self._h, which, ctypes.byref(v)))
             out[key] = v.value

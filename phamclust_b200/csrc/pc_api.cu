@@ -266,7 +266,19 @@ static int upload(pc_ctx *ctx, DevBuf &b, const T *src, size_t count)
     if (count)
         PC_CUDA(ctx, cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice,
                                      ctx->stream));
+    ctx->h2d_bytes += (int64_t)(count * sizeof(T));
     return PC_OK;
+}
+
+// is this host buffer page-locked (a DMA engine can read it at full PCIe rate, asynchronously)?
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
 }
 
 // host threads for the O(nnz) passes over the caller's table (PC_HOST_THREADS overrides)
@@ -671,6 +683,19 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
         // with every thread's share of the arena and of the staging known -- offsets and the
         // gather of the owned residues into page-locked staging (1 / n_parts of the arena); the
         // device sees length 0 for every other gene.
+        // Gathering costs the host about as much per byte as 7 bytes cost the DMA engine (one cache
+        // miss per gene, ~1.2 GB/s per thread against ~24 GB/s per PCIe link, measured with
+        // tools/probe_partial_load.py): with fewer than 8 partitions and a page-locked caller buffer
+        // it is cheaper to ship the whole arena asynchronously and let the device skip the genes of
+        // other ranks (their length is 0 there) -- every GPU has its own link.  PC_SHIP_ALL=0/1 forces.
+        const int ship_env = getenv("PC_SHIP_ALL") ? atoi(getenv("PC_SHIP_ALL")) : -1;
+        const bool ship_all = total > 0 && (ship_env >= 0 ? ship_env != 0 : (n_parts < 8 && is_pinned(residues)));
+        if (ship_all) {
+            PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+            PC_TRY(upload(ctx, ctx->d_raw, residues, (size_t)total));
+            PC_TRY(upload(ctx, ctx->d_raw_off, seq_off, (size_t)n_genes + 1));
+            PC_TRY(pc_stage_end(ctx));
+        }
         deal_phams(ctx, n_parts);
         dbg_mark("seqs: phams dealt");
         const int T = host_threads(ctx->nnz);
@@ -698,7 +723,10 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
             }
         });
         dbg_mark("seqs: lengths");
-        if (const std::string *msg = first_error(part)) return pc_fail(ctx, PC_EINVAL, "%s", msg->c_str());
+        if (const std::string *msg = first_error(part)) {
+            if (ship_all) cudaStreamSynchronize(ctx->stream);      // the uploads read the caller's buffers
+            return pc_fail(ctx, PC_EINVAL, "%s", msg->c_str());
+        }
         std::vector<int64_t> base(T + 1, 0), raw_base(T + 1, 0);
         int32_t max_len = 0;
         for (int t = 0; t < T; ++t) {
@@ -708,7 +736,7 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
         }
         cursor = base[T];
         ctx->max_gene_len = max_len;
-        const size_t need = (size_t)raw_base[T] + 16;
+        const size_t need = ship_all ? 0 : (size_t)raw_base[T] + 16;
         if (ctx->h_stage_cap < need) {
             if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
             ctx->h_stage = nullptr;
@@ -728,7 +756,7 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
             for (int64_t e = elo_of(t); e < e_end; ++e) {
                 // the owned genes sit ~n_parts genes apart in the caller's arena: every copy would
                 // start with a cache miss, so ask for the lines of an owned entry a few entries early
-                if (e + AHEAD < e_end && ctx->h_pham_part[ctx->h_pham_id[e + AHEAD]] == my_part) {
+                if (!ship_all && e + AHEAD < e_end && ctx->h_pham_part[ctx->h_pham_id[e + AHEAD]] == my_part) {
                     const uint8_t *src = residues + seq_off[ctx->h_entry_first_gene[e + AHEAD]];
                     for (int64_t o = 0; o < (int64_t)ctx->h_len_sum[e + AHEAD]; o += 64) __builtin_prefetch(src + o, 0, 0);
                 }
@@ -742,19 +770,21 @@ static int load_sequences_impl(pc_ctx *ctx, int64_t n_genes, const int64_t *seq_
                     }
                     const int32_t len = gene_len[g];
                     ctx->h_gene_len_dev[g] = len;
-                    memcpy(stage + raw_at, residues + seq_off[g], (size_t)len);
+                    if (!ship_all) memcpy(stage + raw_at, residues + seq_off[g], (size_t)len);
                     raw_at += len;
                     at += ((int64_t)len + 15) / 16 * 16;
                 }
             }
         });
         gene_off[n_genes] = cursor;
-        ctx->h_raw_off[n_genes] = raw_base[T];
+        ctx->h_raw_off[n_genes] = ship_all ? total : raw_base[T];
         dbg_mark("seqs: offsets + staging");
-        PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
-        PC_TRY(upload(ctx, ctx->d_raw, (const uint8_t *)ctx->h_stage, (size_t)raw_base[T]));
-        PC_TRY(upload(ctx, ctx->d_raw_off, ctx->h_raw_off.data(), (size_t)n_genes + 1));
-        PC_TRY(pc_stage_end(ctx));
+        if (!ship_all) {
+            PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
+            PC_TRY(upload(ctx, ctx->d_raw, (const uint8_t *)ctx->h_stage, (size_t)raw_base[T]));
+            PC_TRY(upload(ctx, ctx->d_raw_off, ctx->h_raw_off.data(), (size_t)n_genes + 1));
+            PC_TRY(pc_stage_end(ctx));
+        }
     } else {
         // the residues go first: the copy runs while the host validates the offsets
         PC_TRY(pc_stage_begin(ctx, PC_T_H2D));
@@ -2019,6 +2049,7 @@ extern "C" int pc_stat(pc_ctx *ctx, int which, int64_t *out)
         break;
     }
     case PC_STAT_I8_TILE_STEPS_DENSE: *out = ctx->i8_dense_steps; break;
+    case PC_STAT_H2D_BYTES: *out = ctx->h2d_bytes; break;
     case PC_STAT_DP_CONFIGS_USED: {
         int64_t used = 0;
         for (char c : ctx->cfg_used) used += c;
@@ -2059,6 +2090,7 @@ extern "C" int pc_reset_counters(pc_ctx *ctx)
     ctx->alignments = 0;
     ctx->logical_alignments = 0;
     ctx->lex_alignments = 0;
+    ctx->h2d_bytes = 0;
     std::fill(ctx->cfg_used.begin(), ctx->cfg_used.end(), 0);
     ctx->i8_dense_steps = 0;
     if (ctx->d_i8_steps.p)

@@ -218,6 +218,7 @@ struct pc_ctx {
     // ---- aai work buffers ----
     AlignPlan plan;
     DevBuf d_task_q, d_task_r, d_hitlen, d_score, d_spill, d_counters, d_perm, d_fallback;
+    int64_t h2d_bytes = 0;           // bytes handed to H2D copies since pc_reset_counters (the table / sequence loads)
     bool lexc_off = false;           // LEXC fell back too often on the loaded sequences
     int64_t lexc_last_tasks = 0;     // LEXC alignments of the previous align_tasks call
     DevBuf d_acc;                                  // uint64 accumulators (single-GPU path)

@@ -28,8 +28,11 @@ def _torch():
     return torch
 
 
-@pytest.mark.parametrize("n_parts,metric", [(2, "peq"), (3, "aai"), (5, "peq")])
-def test_partitioned_records_equal_the_dense_path(gpu_ctx, n_parts, metric):
+@pytest.mark.parametrize("n_parts,metric,ship_all", [(2, "peq", "0"), (3, "aai", "1"), (5, "peq", "0"), (2, "peq", "1")])
+def test_partitioned_records_equal_the_dense_path(gpu_ctx, monkeypatch, n_parts, metric, ship_all):
+    # PC_SHIP_ALL: a rank either gathers its genes on the host or ships the whole arena and lets
+    # the device skip the others (what pc_load_sequences_part picks for page-locked buffers below 8 ranks)
+    monkeypatch.setenv("PC_SHIP_ALL", ship_all)
     torch = _torch()
     dev = torch.device("cuda", gpu_ctx.device)
     table = synthetic.phage_table(260, seed=11, genomes_per_cluster=40, pool=90)
