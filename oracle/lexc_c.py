@@ -44,12 +44,12 @@ def choose_k(m, n):
 
 
 def align(q, r, K=None, rebase=REBASE, bits=BITS, band=BAND, ppos=False):
-    """dict(matched, columns, score, flagged, field_dev, frame_dev, broke, score_field) of the model run;
+    """dict(matched, columns, score, flagged, field_dev, frame_dev, broke, score_field, lane_spread) of the model run;
     matched / columns / score are only meaningful when ``flagged`` is False."""
     a, b = q.encode("latin-1"), r.encode("latin-1")
-    out = (ctypes.c_int * 8)()
+    out = (ctypes.c_int * 9)()
     rc = lib().lexc_align(a, len(a), b, len(b), K or choose_k(len(a), len(b)), rebase, bits, band, int(ppos), out)
     if rc:
         raise ValueError("lexc_align: parameters outside the soundness conditions")
-    keys = ("matched", "columns", "score", "flagged", "field_dev", "frame_dev", "broke", "score_field")
+    keys = ("matched", "columns", "score", "flagged", "field_dev", "frame_dev", "broke", "score_field", "lane_spread")
     return dict(zip(keys, out))

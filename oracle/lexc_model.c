@@ -60,7 +60,9 @@ static inline int32_t imax2(int32_t a, int32_t b) { return a > b ? a : b; }
  * out[0] matched, out[1] columns, out[2] score, out[3] flagged, out[4] largest |field - c0| any
  * checked word had (diagnostic), out[5] largest |frame difference| between neighbours, out[6]
  * 1 if an UNCHECKED invariant broke (a field actually left [0, 2^B) -- must never happen while
- * the flag is clear), out[7] largest |score field|.
+ * the flag is clear), out[7] largest |score field|, out[8] largest spread (max - min) of a counter
+ * field over one lane's state at a re-centring: what a band centred on the lane's mid-range instead
+ * of its centre column would have to hold (diagnostic for DESIGN.md "what comes next").
  */
 int lexc_align(const char *q, int m, const char *r, int n, int K, int R, int B, int band,
                int ppos, int *out)
@@ -87,7 +89,7 @@ int lexc_align(const char *q, int m, const char *r, int n, int K, int R, int B, 
     const int32_t EDGE0 = (EXT - OPEN) * U;
     const int32_t NEG0 = EDGE0 + CU - 4 * U;
     const int CAP = G * K;
-    memset(out, 0, 8 * sizeof(int));
+    memset(out, 0, 9 * sizeof(int));
     if (n == 0) {
         out[0] = 0; out[1] = m; out[2] = m == 0 ? 0 : -OPEN - (m - 1) * EXT;
         return 0;
@@ -96,7 +98,7 @@ int lexc_align(const char *q, int m, const char *r, int n, int K, int R, int B, 
     typedef struct { int32_t h, e; uint32_t u; int32_t dm; } spill_t;
     spill_t *spill = (spill_t *)calloc((size_t)m + 2, sizeof(spill_t));
     lane_t *L = (lane_t *)calloc(G, sizeof(lane_t));
-    int dev_max = 0, delta_max = 0, broke = 0, score_max = 0;
+    int dev_max = 0, delta_max = 0, broke = 0, score_max = 0, spread_max = 0;
     int res_word = 0, res_rb = 0, res_dm = 0;
     uint32_t flag = 0;
 
@@ -147,6 +149,21 @@ int lexc_align(const char *q, int m, const char *r, int n, int K, int R, int B, 
                         p->Fp[x] = add32(p->Fp[x], -d);
                         CHECK(p, p->Hp[x]);
                         CHECK(p, p->Fp[x]);
+                    }
+                    if (!p->chk && chunk * CAP + l * K < n) {
+                        int lo_d = CMASK, hi_d = 0, lo_m = CMASK, hi_m = 0;
+                        for (int x = 0; x < K; ++x) {
+                            const int32_t w2[2] = {p->Hp[x], p->Fp[x]};
+                            for (int z = 0; z < 2; ++z) {
+                                const int fd = (w2[z] >> B) & CMASK, fm = w2[z] & CMASK;
+                                if (fd < lo_d) lo_d = fd;
+                                if (fd > hi_d) hi_d = fd;
+                                if (fm < lo_m) lo_m = fm;
+                                if (fm > hi_m) hi_m = fm;
+                            }
+                        }
+                        if (hi_d - lo_d > spread_max) spread_max = hi_d - lo_d;
+                        if (hi_m - lo_m > spread_max) spread_max = hi_m - lo_m;
                     }
                     p->diagH = add32(p->diagH, -d);
                     p->outH = add32(p->outH, -d);
@@ -233,6 +250,7 @@ int lexc_align(const char *q, int m, const char *r, int n, int K, int R, int B, 
     out[5] = delta_max;
     out[6] = broke;
     out[7] = score_max;
+    out[8] = spread_max;
     free(spill);
     free(L);
     return 0;
