@@ -558,3 +558,48 @@ def test_medoid_on_the_packed_triangle_equals_the_reference(reference):
                 assert ours.nodes == theirs.nodes
                 assert ours.medoid == theirs.medoid, (n, tie, is_distance)
                 assert ours.anti_medoid == theirs.anti_medoid, (n, tie, is_distance)
+
+
+def test_tree_order_and_large_submatrices_without_the_reference_limits(reference):
+    """``reorder()`` with no argument takes the leaf order of a single-linkage dendrogram
+    (matrix.py:673-686).  Ours walks the tree with a stack: the order must equal the verbatim
+    reference's (scipy's recursive ``dendrogram``) wherever that one works -- ties included -- and
+    still come out for a chain-shaped tree deeper than the interpreter's recursion limit, where
+    upstream raises RecursionError.  ``extract_submatrix`` of many nodes (row-wise gather, no
+    k(k+1)/2 index arrays) must equal the small-block path entry for entry."""
+    from phamclust_b200._native import tri_len
+    ref_matrix = reference.matrix
+    rng = np.random.default_rng(21)
+    for n, hi in ((2, 1000001), (3, 5), (17, 1000001), (60, 30), (150, 1000001)):
+        names = [f"n{k:03d}" for k in range(n)]
+        vals = np.triu(rng.integers(1, hi, size=(n, n)), 1)
+        vals = vals + vals.T
+        for is_distance in (True, False):
+            ours = SymMatrix(list(names), is_distance=is_distance)
+            theirs = ref_matrix.SymMatrix(list(names), is_distance=is_distance)
+            for i in range(n):
+                for j in range(i, n):
+                    w = ((0 if is_distance else 1000000) if i == j else int(vals[i, j]) % 1000001) / 1e6
+                    ours.set_weight(names[i], names[j], w)
+                    theirs.set_weight(names[i], names[j], w)
+            ours.reorder()
+            theirs.reorder()
+            assert ours.nodes == theirs.nodes, (n, hi, is_distance)
+    # a chain: node k sits k apart from node 0 on a line -> single linkage merges one leaf at a time
+    n = 3000
+    pos = np.cumsum(rng.integers(1, 300, size=n)).astype(np.int64)
+    i, j = np.triu_indices(n)
+    micro = np.minimum(np.abs(pos[i] - pos[j]), 1000000).astype(np.int32)
+    chain = SymMatrix.from_micro([f"c{k:04d}" for k in range(n)], micro, True)
+    chain.reorder()
+    assert sorted(chain.nodes) == sorted(f"c{k:04d}" for k in range(n))
+    # large block == small-block path
+    pick = [f"c{k:04d}" for k in rng.permutation(n)[:700]]
+    big = chain.extract_submatrix(pick)
+    assert big.nodes == pick and big.micro.shape[0] == tri_len(700)
+    for a in range(0, 700, 97):
+        small = chain.extract_submatrix(pick[a:a + 40])
+        for x in range(len(small.nodes)):
+            for y in range(x, len(small.nodes)):
+                assert small.get_weight(small.nodes[x], small.nodes[y]) == big.get_weight(small.nodes[x], small.nodes[y])
+    assert big.get_weight(pick[3], pick[650]) == chain.get_weight(pick[3], pick[650])
