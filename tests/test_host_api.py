@@ -585,14 +585,21 @@ def test_tree_order_and_large_submatrices_without_the_reference_limits(reference
             ours.reorder()
             theirs.reorder()
             assert ours.nodes == theirs.nodes, (n, hi, is_distance)
-    # a chain: node k sits k apart from node 0 on a line -> single linkage merges one leaf at a time
+    # a chain: points on a line with growing gaps -> single linkage adds one leaf per merge, the tree is
+    # 3000 levels deep (scipy's dendrogram, and with it the reference's reorder(), raises RecursionError)
     n = 3000
-    pos = np.cumsum(rng.integers(1, 300, size=n)).astype(np.int64)
+    pos = np.cumsum(np.arange(1, n + 1)).astype(np.int64)
     i, j = np.triu_indices(n)
     micro = np.minimum(np.abs(pos[i] - pos[j]), 1000000).astype(np.int32)
     chain = SymMatrix.from_micro([f"c{k:04d}" for k in range(n)], micro, True)
+    from scipy.cluster.hierarchy import dendrogram, linkage
+    with pytest.raises(RecursionError):
+        dendrogram(linkage(chain.to_ndarray(condensed=True), method="single"), no_plot=True, get_leaves=True,
+                   count_sort="descending")
     chain.reorder()
     assert sorted(chain.nodes) == sorted(f"c{k:04d}" for k in range(n))
+    # the bigger child first at every merge: the growing cluster, then the leaf that joined it
+    assert chain.nodes[2:] == [f"c{k:04d}" for k in range(2, n)] and set(chain.nodes[:2]) == {"c0000", "c0001"}
     # large block == small-block path
     pick = [f"c{k:04d}" for k in rng.permutation(n)[:700]]
     big = chain.extract_submatrix(pick)
